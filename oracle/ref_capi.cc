@@ -1,0 +1,318 @@
+// TEST INFRASTRUCTURE -- not product code. Nothing under randblas_b200/ may link or load this.
+//
+// extern "C" face of the UNMODIFIED reference (header-only RandBLAS, read where it lies under
+// /root/reference) so that Python tests / golden generation / the CPU-baseline leg of bench.py
+// can run the reference's own loops: fill_dense_submat_impl, repeated_fisher_yates, lskge3,
+// lskges, lsksp3, left_spmm ... Only the two un-vendored leaf dependencies (Random123, BLAS++)
+// come from oracle/shims/. Built by oracle/Makefile into oracle/_ref/librb_ref.so.
+//
+// Every function returns 0 on success, 1 if the reference threw RandBLAS::Error (argument
+// validation, exceptions.hh:57-95), 2 for any other exception; message via rbref_last_error().
+
+#include <RandBLAS.hh>
+#include <omp.h>
+#include <cstdint>
+#include <cstring>
+#include <string>
+
+using RandBLAS::RNGState;
+using RandBLAS::DenseDist;
+using RandBLAS::DenseSkOp;
+using RandBLAS::SparseDist;
+using RandBLAS::SparseSkOp;
+using RandBLAS::ScalarDist;
+using RandBLAS::Axis;
+using blas::Layout;
+using blas::Op;
+using RNG = r123::Philox4x32;
+
+static thread_local std::string g_err;
+
+#define RBREF_TRY try {
+#define RBREF_CATCH                                              \
+    } catch (const RandBLAS::Error& e) { g_err = e.what(); return 1; } \
+      catch (const std::exception& e) { g_err = e.what(); return 2; }  \
+      catch (...) { g_err = "unknown exception"; return 2; }           \
+    return 0;
+
+static RNGState<RNG> mk_state(const uint32_t* ctr, const uint32_t* key) {
+    RNGState<RNG> s;
+    for (int i = 0; i < 4; ++i) s.counter.v[i] = ctr[i];
+    for (int i = 0; i < 2; ++i) s.key.v[i] = key[i];
+    return s;
+}
+static void put_ctr(const RNGState<RNG>& s, uint32_t* ctr_out) {
+    if (ctr_out) for (int i = 0; i < 4; ++i) ctr_out[i] = s.counter.v[i];
+}
+static DenseDist mk_dd(int64_t r, int64_t c, char family, char axis) {
+    return DenseDist(r, c, (ScalarDist) family, (Axis) axis);
+}
+static SparseDist mk_sd(int64_t r, int64_t c, int64_t vec_nnz, char axis) {
+    return SparseDist(r, c, vec_nnz, (Axis) axis);
+}
+
+extern "C" {
+
+const char* rbref_last_error(void) { return g_err.c_str(); }
+const char* rbref_blas_config(void) { return scipy_openblas_get_config(); }
+int rbref_set_threads(int n) { omp_set_num_threads(n); scipy_openblas_set_num_threads(n); return 0; }
+int rbref_get_threads(void) { return omp_get_max_threads(); }
+int rbref_get_blas_threads(void) { return scipy_openblas_get_num_threads(); }
+
+int rbref_philox4x32_10(const uint32_t* ctr, const uint32_t* key, uint32_t* out) {
+    RBREF_TRY
+    auto s = mk_state(ctr, key);
+    RNG rng;
+    auto r = rng(s.counter, s.key);
+    for (int i = 0; i < 4; ++i) out[i] = r.v[i];
+    RBREF_CATCH
+}
+
+int rbref_ctr_incr(uint32_t* ctr, uint64_t n) {
+    RBREF_TRY
+    RNG::ctr_type c;
+    for (int i = 0; i < 4; ++i) c.v[i] = ctr[i];
+    c.incr(n);
+    for (int i = 0; i < 4; ++i) ctr[i] = c.v[i];
+    RBREF_CATCH
+}
+
+int rbref_rngstate_from_u64(uint64_t k, uint32_t* ctr, uint32_t* key) {
+    RBREF_TRY
+    RNGState<RNG> s(k);
+    for (int i = 0; i < 4; ++i) ctr[i] = s.counter.v[i];
+    for (int i = 0; i < 2; ++i) key[i] = s.key.v[i];
+    RBREF_CATCH
+}
+
+int rbref_uneg11_f32(const uint32_t* ctr, const uint32_t* key, float* out) {
+    RBREF_TRY
+    auto s = mk_state(ctr, key);
+    RNG rng;
+    auto r = r123ext::uneg11::generate(rng, s.counter, s.key);
+    for (int i = 0; i < 4; ++i) out[i] = r[i];
+    RBREF_CATCH
+}
+
+int rbref_boxmul_f32(const uint32_t* ctr, const uint32_t* key, float* out) {
+    RBREF_TRY
+    auto s = mk_state(ctr, key);
+    RNG rng;
+    auto r = r123ext::boxmul::generate(rng, s.counter, s.key);
+    for (int i = 0; i < 4; ++i) out[i] = r[i];
+    RBREF_CATCH
+}
+
+// info[0]=dim_major info[1]=dim_minor info[2]=natural_layout ('R'/'C')
+int rbref_dense_dist_info(int64_t n_rows, int64_t n_cols, char family, char axis, int64_t* info, double* iso) {
+    RBREF_TRY
+    auto D = mk_dd(n_rows, n_cols, family, axis);
+    info[0] = D.dim_major; info[1] = D.dim_minor; info[2] = (int64_t)(char) D.natural_layout;
+    *iso = D.isometry_scale;
+    RBREF_CATCH
+}
+
+int rbref_dense_next_state(int64_t n_rows, int64_t n_cols, char family, char axis, const uint32_t* ctr,
+                           const uint32_t* key, uint32_t* next_ctr) {
+    RBREF_TRY
+    auto D = mk_dd(n_rows, n_cols, family, axis);
+    DenseSkOp<float, RNG> S(D, mk_state(ctr, key));
+    put_ctr(S.next_state, next_ctr);
+    RBREF_CATCH
+}
+
+// info[0]=dim_major info[1]=dim_minor info[2]=full_nnz
+int rbref_sparse_dist_info(int64_t n_rows, int64_t n_cols, int64_t vec_nnz, char axis, int64_t* info, double* iso) {
+    RBREF_TRY
+    auto D = mk_sd(n_rows, n_cols, vec_nnz, axis);
+    info[0] = D.dim_major; info[1] = D.dim_minor; info[2] = D.full_nnz;
+    *iso = D.isometry_scale;
+    RBREF_CATCH
+}
+
+int rbref_sparse_next_state(int64_t n_rows, int64_t n_cols, int64_t vec_nnz, char axis, const uint32_t* ctr,
+                            const uint32_t* key, uint32_t* next_ctr) {
+    RBREF_TRY
+    auto D = mk_sd(n_rows, n_cols, vec_nnz, axis);
+    SparseSkOp<float, RNG> S(D, mk_state(ctr, key));
+    put_ctr(S.next_state, next_ctr);
+    RBREF_CATCH
+}
+
+} // extern "C"
+
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+static int fill_dense_unpacked_t(char layout, int64_t Dr, int64_t Dc, char family, char axis, int64_t n_rows,
+                                 int64_t n_cols, int64_t ro_s, int64_t co_s, T* buff, const uint32_t* ctr,
+                                 const uint32_t* key, uint32_t* next_ctr) {
+    RBREF_TRY
+    auto D = mk_dd(Dr, Dc, family, axis);
+    auto next = RandBLAS::fill_dense_unpacked((Layout) layout, D, n_rows, n_cols, ro_s, co_s, buff, mk_state(ctr, key));
+    put_ctr(next, next_ctr);
+    RBREF_CATCH
+}
+
+template <typename T, typename sint_t>
+static int fill_sparse_t(int64_t Dr, int64_t Dc, int64_t vec_nnz, char axis, const uint32_t* ctr, const uint32_t* key,
+                         T* vals, sint_t* rows, sint_t* cols, int64_t* nnz, uint32_t* next_ctr) {
+    RBREF_TRY
+    auto D = mk_sd(Dr, Dc, vec_nnz, axis);
+    auto next = RandBLAS::fill_sparse_unpacked_nosub(D, *nnz, vals, rows, cols, mk_state(ctr, key));
+    put_ctr(next, next_ctr);
+    RBREF_CATCH
+}
+
+template <typename sint_t>
+static int rfy_t(int64_t k, int64_t n, int64_t r, sint_t* samples, const uint32_t* ctr, const uint32_t* key,
+                 uint32_t* next_ctr) {
+    RBREF_TRY
+    auto next = RandBLAS::repeated_fisher_yates(k, n, r, samples, mk_state(ctr, key));
+    put_ctr(next, next_ctr);
+    RBREF_CATCH
+}
+
+// dense operator, left/right sketch. prefill != 0 => fill_dense(S) first (exercises the buff != nullptr path)
+template <typename T>
+static int skge_dense_t(int side_left, char layout, char op1, char op2, int64_t d, int64_t n, int64_t m, T alpha,
+                        int64_t Dr, int64_t Dc, char family, char axis, const uint32_t* ctr, const uint32_t* key,
+                        int prefill, int64_t ro_s, int64_t co_s, const T* A, int64_t lda, T beta, T* B, int64_t ldb) {
+    RBREF_TRY
+    DenseSkOp<T, RNG> S(mk_dd(Dr, Dc, family, axis), mk_state(ctr, key));
+    if (prefill) RandBLAS::fill_dense(S);
+    if (side_left) {
+        // (layout, opS, opA, d, n, m, alpha, S, ro_s, co_s, A, lda, beta, B, ldb)   skge.hh:799-821
+        RandBLAS::sketch_general((Layout) layout, (Op) op1, (Op) op2, d, n, m, alpha, S, ro_s, co_s, A, lda, beta, B, ldb);
+    } else {
+        // (layout, opA, opS, m, d, n, alpha, A, lda, S, ro_s, co_s, beta, B, ldb)   skge.hh:947-968
+        // here the caller passes (d, n, m) in the *reference's right-sketch order* (m, d, n)
+        RandBLAS::sketch_general((Layout) layout, (Op) op1, (Op) op2, d, n, m, alpha, A, lda, S, ro_s, co_s, beta, B, ldb);
+    }
+    RBREF_CATCH
+}
+
+template <typename T>
+static int skge_sparse_t(int side_left, char layout, char op1, char op2, int64_t d, int64_t n, int64_t m, T alpha,
+                         int64_t Dr, int64_t Dc, int64_t vec_nnz, char axis, const uint32_t* ctr, const uint32_t* key,
+                         int prefill, int64_t ro_s, int64_t co_s, const T* A, int64_t lda, T beta, T* B, int64_t ldb) {
+    RBREF_TRY
+    SparseSkOp<T, RNG> S(mk_sd(Dr, Dc, vec_nnz, axis), mk_state(ctr, key));
+    if (prefill) RandBLAS::fill_sparse(S);
+    if (side_left) {
+        RandBLAS::sketch_general((Layout) layout, (Op) op1, (Op) op2, d, n, m, alpha, S, ro_s, co_s, A, lda, beta, B, ldb);
+    } else {
+        RandBLAS::sketch_general((Layout) layout, (Op) op1, (Op) op2, d, n, m, alpha, A, lda, S, ro_s, co_s, beta, B, ldb);
+    }
+    RBREF_CATCH
+}
+
+// sparse data times dense operator. fmt: 0 = CSR (idx0=rowptr, idx1=colidxs), 1 = CSC (idx0=rowidxs, idx1=colptr),
+// 2 = COO (idx0=rows, idx1=cols). int64 indices (the reference's default sint_t).
+template <typename T>
+static int sksp_t(int side_left, int fmt, char layout, char op1, char op2, int64_t d, int64_t n, int64_t m, T alpha,
+                  int64_t Dr, int64_t Dc, char family, char axis, const uint32_t* ctr, const uint32_t* key, int prefill,
+                  int64_t ro_s, int64_t co_s, int64_t Ar, int64_t Ac, int64_t nnz, T* vals, int64_t* idx0, int64_t* idx1,
+                  T beta, T* B, int64_t ldb) {
+    RBREF_TRY
+    using namespace RandBLAS::sparse_data;
+    DenseSkOp<T, RNG> S(mk_dd(Dr, Dc, family, axis), mk_state(ctr, key));
+    if (prefill) RandBLAS::fill_dense(S);
+    auto run = [&](auto& Asp) {
+        if (side_left)
+            RandBLAS::sketch_sparse((Layout) layout, (Op) op1, (Op) op2, d, n, m, alpha, S, ro_s, co_s, Asp, beta, B, ldb);
+        else
+            RandBLAS::sketch_sparse((Layout) layout, (Op) op1, (Op) op2, d, n, m, alpha, Asp, S, ro_s, co_s, beta, B, ldb);
+    };
+    if (fmt == 0) { CSRMatrix<T, int64_t> Asp(Ar, Ac, nnz, vals, idx0, idx1); run(Asp); }
+    else if (fmt == 1) { CSCMatrix<T, int64_t> Asp(Ar, Ac, nnz, vals, idx0, idx1); run(Asp); }
+    else { COOMatrix<T, int64_t> Asp(Ar, Ac, nnz, vals, idx0, idx1); run(Asp); }
+    RBREF_CATCH
+}
+
+template <typename T>
+static int skve_dense_t(char opS, int64_t d, int64_t m, T alpha, int64_t Dr, int64_t Dc, char family, char axis,
+                        const uint32_t* ctr, const uint32_t* key, int64_t ro_s, int64_t co_s, const T* x, int64_t incx,
+                        T beta, T* y, int64_t incy) {
+    RBREF_TRY
+    DenseSkOp<T, RNG> S(mk_dd(Dr, Dc, family, axis), mk_state(ctr, key));
+    RandBLAS::sketch_vector((Op) opS, d, m, alpha, S, ro_s, co_s, x, incx, beta, y, incy);
+    RBREF_CATCH
+}
+
+template <typename T>
+static int skve_sparse_t(char opS, int64_t d, int64_t m, T alpha, int64_t Dr, int64_t Dc, int64_t vec_nnz, char axis,
+                         const uint32_t* ctr, const uint32_t* key, int64_t ro_s, int64_t co_s, const T* x, int64_t incx,
+                         T beta, T* y, int64_t incy) {
+    RBREF_TRY
+    SparseSkOp<T, RNG> S(mk_sd(Dr, Dc, vec_nnz, axis), mk_state(ctr, key));
+    RandBLAS::sketch_vector((Op) opS, d, m, alpha, S, ro_s, co_s, x, incx, beta, y, incy);
+    RBREF_CATCH
+}
+
+extern "C" {
+
+#define DEF_FOR_T(T, sfx)                                                                                              \
+    int rbref_fill_dense_unpacked_##sfx(char layout, int64_t Dr, int64_t Dc, char family, char axis, int64_t n_rows,   \
+                                        int64_t n_cols, int64_t ro_s, int64_t co_s, T* buff, const uint32_t* ctr,      \
+                                        const uint32_t* key, uint32_t* next_ctr) {                                     \
+        return fill_dense_unpacked_t<T>(layout, Dr, Dc, family, axis, n_rows, n_cols, ro_s, co_s, buff, ctr, key,      \
+                                        next_ctr);                                                                     \
+    }                                                                                                                  \
+    int rbref_fill_sparse_##sfx##_i32(int64_t Dr, int64_t Dc, int64_t vec_nnz, char axis, const uint32_t* ctr,         \
+                                      const uint32_t* key, T* vals, int32_t* rows, int32_t* cols, int64_t* nnz,        \
+                                      uint32_t* next_ctr) {                                                            \
+        return fill_sparse_t<T, int32_t>(Dr, Dc, vec_nnz, axis, ctr, key, vals, rows, cols, nnz, next_ctr);            \
+    }                                                                                                                  \
+    int rbref_fill_sparse_##sfx##_i64(int64_t Dr, int64_t Dc, int64_t vec_nnz, char axis, const uint32_t* ctr,         \
+                                      const uint32_t* key, T* vals, int64_t* rows, int64_t* cols, int64_t* nnz,        \
+                                      uint32_t* next_ctr) {                                                            \
+        return fill_sparse_t<T, int64_t>(Dr, Dc, vec_nnz, axis, ctr, key, vals, rows, cols, nnz, next_ctr);            \
+    }                                                                                                                  \
+    int rbref_sketch_general_dense_##sfx(int side_left, char layout, char op1, char op2, int64_t d, int64_t n,         \
+                                         int64_t m, T alpha, int64_t Dr, int64_t Dc, char family, char axis,           \
+                                         const uint32_t* ctr, const uint32_t* key, int prefill, int64_t ro_s,          \
+                                         int64_t co_s, const T* A, int64_t lda, T beta, T* B, int64_t ldb) {           \
+        return skge_dense_t<T>(side_left, layout, op1, op2, d, n, m, alpha, Dr, Dc, family, axis, ctr, key, prefill,   \
+                               ro_s, co_s, A, lda, beta, B, ldb);                                                      \
+    }                                                                                                                  \
+    int rbref_sketch_general_sparse_##sfx(int side_left, char layout, char op1, char op2, int64_t d, int64_t n,        \
+                                          int64_t m, T alpha, int64_t Dr, int64_t Dc, int64_t vec_nnz, char axis,      \
+                                          const uint32_t* ctr, const uint32_t* key, int prefill, int64_t ro_s,         \
+                                          int64_t co_s, const T* A, int64_t lda, T beta, T* B, int64_t ldb) {          \
+        return skge_sparse_t<T>(side_left, layout, op1, op2, d, n, m, alpha, Dr, Dc, vec_nnz, axis, ctr, key, prefill, \
+                                ro_s, co_s, A, lda, beta, B, ldb);                                                     \
+    }                                                                                                                  \
+    int rbref_sketch_sparse_##sfx(int side_left, int fmt, char layout, char op1, char op2, int64_t d, int64_t n,       \
+                                  int64_t m, T alpha, int64_t Dr, int64_t Dc, char family, char axis,                  \
+                                  const uint32_t* ctr, const uint32_t* key, int prefill, int64_t ro_s, int64_t co_s,   \
+                                  int64_t Ar, int64_t Ac, int64_t nnz, T* vals, int64_t* idx0, int64_t* idx1, T beta,  \
+                                  T* B, int64_t ldb) {                                                                 \
+        return sksp_t<T>(side_left, fmt, layout, op1, op2, d, n, m, alpha, Dr, Dc, family, axis, ctr, key, prefill,    \
+                         ro_s, co_s, Ar, Ac, nnz, vals, idx0, idx1, beta, B, ldb);                                     \
+    }                                                                                                                  \
+    int rbref_sketch_vector_dense_##sfx(char opS, int64_t d, int64_t m, T alpha, int64_t Dr, int64_t Dc, char family,  \
+                                        char axis, const uint32_t* ctr, const uint32_t* key, int64_t ro_s,             \
+                                        int64_t co_s, const T* x, int64_t incx, T beta, T* y, int64_t incy) {          \
+        return skve_dense_t<T>(opS, d, m, alpha, Dr, Dc, family, axis, ctr, key, ro_s, co_s, x, incx, beta, y, incy);  \
+    }                                                                                                                  \
+    int rbref_sketch_vector_sparse_##sfx(char opS, int64_t d, int64_t m, T alpha, int64_t Dr, int64_t Dc,              \
+                                         int64_t vec_nnz, char axis, const uint32_t* ctr, const uint32_t* key,         \
+                                         int64_t ro_s, int64_t co_s, const T* x, int64_t incx, T beta, T* y,           \
+                                         int64_t incy) {                                                               \
+        return skve_sparse_t<T>(opS, d, m, alpha, Dr, Dc, vec_nnz, axis, ctr, key, ro_s, co_s, x, incx, beta, y,       \
+                                incy);                                                                                 \
+    }
+
+DEF_FOR_T(float, f32)
+DEF_FOR_T(double, f64)
+
+int rbref_repeated_fisher_yates_i32(int64_t k, int64_t n, int64_t r, int32_t* samples, const uint32_t* ctr,
+                                    const uint32_t* key, uint32_t* next_ctr) {
+    return rfy_t<int32_t>(k, n, r, samples, ctr, key, next_ctr);
+}
+int rbref_repeated_fisher_yates_i64(int64_t k, int64_t n, int64_t r, int64_t* samples, const uint32_t* ctr,
+                                    const uint32_t* key, uint32_t* next_ctr) {
+    return rfy_t<int64_t>(k, n, r, samples, ctr, key, next_ctr);
+}
+
+} // extern "C"
