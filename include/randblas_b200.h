@@ -1,0 +1,178 @@
+/* randblas_b200 -- C ABI of the B200-native sketching hot path.
+ *
+ * This is the drop-in boundary: the header-only C++ layer in include/RandBLAS/ (same names and
+ * signatures as the reference's public API) forwards each hot call to exactly one symbol below,
+ * and any other host language can bind the same symbols.
+ *
+ * Conventions
+ *   - plain C types only; sizes are int64_t; enums are chars with BLAS++'s values:
+ *       layout 'C' (ColMajor) / 'R' (RowMajor); op 'N' / 'T';
+ *       family 'G' (Gaussian) / 'U' (Uniform on [-sqrt3, sqrt3]); major_axis 'S' (Short) / 'L' (Long).
+ *   - an RNGState is passed as its two arrays: ctr[4] (128-bit little-endian counter) and key[2]
+ *     (reference: RandBLAS/base.hh:64-164). States are never mutated; functions that advance the
+ *     stream write the advanced counter to next_ctr[4] (may be NULL).
+ *   - data pointers (buff, A, B, vals, rows, cols, ...) may be DEVICE pointers (used in place, the
+ *     measured mode) or HOST pointers (staged through device memory inside the call: this is what
+ *     a caller of the CPU reference has). Both are detected with cudaPointerGetAttributes.
+ *   - every call is ordered on `stream` (a cudaStream_t passed as void*, NULL = default stream).
+ *     Calls with host buffers return after the results are back in host memory; calls with device
+ *     buffers return after enqueueing (synchronise the stream to observe the result).
+ *   - return value: 0 = ok; RB_ERR_ARG = an argument check failed (the reference would have thrown
+ *     RandBLAS::Error before touching data, exceptions.hh:57-95); RB_ERR_CUDA = a CUDA error.
+ *     rb_last_error() returns the thread-local message. No exception crosses this boundary.
+ *   - the library never allocates or frees caller-visible memory. Internal workspace is cached per
+ *     device and released by rb_release_workspace().
+ */
+#ifndef RANDBLAS_B200_H
+#define RANDBLAS_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RB_OK 0
+#define RB_ERR_ARG 1
+#define RB_ERR_CUDA 2
+
+const char* rb_last_error(void);
+int rb_version(void);                 /* 100 * major + minor */
+int rb_release_workspace(void);
+/* info[0] = SM count, info[1] = compute capability * 10 + minor, info[2] = total global memory (bytes) */
+int rb_device_info(int64_t info[3]);
+
+/* ---- RNG state arithmetic (host-side, pure integer; RandBLAS/base.hh:116-119, Random123 array.h incr) ---- */
+void rb_rngstate_from_u64(uint64_t k, uint32_t ctr[4], uint32_t key[2]);
+void rb_ctr_incr(uint32_t ctr[4], uint64_t n);
+/* DenseDist / SparseDist derived fields (RandBLAS/dense_skops.hh:231-350, sparse_skops.hh:131-246).
+ * dense info = {dim_major, dim_minor, natural_layout}; sparse info = {dim_major, dim_minor, full_nnz} */
+int rb_dense_dist_info(int64_t n_rows, int64_t n_cols, char family, char major_axis, int64_t info[3],
+                       double* isometry_scale);
+int rb_sparse_dist_info(int64_t n_rows, int64_t n_cols, int64_t vec_nnz, char major_axis, int64_t info[3],
+                        double* isometry_scale);
+/* next_state of DenseSkOp / SparseSkOp constructors (dense_skops.hh:172-185, sparse_skops.hh:266-283) */
+int rb_dense_next_state(int64_t n_rows, int64_t n_cols, char family, char major_axis, const uint32_t ctr[4],
+                        uint32_t next_ctr[4]);
+int rb_sparse_next_state(int64_t n_rows, int64_t n_cols, int64_t vec_nnz, char major_axis, const uint32_t ctr[4],
+                         uint32_t next_ctr[4]);
+
+/* ---- raw generator output (for bit-exact checks of the device generator) ----
+ * out[4*i .. 4*i+3] = Philox4x32_10(ctr + i, key), i in [0, n_blocks). Replaces: r123::Philox4x32::operator()
+ * as called at RandBLAS/random_gen.hh:107,135. */
+int rb_philox_words(const uint32_t ctr[4], const uint32_t key[2], int64_t n_blocks, uint32_t* out, void* stream);
+
+/* ---- K1: fill_dense ----
+ * Replaces RandBLAS::fill_dense_unpacked (RandBLAS/dense_skops.hh:563-606) and through it
+ * fill_dense(D, buff, seed) (:623-626), fill_dense(S) (:649-658), dense::fill_dense_submat_impl (:96-170).
+ * Writes the n_rows x n_cols window at (ro_s, co_s) of the sample of DenseDist(D_rows, D_cols, family,
+ * major_axis) in `layout`, with leading dimension ld (0 = packed, the reference's behaviour). */
+int rb_fill_dense_f32(char layout, int64_t D_rows, int64_t D_cols, char family, char major_axis, int64_t n_rows,
+                      int64_t n_cols, int64_t ro_s, int64_t co_s, float* buff, int64_t ld, const uint32_t ctr[4],
+                      const uint32_t key[2], uint32_t next_ctr[4], void* stream);
+int rb_fill_dense_f64(char layout, int64_t D_rows, int64_t D_cols, char family, char major_axis, int64_t n_rows,
+                      int64_t n_cols, int64_t ro_s, int64_t co_s, double* buff, int64_t ld, const uint32_t ctr[4],
+                      const uint32_t key[2], uint32_t next_ctr[4], void* stream);
+
+/* ---- K3a: SASO index/sign generation ----
+ * Replaces RandBLAS::fill_sparse_unpacked_nosub, SASO branch (RandBLAS/sparse_skops.hh:515-533), fill_sparse(S)
+ * (:587-603) and sparse::repeated_fisher_yates (:51-106). val_bytes in {4, 8} (float/double), idx_bytes in {4, 8}.
+ * vals/rows/cols hold full_nnz = vec_nnz * dim_minor entries. *nnz (host) receives full_nnz. */
+int rb_fill_sparse_saso(int64_t D_rows, int64_t D_cols, int64_t vec_nnz, const uint32_t ctr[4], const uint32_t key[2],
+                        void* vals, int val_bytes, void* rows, void* cols, int idx_bytes, int64_t* nnz,
+                        uint32_t next_ctr[4], void* stream);
+/* public repeated_fisher_yates(k, n, r, samples, state) (RandBLAS/sparse_skops.hh:259-264) */
+int rb_repeated_fisher_yates(int64_t k, int64_t n, int64_t r, void* samples, int idx_bytes, const uint32_t ctr[4],
+                             const uint32_t key[2], uint32_t next_ctr[4], void* stream);
+
+/* ---- K2: dense operator applied to dense data ----
+ * Replaces dense::lskge3 (RandBLAS/skge.hh:154-202) / dense::rskge3 (:307-355), i.e. the DenseSkOp
+ * overloads of sketch_general (:799-821, :947-968, :1073-1097, :1175-1199) and sketch_vector (skve.hh:141-164).
+ *   left : B(d x n) = alpha * op(S[ro_s:, co_s:])(d x m) * op(A)(m x n) + beta * B
+ *   right: B(m x d) = alpha * op(A)(m x n) * op(S[ro_s:, co_s:])(n x d) + beta * B
+ * S is the sample of DenseDist(D_rows, D_cols, family, major_axis) at (ctr, key). If S_buff is NULL the
+ * operator is regenerated tile by tile inside the kernel and never touches HBM; otherwise S_buff is the
+ * filled operator (S.buff, in the operator's natural layout, leading dimension dim_major) and is read. */
+int rb_lskge3_f32(char layout, char opS, char opA, int64_t d, int64_t n, int64_t m, float alpha, int64_t D_rows,
+                  int64_t D_cols, char family, char major_axis, const uint32_t ctr[4], const uint32_t key[2],
+                  const float* S_buff, int64_t ro_s, int64_t co_s, const float* A, int64_t lda, float beta, float* B,
+                  int64_t ldb, void* stream);
+int rb_lskge3_f64(char layout, char opS, char opA, int64_t d, int64_t n, int64_t m, double alpha, int64_t D_rows,
+                  int64_t D_cols, char family, char major_axis, const uint32_t ctr[4], const uint32_t key[2],
+                  const double* S_buff, int64_t ro_s, int64_t co_s, const double* A, int64_t lda, double beta,
+                  double* B, int64_t ldb, void* stream);
+int rb_rskge3_f32(char layout, char opA, char opS, int64_t m, int64_t d, int64_t n, float alpha, const float* A,
+                  int64_t lda, int64_t D_rows, int64_t D_cols, char family, char major_axis, const uint32_t ctr[4],
+                  const uint32_t key[2], const float* S_buff, int64_t ro_s, int64_t co_s, float beta, float* B,
+                  int64_t ldb, void* stream);
+int rb_rskge3_f64(char layout, char opA, char opS, int64_t m, int64_t d, int64_t n, double alpha, const double* A,
+                  int64_t lda, int64_t D_rows, int64_t D_cols, char family, char major_axis, const uint32_t ctr[4],
+                  const uint32_t key[2], const double* S_buff, int64_t ro_s, int64_t co_s, double beta, double* B,
+                  int64_t ldb, void* stream);
+
+/* ---- K3b: SASO operator applied to dense data ----
+ * Replaces sparse::lskges (RandBLAS/skge.hh:465-492) / sparse::rskges (:598-626) and the left_spmm COO path
+ * under them (sparse_data/spmm_dispatch.hh:52-179, coo_spmm_impl.hh:53-105). The operator is
+ * SparseDist(D_rows, D_cols, vec_nnz, Short) at (ctr, key); its (row, sign) lists are regenerated in
+ * registers, the COO arrays are never materialised. */
+int rb_lskges_f32(char layout, char opS, char opA, int64_t d, int64_t n, int64_t m, float alpha, int64_t D_rows,
+                  int64_t D_cols, int64_t vec_nnz, const uint32_t ctr[4], const uint32_t key[2], int64_t ro_s,
+                  int64_t co_s, const float* A, int64_t lda, float beta, float* B, int64_t ldb, void* stream);
+int rb_lskges_f64(char layout, char opS, char opA, int64_t d, int64_t n, int64_t m, double alpha, int64_t D_rows,
+                  int64_t D_cols, int64_t vec_nnz, const uint32_t ctr[4], const uint32_t key[2], int64_t ro_s,
+                  int64_t co_s, const double* A, int64_t lda, double beta, double* B, int64_t ldb, void* stream);
+int rb_rskges_f32(char layout, char opA, char opS, int64_t m, int64_t d, int64_t n, float alpha, const float* A,
+                  int64_t lda, int64_t D_rows, int64_t D_cols, int64_t vec_nnz, const uint32_t ctr[4],
+                  const uint32_t key[2], int64_t ro_s, int64_t co_s, float beta, float* B, int64_t ldb, void* stream);
+int rb_rskges_f64(char layout, char opA, char opS, int64_t m, int64_t d, int64_t n, double alpha, const double* A,
+                  int64_t lda, int64_t D_rows, int64_t D_cols, int64_t vec_nnz, const uint32_t ctr[4],
+                  const uint32_t key[2], int64_t ro_s, int64_t co_s, double beta, double* B, int64_t ldb, void* stream);
+/* Same contraction for an ALREADY SAMPLED sparse operator given as COO arrays (S.vals/rows/cols with S.nnz >= 0,
+ * skge.hh:489-490): generic COO x dense. idx_bytes in {4, 8}. */
+int rb_coo_apply_f32(int side_left, char layout, char opS, char opA, int64_t d, int64_t n, int64_t m, float alpha,
+                     int64_t S_rows, int64_t S_cols, int64_t nnz, const float* vals, const void* rows,
+                     const void* cols, int idx_bytes, int64_t ro_s, int64_t co_s, const float* A, int64_t lda,
+                     float beta, float* B, int64_t ldb, void* stream);
+int rb_coo_apply_f64(int side_left, char layout, char opS, char opA, int64_t d, int64_t n, int64_t m, double alpha,
+                     int64_t S_rows, int64_t S_cols, int64_t nnz, const double* vals, const void* rows,
+                     const void* cols, int idx_bytes, int64_t ro_s, int64_t co_s, const double* A, int64_t lda,
+                     double beta, double* B, int64_t ldb, void* stream);
+
+/* ---- K4: dense operator applied to sparse data ----
+ * Replaces sparse_data::lsksp3 (RandBLAS/sparse_data/sksp.hh:132-182) / rsksp3 (:277-326), i.e. sketch_sparse
+ * (:418-437, :520-539) and the right_spmm/left_spmm kernels under them (spmm_dispatch.hh:52-219,
+ * csc_spmm_impl.hh, csr_spmm_impl.hh, coo_spmm_impl.hh).
+ *   left : B(d x n) = alpha * op(S[ro_s:, co_s:]) * op(A_sp[ro_a:, co_a:]) + beta * B
+ *   right: B(m x d) = alpha * op(A_sp[ro_a:, co_a:]) * op(S[ro_s:, co_s:]) + beta * B
+ * fmt 0 = CSR (idx0 = rowptr[A_rows+1], idx1 = colidxs[nnz]); 1 = CSC (idx0 = rowidxs[nnz], idx1 = colptr[A_cols+1]);
+ * 2 = COO (idx0 = rows[nnz], idx1 = cols[nnz]). Zero-based indices, idx_bytes in {4, 8}. */
+int rb_lsksp3_f32(int fmt, char layout, char opS, char opA, int64_t d, int64_t n, int64_t m, float alpha,
+                  int64_t D_rows, int64_t D_cols, char family, char major_axis, const uint32_t ctr[4],
+                  const uint32_t key[2], int64_t ro_s, int64_t co_s, int64_t A_rows, int64_t A_cols, int64_t nnz,
+                  const float* vals, const void* idx0, const void* idx1, int idx_bytes, int64_t ro_a, int64_t co_a,
+                  float beta, float* B, int64_t ldb, void* stream);
+int rb_lsksp3_f64(int fmt, char layout, char opS, char opA, int64_t d, int64_t n, int64_t m, double alpha,
+                  int64_t D_rows, int64_t D_cols, char family, char major_axis, const uint32_t ctr[4],
+                  const uint32_t key[2], int64_t ro_s, int64_t co_s, int64_t A_rows, int64_t A_cols, int64_t nnz,
+                  const double* vals, const void* idx0, const void* idx1, int idx_bytes, int64_t ro_a, int64_t co_a,
+                  double beta, double* B, int64_t ldb, void* stream);
+int rb_rsksp3_f32(int fmt, char layout, char opA, char opS, int64_t m, int64_t d, int64_t n, float alpha,
+                  int64_t A_rows, int64_t A_cols, int64_t nnz, const float* vals, const void* idx0, const void* idx1,
+                  int idx_bytes, int64_t ro_a, int64_t co_a, int64_t D_rows, int64_t D_cols, char family,
+                  char major_axis, const uint32_t ctr[4], const uint32_t key[2], int64_t ro_s, int64_t co_s,
+                  float beta, float* B, int64_t ldb, void* stream);
+int rb_rsksp3_f64(int fmt, char layout, char opA, char opS, int64_t m, int64_t d, int64_t n, double alpha,
+                  int64_t A_rows, int64_t A_cols, int64_t nnz, const double* vals, const void* idx0, const void* idx1,
+                  int idx_bytes, int64_t ro_a, int64_t co_a, int64_t D_rows, int64_t D_cols, char family,
+                  char major_axis, const uint32_t ctr[4], const uint32_t key[2], int64_t ro_s, int64_t co_s,
+                  double beta, double* B, int64_t ldb, void* stream);
+
+/* ---- tuning / introspection (not part of the reference's surface) ----
+ * rb_set_option("dense_path", v): 0 = auto (tensor-core kernels where the shape allows), 1 = force the
+ * generic SIMT kernel. rb_get_counter("kernel_launches") counts kernels this library launched. */
+int rb_set_option(const char* name, int64_t value);
+int64_t rb_get_counter(const char* name);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RANDBLAS_B200_H */

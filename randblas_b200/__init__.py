@@ -1,0 +1,10 @@
+"""randblas_b200 -- B200-native sketching hot path behind the RandBLAS API.
+
+The product is the CUDA library `librandblas_b200.so` (C ABI: include/randblas_b200.h) plus the header-only
+C++ drop-in layer under include/RandBLAS/. This Python package is a thin host-side mirror of the same API
+(same names, argument order and error behaviour as the reference) used by the tests and by bench.py.
+"""
+from .api import (Axis, COOMatrix, CSCMatrix, CSRMatrix, DenseDist, DenseSkOp, Layout, Op, RNGState, ScalarDist,  # noqa
+                  SparseDist, SparseSkOp, fill_dense, fill_dense_unpacked, fill_sparse, fill_sparse_unpacked_nosub,
+                  philox_words, repeated_fisher_yates, sketch_general, sketch_sparse, sketch_vector)
+from ._lib import RandBLASError, counter, set_option  # noqa

@@ -1,0 +1,421 @@
+"""Host-side mirror of the reference's public API for the sketching hot path.
+
+Names, argument order, defaults and argument checks follow the reference (file:line cited per item, relative
+to the reference root); every function that does work forwards to one C-ABI entry point of
+librandblas_b200.so. Buffers may be torch CUDA tensors (used in place; the measured mode) or host arrays
+(numpy arrays / CPU torch tensors: staged through device memory inside the C call, as a caller of the CPU
+reference would pass them).
+"""
+import ctypes
+import math
+
+import numpy as np
+
+from . import _lib
+from ._lib import RandBLASError, call
+
+try:  # torch is plumbing only (device memory + streams); the library itself does not need it
+    import torch
+except Exception:  # pragma: no cover
+    torch = None
+
+
+class Layout:               # blas::Layout (BLAS++ values)
+    ColMajor = "C"
+    RowMajor = "R"
+
+
+class Op:                   # blas::Op
+    NoTrans = "N"
+    Trans = "T"
+
+
+class Axis:                 # RandBLAS/base.hh:306-312
+    Short = "S"
+    Long = "L"
+
+
+class ScalarDist:           # RandBLAS/dense_skops.hh:215-224
+    Gaussian = "G"
+    Uniform = "U"
+
+
+def _require(cond, text):
+    # randblas_require, RandBLAS/exceptions.hh:152-162
+    if not cond:
+        raise RandBLASError(f"({text}) was required, but did not hold")
+
+
+# ------------------------------------------------------------------------------------------------
+class RNGState:
+    """RandBLAS/base.hh:64-164. counter: 4 x u32 (128-bit little-endian), key: 2 x u32."""
+
+    def __init__(self, k=0, counter=None, key=None):
+        if isinstance(k, RNGState):
+            counter, key = k.counter, k.key
+            k = 0
+        if counter is not None or key is not None:
+            self.counter = [int(x) & 0xFFFFFFFF for x in (counter if counter is not None else [0, 0, 0, 0])]
+            self.key = [int(x) & 0xFFFFFFFF for x in (key if key is not None else [0, 0])]
+        else:
+            c = (ctypes.c_uint32 * 4)()
+            kk = (ctypes.c_uint32 * 2)()
+            _lib.lib().rb_rngstate_from_u64(ctypes.c_uint64(int(k)), c, kk)   # base.hh:116-119
+            self.counter, self.key = list(c), list(kk)
+
+    def copy(self):
+        return RNGState(counter=self.counter, key=self.key)
+
+    def incr(self, n):
+        """A new state whose counter is advanced by n (Random123 array.h `incr`)."""
+        c = (ctypes.c_uint32 * 4)(*self.counter)
+        _lib.lib().rb_ctr_incr(c, ctypes.c_uint64(int(n)))
+        return RNGState(counter=list(c), key=self.key)
+
+    def __eq__(self, o):
+        return isinstance(o, RNGState) and self.counter == o.counter and self.key == o.key
+
+    def __repr__(self):
+        return f"counter : {{{', '.join(map(str, self.counter))}}}\nkey     : {{{', '.join(map(str, self.key))}}}"
+
+    # ctypes views
+    def _c(self):
+        return (ctypes.c_uint32 * 4)(*self.counter)
+
+    def _k(self):
+        return (ctypes.c_uint32 * 2)(*self.key)
+
+
+def _addr(x):
+    # ctypes objects are handed to _lib.call as objects (passed by reference there) so they stay alive
+    return x
+
+
+class DenseDist:
+    """RandBLAS/dense_skops.hh:231-350."""
+
+    def __init__(self, n_rows, n_cols, family=ScalarDist.Gaussian, major_axis=Axis.Long):
+        n_rows, n_cols = int(n_rows), int(n_cols)
+        _require(n_rows > 0, "n_rows > 0")          # :327
+        _require(n_cols > 0, "n_cols > 0")          # :328
+        info = (ctypes.c_int64 * 3)()
+        iso = ctypes.c_double()
+        call("rb_dense_dist_info", "qqccpp", n_rows, n_cols, family, major_axis, _addr(info), _addr(iso))
+        self.n_rows, self.n_cols, self.family, self.major_axis = n_rows, n_cols, family, major_axis
+        self.dim_major, self.dim_minor = int(info[0]), int(info[1])
+        self.natural_layout = chr(info[2])
+        self.isometry_scale = iso.value
+
+    def sample(self, seed_state, dtype=np.float32):
+        return DenseSkOp(self, seed_state, dtype)
+
+    def _t(self):
+        return (self.n_rows, self.n_cols, self.family, self.major_axis)
+
+
+class SparseDist:
+    """RandBLAS/sparse_skops.hh:131-246."""
+
+    def __init__(self, n_rows, n_cols, vec_nnz=4, major_axis=Axis.Short):
+        n_rows, n_cols, vec_nnz = int(n_rows), int(n_cols), int(vec_nnz)
+        _require(n_rows > 0, "n_rows > 0")
+        _require(n_cols > 0, "n_cols > 0")
+        _require(vec_nnz > 0, "vec_nnz > 0")
+        info = (ctypes.c_int64 * 3)()
+        iso = ctypes.c_double()
+        call("rb_sparse_dist_info", "qqqcpp", n_rows, n_cols, vec_nnz, major_axis, _addr(info), _addr(iso))
+        self.n_rows, self.n_cols, self.vec_nnz, self.major_axis = n_rows, n_cols, vec_nnz, major_axis
+        self.dim_major, self.dim_minor, self.full_nnz = int(info[0]), int(info[1]), int(info[2])
+        self.isometry_scale = iso.value
+
+    def sample(self, seed_state, dtype=np.float32, index_dtype=np.int64):
+        return SparseSkOp(self, seed_state, dtype=dtype, index_dtype=index_dtype)
+
+
+class DenseSkOp:
+    """RandBLAS/dense_skops.hh:357-478. `buff` stays None until fill_dense(S); sketching with an unfilled
+    operator regenerates it inside the kernel (the reference materialises a temporary, skge.hh:174-181)."""
+
+    def __init__(self, dist, seed_state, dtype=np.float32):
+        self.dist = dist
+        self.seed_state = RNGState(seed_state)
+        nxt = (ctypes.c_uint32 * 4)()
+        call("rb_dense_next_state", "qqccpp", dist.n_rows, dist.n_cols, dist.family, dist.major_axis,
+             _addr(self.seed_state._c()), _addr(nxt))
+        self.next_state = RNGState(counter=list(nxt), key=self.seed_state.key)    # dense_skops.hh:172-185
+        self.n_rows, self.n_cols = dist.n_rows, dist.n_cols
+        self.own_memory = True
+        self.buff = None
+        self.layout = dist.natural_layout
+        self.dtype = np.dtype(_np_dtype(dtype))
+
+
+class SparseSkOp:
+    """RandBLAS/sparse_skops.hh:289-450. nnz < 0 until fill_sparse(S)."""
+
+    def __init__(self, dist, seed_state, next_state=None, nnz=-1, vals=None, rows=None, cols=None, dtype=np.float32,
+                 index_dtype=np.int64):
+        self.dist = dist
+        self.seed_state = RNGState(seed_state)
+        if next_state is None:
+            nxt = (ctypes.c_uint32 * 4)()
+            call("rb_sparse_next_state", "qqqcpp", dist.n_rows, dist.n_cols, dist.vec_nnz, dist.major_axis,
+                 _addr(self.seed_state._c()), _addr(nxt))
+            next_state = RNGState(counter=list(nxt), key=self.seed_state.key)     # sparse_skops.hh:266-283
+            self.own_memory = True
+        else:
+            self.own_memory = False                                             # expert constructor, :413-428
+        self.next_state = RNGState(next_state)
+        self.n_rows, self.n_cols = dist.n_rows, dist.n_cols
+        self.nnz, self.vals, self.rows, self.cols = nnz, vals, rows, cols
+        self.dtype = np.dtype(_np_dtype(dtype if vals is None else _dtype_of(vals)))
+        self.index_dtype = np.dtype(_np_dtype(index_dtype if rows is None else _dtype_of(rows)))
+
+
+class _SpMat:
+    def __init__(self, n_rows, n_cols, nnz, vals, idx0, idx1, fmt):
+        self.n_rows, self.n_cols, self.nnz, self.vals = int(n_rows), int(n_cols), int(nnz), vals
+        self._idx0, self._idx1, self._fmt = idx0, idx1, fmt
+        self.own_memory = False
+        self.index_base = 0
+
+
+class CSRMatrix(_SpMat):    # RandBLAS/sparse_data/csr_matrix.hh:159-168 (view constructor)
+    def __init__(self, n_rows, n_cols, nnz, vals, rowptr, colidxs):
+        super().__init__(n_rows, n_cols, nnz, vals, rowptr, colidxs, 0)
+        self.rowptr, self.colidxs = rowptr, colidxs
+
+
+class CSCMatrix(_SpMat):    # RandBLAS/sparse_data/csc_matrix.hh:158-167
+    def __init__(self, n_rows, n_cols, nnz, vals, rowidxs, colptr):
+        super().__init__(n_rows, n_cols, nnz, vals, rowidxs, colptr, 1)
+        self.rowidxs, self.colptr = rowidxs, colptr
+
+
+class COOMatrix(_SpMat):    # RandBLAS/sparse_data/coo_matrix.hh:177-193
+    def __init__(self, n_rows, n_cols, nnz, vals, rows, cols):
+        super().__init__(n_rows, n_cols, nnz, vals, rows, cols, 2)
+        self.rows, self.cols = rows, cols
+
+
+# ------------------------------------------------------------------------------------------------
+def _np_dtype(dt):
+    if torch is not None and isinstance(dt, torch.dtype):
+        return {torch.float32: np.float32, torch.float64: np.float64, torch.int32: np.int32, torch.int64: np.int64}[dt]
+    return np.dtype(dt).type
+
+
+def _dtype_of(x):
+    if torch is not None and isinstance(x, torch.Tensor):
+        return _np_dtype(x.dtype)
+    return x.dtype.type
+
+
+def _ptr(x):
+    if x is None:
+        return 0
+    if torch is not None and isinstance(x, torch.Tensor):
+        return x.data_ptr()
+    assert isinstance(x, np.ndarray)
+    return x.ctypes.data
+
+
+def _stream(*bufs):
+    if torch is not None:
+        for b in bufs:
+            if isinstance(b, torch.Tensor) and b.is_cuda:
+                return torch.cuda.current_stream(b.device).cuda_stream
+    return 0
+
+
+def _sfx(dt):
+    dt = np.dtype(dt)
+    if dt == np.float32:
+        return "f32", "f"
+    if dt == np.float64:
+        return "f64", "d"
+    raise TypeError(f"unsupported scalar type {dt}")
+
+
+def philox_words(state, n_blocks, out):
+    """out[4i:4i+4] = Philox4x32_10(state.counter + i, state.key). out: uint32 buffer viewed as int32 if torch."""
+    call("rb_philox_words", "ppqpp", _addr(state._c()), _addr(state._k()), int(n_blocks), _ptr(out), _stream(out))
+    return out
+
+
+def fill_dense_unpacked(layout, D, n_rows, n_cols, ro_s, co_s, buff, seed, ld=0):
+    """RandBLAS/dense_skops.hh:563-606. Returns the advanced RNGState."""
+    sfx, _ = _sfx(_dtype_of(buff))
+    nxt = (ctypes.c_uint32 * 4)()
+    call(f"rb_fill_dense_{sfx}", "cqqccqqqqpqpppp", layout, D.n_rows, D.n_cols, D.family, D.major_axis, int(n_rows),
+         int(n_cols), int(ro_s), int(co_s), _ptr(buff), int(ld), _addr(seed._c()), _addr(seed._k()), _addr(nxt),
+         _stream(buff))
+    return RNGState(counter=list(nxt), key=seed.key)
+
+
+def fill_dense(*args):
+    """fill_dense(D, buff, seed) -> RNGState (dense_skops.hh:623-626), or fill_dense(S) (:649-658)."""
+    if len(args) == 3:
+        D, buff, seed = args
+        return fill_dense_unpacked(D.natural_layout, D, D.n_rows, D.n_cols, 0, 0, buff, seed)
+    (S,) = args
+    if S.own_memory and S.buff is None:
+        # the reference allocates host memory with new[]; a GPU library keeps the operator in device memory
+        _require(torch is not None, "torch available to allocate S.buff")
+        S.buff = torch.empty(S.n_rows * S.n_cols, dtype={np.float32: torch.float32, np.float64: torch.float64}[S.dtype.type],
+                             device="cuda")
+    _require(S.buff is not None, "S.buff != nullptr")
+    fill_dense_unpacked(S.layout, S.dist, S.n_rows, S.n_cols, 0, 0, S.buff, S.seed_state)
+
+
+def fill_sparse_unpacked_nosub(D, vals, rows, cols, seed_state):
+    """RandBLAS/sparse_skops.hh:515-565 (SASO). Returns (nnz, next_state)."""
+    _require(D.major_axis == Axis.Short, "D.major_axis == Axis::Short (LASO is not built yet)")
+    nnz = ctypes.c_int64(-1)
+    nxt = (ctypes.c_uint32 * 4)()
+    call("rb_fill_sparse_saso", "qqqpppippippp", D.n_rows, D.n_cols, D.vec_nnz, _addr(seed_state._c()),
+         _addr(seed_state._k()), _ptr(vals), np.dtype(_dtype_of(vals)).itemsize, _ptr(rows), _ptr(cols),
+         np.dtype(_dtype_of(rows)).itemsize, _addr(nnz), _addr(nxt), _stream(vals, rows, cols))
+    return nnz.value, RNGState(counter=list(nxt), key=seed_state.key)
+
+
+def fill_sparse(S):
+    """RandBLAS/sparse_skops.hh:587-603."""
+    full = S.dist.full_nnz
+    if S.own_memory:
+        _require(torch is not None, "torch available to allocate the COO arrays")
+        tdt = {np.float32: torch.float32, np.float64: torch.float64}[S.dtype.type]
+        idt = {np.int32: torch.int32, np.int64: torch.int64}[S.index_dtype.type]
+        if S.rows is None:
+            S.rows = torch.empty(full, dtype=idt, device="cuda")
+        if S.cols is None:
+            S.cols = torch.empty(full, dtype=idt, device="cuda")
+        if S.vals is None:
+            S.vals = torch.empty(full, dtype=tdt, device="cuda")
+    _require(S.rows is not None, "S.rows != nullptr")
+    _require(S.cols is not None, "S.cols != nullptr")
+    _require(S.vals is not None, "S.vals != nullptr")
+    S.nnz, _ = fill_sparse_unpacked_nosub(S.dist, S.vals, S.rows, S.cols, S.seed_state)
+
+
+def repeated_fisher_yates(k, n, r, samples, state):
+    """RandBLAS/sparse_skops.hh:259-264. Returns the advanced RNGState."""
+    nxt = (ctypes.c_uint32 * 4)()
+    call("rb_repeated_fisher_yates", "qqqpipppp", int(k), int(n), int(r), _ptr(samples),
+         np.dtype(_dtype_of(samples)).itemsize, _addr(state._c()), _addr(state._k()), _addr(nxt), _stream(samples))
+    return RNGState(counter=list(nxt), key=state.key)
+
+
+def _is_op(x):
+    return isinstance(x, (DenseSkOp, SparseSkOp))
+
+
+def sketch_general(layout, op1, op2, x, y, z, alpha, *rest):
+    """The eight overloads of RandBLAS::sketch_general (RandBLAS/skge.hh:756-821, 928-992, 1073-1097, 1175-1199).
+
+    left : sketch_general(layout, opS, opA, d, n, m, alpha, S, [ro_s, co_s,] A, lda, beta, B, ldb)
+    right: sketch_general(layout, opA, opS, m, d, n, alpha, A, lda, S, [ro_s, co_s,] beta, B, ldb)
+    """
+    if _is_op(rest[0]):
+        S = rest[0]
+        opS, opA, d, n, m = op1, op2, int(x), int(y), int(z)
+        if len(rest) == 6:      # full-operator overload: dimension checks of skge.hh:1089-1095
+            A, lda, beta, B, ldb = rest[1:]
+            if opS == Op.NoTrans:
+                _require(S.n_rows == d, "S.n_rows == d"); _require(S.n_cols == m, "S.n_cols == m")
+            else:
+                _require(S.n_rows == m, "S.n_rows == m"); _require(S.n_cols == d, "S.n_cols == d")
+            ro_s = co_s = 0
+        else:
+            ro_s, co_s, A, lda, beta, B, ldb = rest[1:]
+        return _skge(True, layout, opS, opA, d, n, m, alpha, S, int(ro_s), int(co_s), A, int(lda), beta, B, int(ldb))
+    A, lda, S = rest[0], rest[1], rest[2]
+    opA, opS, m, d, n = op1, op2, int(x), int(y), int(z)
+    if len(rest) == 6:          # skge.hh:1191-1197
+        beta, B, ldb = rest[3:]
+        if opS == Op.NoTrans:
+            _require(S.n_rows == n, "S.n_rows == n"); _require(S.n_cols == d, "S.n_cols == d")
+        else:
+            _require(S.n_rows == d, "S.n_rows == d"); _require(S.n_cols == n, "S.n_cols == n")
+        ro_s = co_s = 0
+    else:
+        ro_s, co_s, beta, B, ldb = rest[3:]
+    return _skge(False, layout, opS, opA, d, n, m, alpha, S, int(ro_s), int(co_s), A, int(lda), beta, B, int(ldb))
+
+
+def _skge(left, layout, opS, opA, d, n, m, alpha, S, ro_s, co_s, A, lda, beta, B, ldb):
+    sfx, t = _sfx(_dtype_of(B))
+    st = _stream(A, B)
+    seed = S.seed_state
+    if isinstance(S, DenseSkOp):
+        D = S.dist
+        if left:   # dense::lskge3, skge.hh:154-202
+            call(f"rb_lskge3_{sfx}", "cccqqq" + t + "qqccppp" + "qqpq" + t + "pqp", layout, opS, opA, d, n, m, alpha,
+                 D.n_rows, D.n_cols, D.family, D.major_axis, _addr(seed._c()), _addr(seed._k()), _ptr(S.buff), ro_s,
+                 co_s, _ptr(A), lda, beta, _ptr(B), ldb, st)
+        else:      # dense::rskge3, skge.hh:307-355
+            call(f"rb_rskge3_{sfx}", "cccqqq" + t + "pq" + "qqccppp" + "qq" + t + "pqp", layout, opA, opS, m, d, n,
+                 alpha, _ptr(A), lda, D.n_rows, D.n_cols, D.family, D.major_axis, _addr(seed._c()), _addr(seed._k()),
+                 _ptr(S.buff), ro_s, co_s, beta, _ptr(B), ldb, st)
+        return
+    D = S.dist
+    if S.nnz >= 0:
+        # already sampled (S.vals/rows/cols): coo_view_of_skop + left_spmm/right_spmm, skge.hh:489-490, 621-625
+        call(f"rb_coo_apply_{sfx}", "icccqqq" + t + "qqqpppi" + "qqpq" + t + "pqp", 1 if left else 0, layout, opS, opA,
+             d, n, m, alpha, S.n_rows, S.n_cols, S.nnz, _ptr(S.vals), _ptr(S.rows), _ptr(S.cols),
+             S.index_dtype.itemsize, ro_s, co_s, _ptr(A), lda, beta, _ptr(B), ldb, st)
+        return
+    _require(D.major_axis == Axis.Short, "S.dist.major_axis == Axis::Short (LASO is not built yet)")
+    if left:       # sparse::lskges, skge.hh:465-492
+        call(f"rb_lskges_{sfx}", "cccqqq" + t + "qqqpp" + "qqpq" + t + "pqp", layout, opS, opA, d, n, m, alpha,
+             D.n_rows, D.n_cols, D.vec_nnz, _addr(seed._c()), _addr(seed._k()), ro_s, co_s, _ptr(A), lda, beta,
+             _ptr(B), ldb, st)
+    else:          # sparse::rskges, skge.hh:598-626
+        call(f"rb_rskges_{sfx}", "cccqqq" + t + "pq" + "qqqpp" + "qq" + t + "pqp", layout, opA, opS, m, d, n, alpha,
+             _ptr(A), lda, D.n_rows, D.n_cols, D.vec_nnz, _addr(seed._c()), _addr(seed._k()), ro_s, co_s, beta,
+             _ptr(B), ldb, st)
+
+
+def sketch_vector(opS, *args):
+    """RandBLAS/skve.hh:141-164 (submatrix) and :233-246 (full operator).
+
+    sketch_vector(opS, d, m, alpha, S, ro_s, co_s, x, incx, beta, y, incy)
+    sketch_vector(opS, alpha, S, x, incx, beta, y, incy)
+    """
+    if len(args) == 7:
+        alpha, S, x, incx, beta, y, incy = args
+        d, m, ro_s, co_s = S.dist.n_rows, S.dist.n_cols, 0, 0
+    else:
+        d, m, alpha, S, ro_s, co_s, x, incx, beta, y, incy = args
+    _d, _m = (m, d) if opS == Op.Trans else (d, m)
+    return sketch_general(Layout.RowMajor, opS, Op.NoTrans, _d, 1, _m, alpha, S, ro_s, co_s, x, incx, beta, y, incy)
+
+
+def sketch_sparse(layout, op1, op2, x, y, z, alpha, *rest):
+    """RandBLAS/sparse_data/sksp.hh:418-437 (left) and :520-539 (right).
+
+    left : sketch_sparse(layout, opS, opA, d, n, m, alpha, S, ro_s, co_s, A_sp, beta, B, ldb)
+    right: sketch_sparse(layout, opA, opS, m, d, n, alpha, A_sp, S, ro_s, co_s, beta, B, ldb)
+    """
+    if _is_op(rest[0]):
+        S, ro_s, co_s, A, beta, B, ldb = rest
+        left, opS, opA, d, n, m = True, op1, op2, int(x), int(y), int(z)
+    else:
+        A, S, ro_s, co_s, beta, B, ldb = rest
+        left, opA, opS, m, d, n = False, op1, op2, int(x), int(y), int(z)
+    _require(isinstance(S, DenseSkOp), "S is a DenseSkOp")
+    _require(A.index_base == 0, "A.index_base == IndexBase::Zero")      # spmm_dispatch.hh:92
+    sfx, t = _sfx(_dtype_of(B))
+    D, seed = S.dist, S.seed_state
+    st = _stream(B, A.vals)
+    ib = np.dtype(_dtype_of(A._idx0)).itemsize
+    if left:
+        call(f"rb_lsksp3_{sfx}", "icccqqq" + t + "qqccpp" + "qq" + "qqqpppi" + "qq" + t + "pqp", A._fmt, layout, opS,
+             opA, d, n, m, alpha, D.n_rows, D.n_cols, D.family, D.major_axis, _addr(seed._c()), _addr(seed._k()),
+             int(ro_s), int(co_s), A.n_rows, A.n_cols, A.nnz, _ptr(A.vals), _ptr(A._idx0), _ptr(A._idx1), ib, 0, 0,
+             beta, _ptr(B), int(ldb), st)
+    else:
+        call(f"rb_rsksp3_{sfx}", "icccqqq" + t + "qqqpppi" + "qq" + "qqccpp" + "qq" + t + "pqp", A._fmt, layout, opA,
+             opS, m, d, n, alpha, A.n_rows, A.n_cols, A.nnz, _ptr(A.vals), _ptr(A._idx0), _ptr(A._idx1), ib, 0, 0,
+             D.n_rows, D.n_cols, D.family, D.major_axis, _addr(seed._c()), _addr(seed._k()), int(ro_s), int(co_s),
+             beta, _ptr(B), int(ldb), st)

@@ -1,0 +1,147 @@
+// K1: fill_dense -- a window of a DenseSkOp sample written straight into the requested layout.
+//
+// Replaces (reference file:line): dense::fill_dense_submat_impl (RandBLAS/dense_skops.hh:96-170),
+// the Uniform post-scale (:587-590) and the out-of-place layout flip (:596-604) of fill_dense_unpacked.
+//
+// Work unit = one Philox4x32-10 counter block (4 samples) per thread per step. In the operator's
+// natural layout the sample is dim_minor "major-axis vectors" of R = ceil(dim_major/4) blocks each;
+// element (v, u) is lane u%4 of block (seed + v*R + u/4). The window is [v0, v0+nv) x [u0, u0+nu).
+// Threads walk the linear block index L = v_local * nblk + b with a grid stride, so consecutive
+// lanes write consecutive 16 B (float) / 32 B (double) pieces of the same vector: fully coalesced
+// 128-bit / 256-bit stores when the destination is written in natural orientation. When the
+// requested layout is the transpose of the natural one the lanes of a warp walk v instead, so each
+// of the four per-thread stores is still a contiguous warp-wide segment.
+//
+// Roofline: HBM write. Algorithmic bytes = sizeof(T) per sample.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace rb {
+
+struct FillArgs {
+    Ctr128 ctr;
+    PhiloxKey key;
+    int64_t R;          // blocks per major-axis vector of the parent operator
+    int64_t v0, nv;     // vector window
+    int64_t u0, nu;     // position window inside a vector
+    int64_t blk_first;  // u0 / 4
+    int64_t nblk;       // blocks touched per vector
+    int64_t sv, su;     // destination strides (elements) per vector step / per position step
+    int64_t total;      // nv * nblk
+    int64_t q_step, r_step;  // grid stride decomposed: stride = q_step * nblk + r_step
+};
+
+template <typename T>
+__device__ __forceinline__ void store4_vec(T* p, T a, T b, T c, T d);
+template <>
+__device__ __forceinline__ void store4_vec<float>(float* p, float a, float b, float c, float d) {
+    asm volatile("st.global.cs.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+template <>
+__device__ __forceinline__ void store4_vec<double>(double* p, double a, double b, double c, double d) {
+    // 256-bit store (sm_100+): one instruction per Philox block of doubles
+    asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+}
+
+template <typename T, bool GAUSS, bool WALK_V>
+__global__ void __launch_bounds__(256) fill_dense_kernel(const FillArgs a, T* __restrict__ dst) {
+    __shared__ __align__(16) double logtab[32];
+    if constexpr (GAUSS) {
+        load_logf_table(logtab);
+        __syncthreads();
+    }
+    int64_t L = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (L >= a.total) return;
+    // (vl, b): local vector index and block index inside the window
+    int64_t vl, b;
+    if constexpr (WALK_V) {          // lanes walk vectors: L = b * nv + vl
+        b = L / a.nv;
+        vl = L - b * a.nv;
+    } else {                         // lanes walk blocks of one vector: L = vl * nblk + b
+        vl = L / a.nblk;
+        b = L - vl * a.nblk;
+    }
+    const int64_t inner = WALK_V ? a.nv : a.nblk;
+    for (; L < a.total; L += (int64_t) gridDim.x * blockDim.x) {
+        const int64_t blk = a.blk_first + b;
+        const Ctr128 c = ctr_add(a.ctr, (uint64_t)((a.v0 + vl) * a.R + blk));
+        const float4 f = transform4<GAUSS>(philox4x32_10(c, a.key), logtab);
+        const T x0 = finish_sample<T, GAUSS>(f.x), x1 = finish_sample<T, GAUSS>(f.y),
+                x2 = finish_sample<T, GAUSS>(f.z), x3 = finish_sample<T, GAUSS>(f.w);
+        const int64_t ur = blk * 4 - a.u0;                 // position of lane 0 relative to the window
+        T* p = dst + vl * a.sv + ur * a.su;
+        const bool full = (ur >= 0) && (ur + 4 <= a.nu);
+        if (!WALK_V && full && a.su == 1 && ((reinterpret_cast<uintptr_t>(p) & (4 * sizeof(T) - 1)) == 0)) {
+            store4_vec<T>(p, x0, x1, x2, x3);
+        } else {
+            if (ur + 0 >= 0 && ur + 0 < a.nu) p[0] = x0;
+            if (ur + 1 >= 0 && ur + 1 < a.nu) p[1 * a.su] = x1;
+            if (ur + 2 >= 0 && ur + 2 < a.nu) p[2 * a.su] = x2;
+            if (ur + 3 >= 0 && ur + 3 < a.nu) p[3 * a.su] = x3;
+        }
+        // advance (vl, b) by the grid stride without a division
+        if constexpr (WALK_V) {
+            vl += a.r_step; b += a.q_step;
+            if (vl >= inner) { vl -= inner; b += 1; }
+        } else {
+            b += a.r_step; vl += a.q_step;
+            if (b >= inner) { b -= inner; vl += 1; }
+        }
+    }
+}
+
+__global__ void philox_words_kernel(Ctr128 ctr, PhiloxKey key, int64_t n_blocks, uint4* __restrict__ out) {
+    for (int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i < n_blocks;
+         i += (int64_t) gridDim.x * blockDim.x)
+        out[i] = philox4x32_10(ctr_add(ctr, (uint64_t) i), key);
+}
+
+int launch_philox_words(Ctr128 ctr, PhiloxKey key, int64_t n_blocks, uint32_t* out, cudaStream_t st) {
+    if (n_blocks <= 0) return 0;
+    int64_t grid = (n_blocks + 255) / 256;
+    int64_t cap = (int64_t) sm_count() * 16;
+    if (grid > cap) grid = cap;
+    philox_words_kernel<<<(unsigned) grid, 256, 0, st>>>(ctr, key, n_blocks, reinterpret_cast<uint4*>(out));
+    count_launch();
+    RB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// Device-pointer launcher. (v0,nv,u0,nu) is the window in natural coordinates; (sv,su) the
+// destination strides for one vector step / one position step.
+template <typename T>
+int launch_fill_dense(const DenseGen& g, char family, int64_t v0, int64_t nv, int64_t u0, int64_t nu, T* dst,
+                      int64_t sv, int64_t su, cudaStream_t st) {
+    if (nv <= 0 || nu <= 0) return 0;
+    FillArgs a;
+    a.ctr = g.ctr; a.key = g.key; a.R = g.R;
+    a.v0 = v0; a.nv = nv; a.u0 = u0; a.nu = nu;
+    a.blk_first = u0 / 4;
+    a.nblk = (u0 + nu - 1) / 4 - a.blk_first + 1;
+    a.sv = sv; a.su = su;
+    a.total = nv * a.nblk;
+    // lanes walk whichever direction is contiguous in memory
+    const bool walk_v = (su != 1) && (sv == 1 || sv < su);
+    int64_t grid = (a.total + 255) / 256;
+    const int64_t cap = (int64_t) sm_count() * 8;      // 8 CTAs of 256 threads per SM, then grid-stride
+    if (grid > cap) grid = cap;
+    const int64_t stride = grid * 256;
+    const int64_t inner = walk_v ? nv : a.nblk;
+    a.q_step = stride / inner;
+    a.r_step = stride % inner;
+    const bool gauss = family == 'G';
+#define RB_LAUNCH_FILL(G, W) fill_dense_kernel<T, G, W><<<(unsigned) grid, 256, 0, st>>>(a, dst)
+    if (gauss) { if (walk_v) RB_LAUNCH_FILL(true, true); else RB_LAUNCH_FILL(true, false); }
+    else       { if (walk_v) RB_LAUNCH_FILL(false, true); else RB_LAUNCH_FILL(false, false); }
+#undef RB_LAUNCH_FILL
+    count_launch();
+    RB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+template int launch_fill_dense<float>(const DenseGen&, char, int64_t, int64_t, int64_t, int64_t, float*, int64_t,
+                                      int64_t, cudaStream_t);
+template int launch_fill_dense<double>(const DenseGen&, char, int64_t, int64_t, int64_t, int64_t, double*, int64_t,
+                                       int64_t, cudaStream_t);
+
+}  // namespace rb

@@ -1,0 +1,456 @@
+"""GPU parity tests (run with -m gpu on the B200 box). Every call goes through the C ABI of
+librandblas_b200.so; the checker is the oracle (oracle/rb_oracle.c), the committed fixtures generated from the
+reference itself, and -- where it travelled -- the compiled reference (oracle/_ref).
+
+Bars (north_star): Philox words, uniform samples, SASO index/sign arrays: bit-exact. Gaussian samples: <= 2
+float ulp (measured: 0 on glibc 2.39 FMA hosts). Sketch products: relative Frobenius error <= 1e-5 (float),
+<= 1e-12 (double).
+"""
+import itertools
+
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+from golden_util import dense_data
+from test_oracle_pins import run_sketch_case, sketch_case_inputs
+
+pytestmark = pytest.mark.gpu
+
+TOL = {np.dtype(np.float32): 1e-5, np.dtype(np.float64): 1e-12}
+
+
+@pytest.fixture(scope="module")
+def gpu():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    from gpu_impl import Gpu
+    return Gpu()
+
+
+@pytest.fixture(scope="module")
+def gpu_host():
+    from gpu_impl import Gpu
+    return Gpu(host_buffers=True)
+
+
+def relerr(a, b):
+    a = np.asarray(a, np.float64)
+    b = np.asarray(b, np.float64)
+    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300)
+
+
+def ulp_diff_f32(a, b):
+    """max distance in float32 ulps between two arrays holding float-representable values"""
+    ia = np.asarray(a, np.float32).view(np.int32).astype(np.int64)
+    ib = np.asarray(b, np.float32).view(np.int32).astype(np.int64)
+    ia = np.where(ia < 0, -(ia & 0x7FFFFFFF), ia)
+    ib = np.where(ib < 0, -(ib & 0x7FFFFFFF), ib)
+    return int(np.abs(ia - ib).max()) if ia.size else 0
+
+
+def test_native_library_is_what_runs():
+    import randblas_b200 as rb
+    from randblas_b200 import _lib
+    assert _lib.lib() is not None
+    info = (np.zeros(3, np.int64))
+    _lib.call("rb_device_info", "p", info.ctypes.data)
+    assert info[1] >= 100, f"expected sm_100, got sm_{info[1]}"
+    before = rb.counter("kernel_launches")
+    import torch
+    out = torch.zeros(8, dtype=torch.int32, device="cuda")
+    rb.philox_words(rb.RNGState(0), 2, out)
+    torch.cuda.synchronize()
+    assert rb.counter("kernel_launches") == before + 1
+
+
+# ---------------------------------------------------------------------------------------- Philox
+def test_philox_words_bit_exact(gpu, port, gold):
+    for w in gold.kat("philox4x32 10"):
+        assert list(gpu.philox(w[0:4], w[4:6])) == w[6:10]
+    for c in gold.m["philox"]:
+        assert list(gpu.philox(c["ctr"], c["key"])) == c["out"]
+    # a stream of blocks that crosses 32-bit and 64-bit limb carries
+    for ctr in ([0xFFFFFFF0, 0, 0, 0], [0xFFFFFFF0, 0xFFFFFFFF, 0, 0], [0xFFFFFFF0, 0xFFFFFFFF, 0xFFFFFFFF, 0xFFFFFFFF]):
+        got = gpu.philox(ctr, [42, 7], 64).reshape(64, 4)
+        for i in (0, 15, 16, 17, 63):
+            assert list(got[i]) == list(port.philox(port.ctr_incr(ctr, i), [42, 7]))
+
+
+# ------------------------------------------------------------------------------------ fill_dense
+def test_fill_dense_goldens(gpu, gold):
+    worst = 0
+    for c in gold.m["fill_dense"]:
+        r, cc, fam, ax = c["D"]
+        nr, nc, ro, co = c["sub"]
+        dt = np.dtype(c["dtype"])
+        buf, nxt = gpu.fill_dense_unpacked(c["layout"], r, cc, fam, ax, nr, nc, ro, co, c["ctr"], c["key"], dt)
+        want = gold.arr(c["buff"])
+        assert list(nxt) == c["next_ctr"], c
+        if fam == "U":
+            assert np.array_equal(buf.view(np.uint8), want.view(np.uint8)), c
+        else:
+            u = ulp_diff_f32(buf, want)
+            worst = max(worst, u)
+            assert u <= 2, (c, u)
+    print("gaussian max ulp over goldens:", worst)
+
+
+def test_fill_dense_sweep_vs_oracle(gpu, port):
+    rng = np.random.default_rng(11)
+    for it in range(80):
+        r, c = int(rng.integers(1, 70)), int(rng.integers(1, 300))
+        if rng.integers(2):
+            r, c = c, r
+        fam, ax, lay = "GU"[rng.integers(2)], "LS"[rng.integers(2)], "RC"[rng.integers(2)]
+        nr, nc = int(rng.integers(1, r + 1)), int(rng.integers(1, c + 1))
+        ro, co = int(rng.integers(0, r - nr + 1)), int(rng.integers(0, c - nc + 1))
+        ctr, key = ol.state_from_u64(int(rng.integers(0, 1 << 62)))
+        ctr = ol.ctr_add(ctr, int(rng.integers(0, 1 << 63)) if it % 3 else (1 << 64) - 3)
+        dt = (np.float32, np.float64)[it % 2]
+        a, n1 = gpu.fill_dense_unpacked(lay, r, c, fam, ax, nr, nc, ro, co, ctr, key, dt)
+        b, n2 = port.fill_dense_unpacked(lay, r, c, fam, ax, nr, nc, ro, co, ctr, key, dt)
+        assert list(n1) == list(n2)
+        if fam == "U":
+            assert np.array_equal(a.view(np.uint8), b.view(np.uint8)), (r, c, fam, ax, lay, nr, nc, ro, co)
+        else:
+            assert ulp_diff_f32(a, b) <= 2
+
+
+def test_fill_dense_leading_dimension_and_untouched_padding(gpu, port):
+    ctr, key = ol.state_from_u64(5)
+    for lay in "RC":
+        nr, nc, ld = 9, 13, 17
+        a, _ = gpu.fill_dense_unpacked(lay, 20, 40, "U", "L", nr, nc, 3, 5, ctr, key, np.float32, ld=ld)
+        b, _ = port.fill_dense_unpacked(lay, 20, 40, "U", "L", nr, nc, 3, 5, ctr, key, np.float32)
+        outer, inner = (nr, nc) if lay == "R" else (nc, nr)
+        a = a.reshape(outer, ld)
+        assert np.array_equal(a[:, :inner].ravel(), b)
+        assert np.all(a[:, inner:] == -777.0)
+
+
+def test_fill_dense_large_slices_of_benchmark_operator(gpu, port):
+    """Slices of the 8192 x 1,000,000 Gaussian double operator (config 2) and of the 1024 x 100000 uniform float
+    operator (config 1), deep inside the counter space; > 1e7 samples compared per family."""
+    ctr, key = ol.state_from_u64(1997)
+    worst = 0
+    for (ro, co, nr, nc) in [(0, 0, 8, 1000000), (8191, 0, 1, 1000000), (4000, 999000, 40, 1000), (17, 123457, 3, 500003)]:
+        a, n1 = gpu.fill_dense_unpacked("R", 8192, 1000000, "G", "L", nr, nc, ro, co, ctr, key, np.float64)
+        b, n2 = port.fill_dense_unpacked("R", 8192, 1000000, "G", "L", nr, nc, ro, co, ctr, key, np.float64)
+        assert list(n1) == list(n2)
+        worst = max(worst, ulp_diff_f32(a, b))
+    print("gaussian max float-ulp vs host libm on benchmark slices:", worst)
+    assert worst <= 2
+    a, _ = gpu.fill_dense_unpacked("R", 1024, 100000, "U", "L", 100, 100000, 500, 0, ctr, key, np.float32)
+    b, _ = port.fill_dense_unpacked("R", 1024, 100000, "U", "L", 100, 100000, 500, 0, ctr, key, np.float32)
+    assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+
+
+def test_fill_dense_properties_from_reference_tests(gpu):
+    """test_denseskop.cc:162-298 (submatrix == slice of the full matrix), :344-403 (wide == tall^T),
+    :410-441 (concatenation via next_state)."""
+    ctr, key = ol.state_from_u64(0)
+    for fam, ax in itertools.product("GU", "LS"):
+        full, nxt = gpu.fill_dense_unpacked("R", 100, 2000, fam, ax, 100, 2000, 0, 0, ctr, key, np.float32)
+        full = full.reshape(100, 2000)
+        for (nr, nc, ro, co) in [(10, 200, 5, 13), (100, 1, 0, 1999), (1, 2000, 99, 0), (37, 41, 63, 1959)]:
+            sub, _ = gpu.fill_dense_unpacked("R", 100, 2000, fam, ax, nr, nc, ro, co, ctr, key, np.float32)
+            assert np.array_equal(sub.reshape(nr, nc), full[ro:ro + nr, co:co + nc])
+        tall, _ = gpu.fill_dense_unpacked("R", 2000, 100, fam, ax, 2000, 100, 0, 0, ctr, key, np.float32)
+        assert np.array_equal(tall.reshape(2000, 100).T, full)
+    # test_denseskop.cc:410-441: tall operators with Long major axis concatenate along columns when the second
+    # one is seeded with the first one's next_state
+    for (nr, nc) in [(13, 7), (80, 40), (83, 41), (97, 47)]:
+        for seed in (0, 1, 2):
+            c0, k0 = ol.state_from_u64(seed)
+            s1, n1 = gpu.fill_dense_unpacked("C", nr, nc // 2, "G", "L", nr, nc // 2, 0, 0, c0, k0, np.float64)
+            s2, _ = gpu.fill_dense_unpacked("C", nr, nc - nc // 2, "G", "L", nr, nc - nc // 2, 0, 0, n1, k0, np.float64)
+            big, _ = gpu.fill_dense_unpacked("C", nr, nc, "G", "L", nr, nc, 0, 0, c0, k0, np.float64)
+            assert np.array_equal(np.concatenate([s1, s2]), big)
+
+
+def test_host_buffers_equal_device_buffers(gpu, gpu_host):
+    ctr, key = ol.state_from_u64(3)
+    a, n1 = gpu.fill_dense_unpacked("C", 50, 70, "G", "L", 20, 30, 4, 5, ctr, key, np.float64)
+    b, n2 = gpu_host.fill_dense_unpacked("C", 50, 70, "G", "L", 20, 30, 4, 5, ctr, key, np.float64)
+    assert np.array_equal(a, b) and list(n1) == list(n2)
+    x = gpu.fill_sparse(30, 400, 5, "S", ctr, key, np.float32, np.int32)
+    y = gpu_host.fill_sparse(30, 400, 5, "S", ctr, key, np.float32, np.int32)
+    for p, q in zip(x, y):
+        assert np.array_equal(p, q)
+
+
+# ------------------------------------------------------------------------------------------ SASO
+def test_saso_goldens(gpu, gold):
+    for c in gold.m["saso"]:
+        r, cc, vn, ax = c["D"]
+        idt = np.dtype(c["idx"])
+        for dt in (np.float32, np.float64):
+            vals, rows, cols, nnz, nxt = gpu.fill_sparse(r, cc, vn, ax, c["ctr"], c["key"], dt, idt)
+            assert nnz == c["nnz"] and list(nxt) == c["next_ctr"]
+            assert np.array_equal(vals.astype(np.int8), gold.arr(c["vals"]))
+            assert np.array_equal(rows.astype(np.int32), gold.arr(c["rows"]))
+            assert np.array_equal(cols.astype(np.int32), gold.arr(c["cols"]))
+    for c in gold.m["rfy"]:
+        s, nxt = gpu.repeated_fisher_yates(c["k"], c["n"], c["r"], c["ctr"], c["key"])
+        assert np.array_equal(s.astype(np.int32), gold.arr(c["samples"])) and list(nxt) == c["next_ctr"]
+
+
+def test_saso_sweep_vs_oracle(gpu, port):
+    rng = np.random.default_rng(2)
+    shapes = [(7, 20, 3), (20, 7, 7), (1, 9, 1), (64, 64, 64), (40, 1000, 33), (2048, 20000, 8), (300, 5, 5),
+              (100, 100000, 32), (33, 50, 1)]
+    for (r, c, k) in shapes:
+        ctr, key = ol.state_from_u64(int(rng.integers(0, 1 << 62)))
+        ctr = ol.ctr_add(ctr, (1 << 32) - 7)
+        for idt in (np.int32, np.int64):
+            a = gpu.fill_sparse(r, c, k, "S", ctr, key, np.float32, idt)
+            b = port.fill_sparse(r, c, k, "S", ctr, key, np.float32, idt)
+            for x, y in zip(a, b):
+                assert np.array_equal(x, y), (r, c, k)
+    # every short-axis vector holds vec_nnz distinct indices (test_sparseskop.cc:64-117)
+    vals, rows, cols, nnz, _ = gpu.fill_sparse(2048, 50000, 8, "S", *ol.state_from_u64(1), np.float32, np.int64)
+    rr = rows.reshape(-1, 8)
+    assert np.all(np.sort(rr, axis=1)[:, 1:] != np.sort(rr, axis=1)[:, :-1])
+    assert rr.min() >= 0 and rr.max() < 2048 and np.array_equal(cols.reshape(-1, 8)[:, 0], np.arange(50000))
+    assert set(np.unique(vals)) == {-1.0, 1.0}
+
+
+# --------------------------------------------------------------------------------------- sketches
+def test_sketch_goldens(gpu, port, gold):
+    for c in gold.m["sketch"]:
+        A, lda, B, ldb = sketch_case_inputs(port.fill_dense_unpacked, c)
+        run_sketch_case(gpu, c, A, lda, B, ldb)
+        want = gold.arr(c["B"])
+        err = relerr(B, want)
+        assert err < TOL[np.dtype(c["dtype"])], (c["kind"], c["dtype"], c["layout"], c["opS"], c["opA"], err)
+
+
+def _mk(rng, rows, cols, lay, pad, dt):
+    ld = (rows if lay == "C" else cols) + pad
+    outer = cols if lay == "C" else rows
+    return rng.standard_normal(outer * ld).astype(dt), ld
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+def test_dense_operator_sketch_all_variants_vs_oracle(gpu, port, dt):
+    rng = np.random.default_rng(0)
+    ctr, key = ol.state_from_u64(1997)
+    tol = TOL[np.dtype(dt)]
+    for lay, opS, opA in itertools.product("RC", "NT", "NT"):
+        for fam, ax in (("G", "L"), ("U", "S"), ("G", "S")):
+            d, n, m = 37, 29, 211
+            Dr, Dc = (d + 3, m + 6) if opS == "N" else (m + 6, d + 3)
+            ro, co = 2, 5
+            rA, cA = (m, n) if opA == "N" else (n, m)
+            A, lda = _mk(rng, rA, cA, lay, 2, dt)
+            B0, ldb = _mk(rng, d, n, lay, 1, dt)
+            for alpha, beta in ((1.0, 0.0), (0.5, -1.5)):
+                B1, B2 = B0.copy(), B0.copy()
+                gpu.lskge3(lay, opS, opA, d, n, m, dt(alpha), (Dr, Dc, fam, ax), ctr, key, ro, co, A, lda, dt(beta), B1, ldb)
+                port.lskge3(lay, opS, opA, d, n, m, dt(alpha), (Dr, Dc, fam, ax), ctr, key, ro, co, A, lda, dt(beta), B2, ldb)
+                assert relerr(B1, B2) < tol, ("lskge3", lay, opS, opA, fam, ax, relerr(B1, B2))
+            mm, dd, nn = 23, 19, 157
+            Dr, Dc = (nn + 2, dd + 3) if opS == "N" else (dd + 3, nn + 2)
+            ro, co = 1, 2
+            rA, cA = (mm, nn) if opA == "N" else (nn, mm)
+            A, lda = _mk(rng, rA, cA, lay, 1, dt)
+            B0, ldb = _mk(rng, mm, dd, lay, 2, dt)
+            for alpha, beta in ((1.0, 0.0), (0.5, -1.5)):
+                B1, B2 = B0.copy(), B0.copy()
+                gpu.rskge3(lay, opA, opS, mm, dd, nn, dt(alpha), A, lda, (Dr, Dc, fam, ax), ctr, key, ro, co, dt(beta), B1, ldb)
+                port.rskge3(lay, opA, opS, mm, dd, nn, dt(alpha), A, lda, (Dr, Dc, fam, ax), ctr, key, ro, co, dt(beta), B2, ldb)
+                assert relerr(B1, B2) < tol, ("rskge3", lay, opS, opA, fam, ax, relerr(B1, B2))
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+def test_prefilled_operator_equals_fused(gpu, dt):
+    """S.buff != nullptr takes the read-S path (reference: blas::gemm branch, skge.hh:194-200)."""
+    rng = np.random.default_rng(1)
+    ctr, key = ol.state_from_u64(9)
+    for lay, opS, ax in itertools.product("RC", "NT", "LS"):
+        d, n, m = 33, 17, 130
+        Dr, Dc = (d + 1, m + 4) if opS == "N" else (m + 4, d + 1)
+        A, lda = _mk(rng, m, n, lay, 0, dt)
+        B1 = np.zeros((d if lay == "C" else n) * (n if lay == "C" else d), dt)
+        B2 = B1.copy()
+        ldb = d if lay == "C" else n
+        gpu.lskge3(lay, opS, "N", d, n, m, dt(1), (Dr, Dc, "G", ax), ctr, key, 1, 3, A, lda, dt(0), B1, ldb, prefill=0)
+        gpu.lskge3(lay, opS, "N", d, n, m, dt(1), (Dr, Dc, "G", ax), ctr, key, 1, 3, A, lda, dt(0), B2, ldb, prefill=1)
+        assert relerr(B1, B2) < TOL[np.dtype(dt)]
+
+
+def test_sketch_identity_reproduces_operator(gpu, port):
+    """linop_common.hh:309-389: applying the operator to the identity must reproduce S (here: exactly for the
+    float path up to the 3xTF32 split, so compared with tolerance 1e-6)."""
+    ctr, key = ol.state_from_u64(42)
+    d, m = 51, 201
+    I = np.eye(m, dtype=np.float32).ravel()
+    B = np.zeros(d * m, np.float32)
+    gpu.lskge3("R", "N", "N", d, m, m, np.float32(1), (d, m, "G", "L"), ctr, key, 0, 0, I, m, np.float32(0), B, m)
+    S, _ = port.fill_dense_unpacked("R", d, m, "G", "L", d, m, 0, 0, ctr, key, np.float32)
+    assert relerr(B, S) < 1e-6
+
+
+def test_sketch_vector_vs_oracle(gpu, port):
+    import randblas_b200 as rb
+    import torch
+    ctr, key = ol.state_from_u64(77)
+    for dt in (np.float32, np.float64):
+        for opS in "NT":
+            d, m = 40, 300
+            S = rb.DenseSkOp(rb.DenseDist(d, m, "G", "L"), rb.RNGState(counter=list(ctr), key=list(key)), dt)
+            nx = m if opS == "N" else d
+            ny = d if opS == "N" else m
+            x = np.random.default_rng(3).standard_normal(nx * 2).astype(dt)
+            y0 = np.random.default_rng(4).standard_normal(ny * 3).astype(dt)
+            xt, yt = torch.from_numpy(x).cuda(), torch.from_numpy(y0.copy()).cuda()
+            rb.sketch_vector(opS, dt(0.5), S, xt, 2, dt(2.0), yt, 3)
+            want = y0.copy()
+            # sketch_vector == sketch_general(RowMajor, opS, NoTrans, d', 1, m', ..., x, incx, ..., y, incy)  (skve.hh:141-164)
+            port.lskge3("R", opS, "N", ny, 1, nx, dt(0.5), (d, m, "G", "L"), ctr, key, 0, 0, x, 2, dt(2.0), want, 3)
+            assert relerr(yt.cpu().numpy(), want) < TOL[np.dtype(dt)]
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+def test_sparse_operator_sketch_all_variants_vs_oracle(gpu, port, dt):
+    rng = np.random.default_rng(0)
+    ctr, key = ol.state_from_u64(1997)
+    tol = TOL[np.dtype(dt)]
+    for lay, opS, opA in itertools.product("RC", "NT", "NT"):
+        for vn in (1, 3, 40):
+            d, n, m = 45, 29, 211
+            Dr, Dc = (d + 3, m + 6) if opS == "N" else (m + 6, d + 3)
+            ro, co = 2, 5
+            rA, cA = (m, n) if opA == "N" else (n, m)
+            A, lda = _mk(rng, rA, cA, lay, 2, dt)
+            B0, ldb = _mk(rng, d, n, lay, 1, dt)
+            for alpha, beta in ((1.0, 0.0), (0.5, -1.5)):
+                B1, B2 = B0.copy(), B0.copy()
+                gpu.lskges(lay, opS, opA, d, n, m, dt(alpha), (Dr, Dc, vn, "S"), ctr, key, ro, co, A, lda, dt(beta), B1, ldb)
+                port.lskges(lay, opS, opA, d, n, m, dt(alpha), (Dr, Dc, vn, "S"), ctr, key, ro, co, A, lda, dt(beta), B2, ldb)
+                assert relerr(B1, B2) < tol, ("lskges", lay, opS, opA, vn, relerr(B1, B2))
+            mm, dd, nn = 23, 41, 157
+            Dr, Dc = (nn + 2, dd + 3) if opS == "N" else (dd + 3, nn + 2)
+            rA, cA = (mm, nn) if opA == "N" else (nn, mm)
+            A, lda = _mk(rng, rA, cA, lay, 1, dt)
+            B0, ldb = _mk(rng, mm, dd, lay, 2, dt)
+            B1, B2 = B0.copy(), B0.copy()
+            gpu.rskges(lay, opA, opS, mm, dd, nn, dt(0.5), A, lda, (Dr, Dc, vn, "S"), ctr, key, 1, 2, dt(-1.5), B1, ldb)
+            port.rskges(lay, opA, opS, mm, dd, nn, dt(0.5), A, lda, (Dr, Dc, vn, "S"), ctr, key, 1, 2, dt(-1.5), B2, ldb)
+            assert relerr(B1, B2) < tol, ("rskges", lay, opS, opA, vn, relerr(B1, B2))
+    # an already-sampled operator (COO arrays on the device) gives the same product
+    B1 = np.zeros(45 * 29, dt); B2 = B1.copy()
+    A, lda = _mk(rng, 211, 29, "R", 0, dt)
+    gpu.lskges("R", "N", "N", 45, 29, 211, dt(1), (45, 211, 4, "S"), ctr, key, 0, 0, A, lda, dt(0), B1, 29, prefill=0)
+    gpu.lskges("R", "N", "N", 45, 29, 211, dt(1), (45, 211, 4, "S"), ctr, key, 0, 0, A, lda, dt(0), B2, 29, prefill=1)
+    assert relerr(B1, B2) < tol
+
+
+def _sp(mat, fmt, dt):
+    if fmt == 0:
+        m = mat.tocsr()
+        return (m.shape[0], m.shape[1], m.nnz, m.data.astype(dt), m.indptr.astype(np.int64), m.indices.astype(np.int64))
+    if fmt == 1:
+        m = mat.tocsc()
+        return (m.shape[0], m.shape[1], m.nnz, m.data.astype(dt), m.indices.astype(np.int64), m.indptr.astype(np.int64))
+    m = mat.tocoo()
+    return (m.shape[0], m.shape[1], m.nnz, m.data.astype(dt), m.row.astype(np.int64), m.col.astype(np.int64))
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+def test_sketch_sparse_all_variants_vs_oracle(gpu, port, dt):
+    import scipy.sparse as sp
+    rng = np.random.default_rng(0)
+    ctr, key = ol.state_from_u64(1997)
+    tol = TOL[np.dtype(dt)]
+    for lay, opS, opA in itertools.product("RC", "NT", "NT"):
+        d, n, m = 37, 53, 119
+        ra, ca = (m, n) if opA == "N" else (n, m)
+        M = sp.random(ra, ca, density=0.15, random_state=1, dtype=np.float64)
+        for fmt in (0, 1, 2):
+            for fam, ax, idt in (("G", "L", np.int64), ("U", "S", np.int32)):
+                spA = _sp(M, fmt, dt)
+                Dr, Dc = (d + 1, m + 2) if opS == "N" else (m + 2, d + 1)
+                B0, ldb = _mk(rng, d, n, lay, 1, dt)
+                for alpha, beta in ((1.0, 0.0), (0.5, -1.5)):
+                    B1, B2 = B0.copy(), B0.copy()
+                    gpu.lsksp3(fmt, lay, opS, opA, d, n, m, dt(alpha), (Dr, Dc, fam, ax), ctr, key, 1, 1, spA, dt(beta), B1, ldb, idx_dtype=idt)
+                    port.lsksp3(fmt, lay, opS, opA, d, n, m, dt(alpha), (Dr, Dc, fam, ax), ctr, key, 1, 1, spA, dt(beta), B2, ldb)
+                    assert relerr(B1, B2) < tol, ("lsksp3", fmt, lay, opS, opA, fam, relerr(B1, B2))
+        mm, dd, nn = 31, 24, 97
+        ra, ca = (mm, nn) if opA == "N" else (nn, mm)
+        M = sp.random(ra, ca, density=0.15, random_state=2, dtype=np.float64)
+        for fmt in (0, 1, 2):
+            spA = _sp(M, fmt, dt)
+            Dr, Dc = (nn + 1, dd + 2) if opS == "N" else (dd + 2, nn + 1)
+            B0, ldb = _mk(rng, mm, dd, lay, 1, dt)
+            B1, B2 = B0.copy(), B0.copy()
+            gpu.rsksp3(fmt, lay, opA, opS, mm, dd, nn, dt(0.5), spA, (Dr, Dc, "G", "L"), ctr, key, 1, 1, dt(-1.5), B1, ldb)
+            port.rsksp3(fmt, lay, opA, opS, mm, dd, nn, dt(0.5), spA, (Dr, Dc, "G", "L"), ctr, key, 1, 1, dt(-1.5), B2, ldb)
+            assert relerr(B1, B2) < tol, ("rsksp3", fmt, lay, opS, opA, relerr(B1, B2))
+
+
+def test_sketch_with_host_buffers(gpu, gpu_host):
+    rng = np.random.default_rng(8)
+    ctr, key = ol.state_from_u64(2)
+    A, lda = _mk(rng, 300, 20, "C", 3, np.float32)
+    B0, ldb = _mk(rng, 24, 20, "C", 2, np.float32)
+    B1, B2 = B0.copy(), B0.copy()
+    gpu.lskge3("C", "N", "N", 24, 20, 300, np.float32(1), (24, 300, "G", "L"), ctr, key, 0, 0, A, lda, np.float32(0.5), B1, ldb)
+    gpu_host.lskge3("C", "N", "N", 24, 20, 300, np.float32(1), (24, 300, "G", "L"), ctr, key, 0, 0, A, lda, np.float32(0.5), B2, ldb)
+    assert np.array_equal(B1, B2)   # same kernel, same bits; padding rows of B untouched on the host path too
+    B1, B2 = B0.copy(), B0.copy()
+    gpu.lskges("C", "N", "N", 24, 20, 300, np.float32(1), (24, 300, 3, "S"), ctr, key, 0, 0, A, lda, np.float32(0), B1, ldb)
+    gpu_host.lskges("C", "N", "N", 24, 20, 300, np.float32(1), (24, 300, 3, "S"), ctr, key, 0, 0, A, lda, np.float32(0), B2, ldb)
+    assert relerr(B1, B2) < 1e-6
+
+
+# ------------------------------------------------------------------- size-independent properties
+def test_dense_sketch_properties_at_scale(gpu):
+    """Medium-size checks that do not need the oracle: linearity in A, additivity over row blocks of A with
+    co_s offsets and beta = 1 (the m-sharded / blocked form, sketch_updates.rst:198-213), and agreement of the
+    tensor-core and generic kernels."""
+    import torch
+    import randblas_b200 as rb
+    torch.manual_seed(0)
+    for dt, tol in ((torch.float32, 1e-5), (torch.float64, 1e-12)):
+        d, n, m = 256, 192, 20000
+        S = rb.DenseSkOp(rb.DenseDist(d, m, "G" if dt == torch.float64 else "U"), rb.RNGState(1997), dt)
+        A1 = torch.randn(m * n, dtype=dt, device="cuda")
+        A2 = torch.randn(m * n, dtype=dt, device="cuda")
+
+        def sk(A, **kw):
+            B = torch.zeros(d * n, dtype=dt, device="cuda")
+            rb.sketch_general("C", "N", "N", d, n, m, 1.0, S, 0, 0, A, m, 0.0, B, d)
+            return B
+        B1, B2, B12 = sk(A1), sk(A2), sk(A1 + 2 * A2)
+        assert ((B12 - (B1 + 2 * B2)).norm() / B12.norm()).item() < 4 * tol
+        # row blocks of A (ColMajor A: a row block is a strided view) accumulate with beta = 1
+        Bacc = torch.zeros(d * n, dtype=dt, device="cuda")
+        blk = 5000
+        for r0 in range(0, m, blk):
+            rb.sketch_general("C", "N", "N", d, n, blk, 1.0, S, 0, r0, A1[r0:], m, 1.0 if r0 else 0.0, Bacc, d)
+        assert ((Bacc - B1).norm() / B1.norm()).item() < 4 * tol
+        # generic kernel agrees with the default (tensor-core) dispatch
+        rb.set_option("dense_path", 1)
+        try:
+            Bg = sk(A1)
+        finally:
+            rb.set_option("dense_path", 0)
+        assert ((Bg - B1).norm() / B1.norm()).item() < 4 * tol
+
+
+def test_argument_errors_on_gpu(gpu):
+    import randblas_b200 as rb
+    import torch
+    S = rb.DenseSkOp(rb.DenseDist(8, 64), rb.RNGState(0))
+    A = torch.zeros(64 * 4, device="cuda")
+    B = torch.zeros(8 * 4, device="cuda")
+    with pytest.raises(rb.RandBLASError):
+        rb.sketch_general("C", "N", "N", 8, 4, 64, 1.0, S, 1, 0, A, 64, 0.0, B, 8)      # window leaves the operator
+    with pytest.raises(rb.RandBLASError):
+        rb.sketch_general("R", "N", "N", 8, 4, 64, 1.0, S, 0, 0, A, 3, 0.0, B, 4)       # lda < cols_A
+    Ssp = rb.SparseSkOp(rb.SparseDist(8, 64, 4, rb.Axis.Long), rb.RNGState(0))
+    with pytest.raises(rb.RandBLASError):
+        rb.sketch_general("C", "N", "N", 8, 4, 64, 1.0, Ssp, 0, 0, A, 64, 0.0, B, 8)    # LASO not built
