@@ -90,6 +90,77 @@ __global__ void __launch_bounds__(256) fill_dense_kernel(const FillArgs a, T* __
     }
 }
 
+// Fast path for long vectors: a tile is FILL_UNROLL x 256 consecutive blocks of ONE vector, so the counter of
+// a block is (tile-uniform 128-bit base) + (small offset) and the destination pointer is base + 4 * offset.
+// Tiles whose blocks are all interior and 4-element aligned take a predicate-free store path.
+constexpr int FILL_UNROLL = 4;
+
+struct FillTileArgs {
+    Ctr128 ctr;
+    PhiloxKey key;
+    int64_t R, v0, nv, u0, nu, blk_first, nblk, sv;
+    int64_t tiles_per_vec, total_tiles;
+    int64_t q_step, r_step;     // gridDim.x = q_step * tiles_per_vec + r_step
+};
+
+template <typename T, bool GAUSS>
+__global__ void __launch_bounds__(256, 3) fill_dense_tiled_kernel(const FillTileArgs a, T* __restrict__ dst) {
+    __shared__ __align__(16) double logtab[32];
+    if constexpr (GAUSS) {
+        load_logf_table(logtab);
+        __syncthreads();
+    }
+    int64_t t = blockIdx.x;
+    if (t >= a.total_tiles) return;
+    int64_t vl = t / a.tiles_per_vec;
+    int64_t ch = t - vl * a.tiles_per_vec;
+    constexpr int64_t TILE = 256 * FILL_UNROLL;
+    for (; t < a.total_tiles; t += gridDim.x) {
+        const int64_t b0 = ch * TILE;                                  // first block of the tile (window-relative)
+        const Ctr128 base = ctr_add(a.ctr, (uint64_t) ((a.v0 + vl) * a.R + a.blk_first + b0));
+        const uint64_t base_lo = ((uint64_t) base.c1 << 32) | base.c0;
+        const uint64_t base_hi = ((uint64_t) base.c3 << 32) | base.c2;
+        const int64_t ur0 = (a.blk_first + b0) * 4 - a.u0;             // position of the tile's first sample
+        T* p0 = dst + vl * a.sv + ur0;
+        const int64_t nb = min((int64_t) TILE, a.nblk - b0);           // blocks in this tile
+        const bool interior = (ur0 >= 0) && (ur0 + 4 * nb <= a.nu) &&
+                              ((reinterpret_cast<uintptr_t>(p0) & (4 * sizeof(T) - 1)) == 0);
+        if (interior && nb == TILE) {
+#pragma unroll
+            for (int j = 0; j < FILL_UNROLL; ++j) {
+                const uint32_t off = j * 256 + threadIdx.x;
+                const uint64_t lo = base_lo + off;
+                const uint64_t hi = base_hi + (lo < base_lo ? 1ull : 0ull);
+                const Ctr128 c{(uint32_t) lo, (uint32_t) (lo >> 32), (uint32_t) hi, (uint32_t) (hi >> 32)};
+                const float4 f = transform4<GAUSS>(philox4x32_10(c, a.key), logtab);
+                store4_vec<T>(p0 + 4 * off, finish_sample<T, GAUSS>(f.x), finish_sample<T, GAUSS>(f.y),
+                              finish_sample<T, GAUSS>(f.z), finish_sample<T, GAUSS>(f.w));
+            }
+        } else {
+            for (int j = 0; j < FILL_UNROLL; ++j) {
+                const int64_t off = j * 256 + threadIdx.x;
+                if (off >= nb) break;
+                const Ctr128 c = ctr_add(base, (uint64_t) off);
+                const float4 f = transform4<GAUSS>(philox4x32_10(c, a.key), logtab);
+                const T x0 = finish_sample<T, GAUSS>(f.x), x1 = finish_sample<T, GAUSS>(f.y),
+                        x2 = finish_sample<T, GAUSS>(f.z), x3 = finish_sample<T, GAUSS>(f.w);
+                const int64_t ur = ur0 + 4 * off;
+                T* p = p0 + 4 * off;
+                if (ur >= 0 && ur + 4 <= a.nu && ((reinterpret_cast<uintptr_t>(p) & (4 * sizeof(T) - 1)) == 0)) {
+                    store4_vec<T>(p, x0, x1, x2, x3);
+                } else {
+                    if (ur + 0 >= 0 && ur + 0 < a.nu) p[0] = x0;
+                    if (ur + 1 >= 0 && ur + 1 < a.nu) p[1] = x1;
+                    if (ur + 2 >= 0 && ur + 2 < a.nu) p[2] = x2;
+                    if (ur + 3 >= 0 && ur + 3 < a.nu) p[3] = x3;
+                }
+            }
+        }
+        ch += a.r_step; vl += a.q_step;
+        if (ch >= a.tiles_per_vec) { ch -= a.tiles_per_vec; vl += 1; }
+    }
+}
+
 __global__ void philox_words_kernel(Ctr128 ctr, PhiloxKey key, int64_t n_blocks, uint4* __restrict__ out) {
     for (int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i < n_blocks;
          i += (int64_t) gridDim.x * blockDim.x)
@@ -122,6 +193,24 @@ int launch_fill_dense(const DenseGen& g, char family, int64_t v0, int64_t nv, in
     a.total = nv * a.nblk;
     // lanes walk whichever direction is contiguous in memory
     const bool walk_v = (su != 1) && (sv == 1 || sv < su);
+    const bool gauss_ = family == 'G';
+    if (!walk_v && su == 1 && a.nblk >= 2 * 256 * FILL_UNROLL) {
+        FillTileArgs t;
+        t.ctr = g.ctr; t.key = g.key; t.R = g.R; t.v0 = v0; t.nv = nv; t.u0 = u0; t.nu = nu;
+        t.blk_first = a.blk_first; t.nblk = a.nblk; t.sv = sv;
+        t.tiles_per_vec = (a.nblk + 256 * FILL_UNROLL - 1) / (256 * FILL_UNROLL);
+        t.total_tiles = nv * t.tiles_per_vec;
+        int64_t tgrid = t.total_tiles;
+        const int64_t tcap = (int64_t) sm_count() * 6;
+        if (tgrid > tcap) tgrid = tcap;
+        t.q_step = tgrid / t.tiles_per_vec;
+        t.r_step = tgrid % t.tiles_per_vec;
+        if (gauss_) fill_dense_tiled_kernel<T, true><<<(unsigned) tgrid, 256, 0, st>>>(t, dst);
+        else fill_dense_tiled_kernel<T, false><<<(unsigned) tgrid, 256, 0, st>>>(t, dst);
+        count_launch();
+        RB_CUDA(cudaGetLastError());
+        return 0;
+    }
     int64_t grid = (a.total + 255) / 256;
     const int64_t cap = (int64_t) sm_count() * 8;      // 8 CTAs of 256 threads per SM, then grid-stride
     if (grid > cap) grid = cap;

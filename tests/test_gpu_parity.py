@@ -241,7 +241,7 @@ def test_dense_operator_sketch_all_variants_vs_oracle(gpu, port, dt):
         for fam, ax in (("G", "L"), ("U", "S"), ("G", "S")):
             d, n, m = 37, 29, 211
             Dr, Dc = (d + 3, m + 6) if opS == "N" else (m + 6, d + 3)
-            ro, co = 2, 5
+            ro, co = (2, 5) if opS == "N" else (5, 2)
             rA, cA = (m, n) if opA == "N" else (n, m)
             A, lda = _mk(rng, rA, cA, lay, 2, dt)
             B0, ldb = _mk(rng, d, n, lay, 1, dt)
@@ -271,12 +271,13 @@ def test_prefilled_operator_equals_fused(gpu, dt):
     for lay, opS, ax in itertools.product("RC", "NT", "LS"):
         d, n, m = 33, 17, 130
         Dr, Dc = (d + 1, m + 4) if opS == "N" else (m + 4, d + 1)
+        off = (1, 3) if opS == "N" else (3, 1)
         A, lda = _mk(rng, m, n, lay, 0, dt)
         B1 = np.zeros((d if lay == "C" else n) * (n if lay == "C" else d), dt)
         B2 = B1.copy()
         ldb = d if lay == "C" else n
-        gpu.lskge3(lay, opS, "N", d, n, m, dt(1), (Dr, Dc, "G", ax), ctr, key, 1, 3, A, lda, dt(0), B1, ldb, prefill=0)
-        gpu.lskge3(lay, opS, "N", d, n, m, dt(1), (Dr, Dc, "G", ax), ctr, key, 1, 3, A, lda, dt(0), B2, ldb, prefill=1)
+        gpu.lskge3(lay, opS, "N", d, n, m, dt(1), (Dr, Dc, "G", ax), ctr, key, *off, A, lda, dt(0), B1, ldb, prefill=0)
+        gpu.lskge3(lay, opS, "N", d, n, m, dt(1), (Dr, Dc, "G", ax), ctr, key, *off, A, lda, dt(0), B2, ldb, prefill=1)
         assert relerr(B1, B2) < TOL[np.dtype(dt)]
 
 
@@ -321,7 +322,7 @@ def test_sparse_operator_sketch_all_variants_vs_oracle(gpu, port, dt):
         for vn in (1, 3, 40):
             d, n, m = 45, 29, 211
             Dr, Dc = (d + 3, m + 6) if opS == "N" else (m + 6, d + 3)
-            ro, co = 2, 5
+            ro, co = (2, 5) if opS == "N" else (5, 2)
             rA, cA = (m, n) if opA == "N" else (n, m)
             A, lda = _mk(rng, rA, cA, lay, 2, dt)
             B0, ldb = _mk(rng, d, n, lay, 1, dt)
