@@ -17,6 +17,7 @@ static thread_local std::string g_err;
 static std::atomic<int64_t> g_launches{0};
 static std::atomic<int64_t> g_dense_path{0};
 static std::atomic<int64_t> g_tc_launches{0};
+static std::atomic<int64_t> g_tc_splits{0};
 
 void set_error(const std::string& m) { g_err = m; }
 int fail(const std::string& m) { g_err = m; return RB_ERR_ARG; }
@@ -41,6 +42,7 @@ int sm_count() {
 
 int64_t get_option(const char* name) {
     if (!std::strcmp(name, "dense_path")) return g_dense_path.load();
+    if (!std::strcmp(name, "tc_splits")) return g_tc_splits.load();
     return 0;
 }
 
@@ -681,6 +683,7 @@ RB_DEF_T(double, f64)
 int rb_set_option(const char* name, int64_t value) {
     RB_REQUIRE(name != nullptr);
     if (!std::strcmp(name, "dense_path")) { g_dense_path = value; return 0; }
+    if (!std::strcmp(name, "tc_splits")) { g_tc_splits = value; return 0; }
     return fail(std::string("unknown option ") + name);
 }
 int64_t rb_get_counter(const char* name) {

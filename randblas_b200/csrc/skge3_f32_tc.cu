@@ -1,6 +1,446 @@
-// placeholder until the tcgen05 kernel lands: reports "shape not supported" so callers use the generic kernel
+// K2a: fused generate-and-multiply dense sketch for float on the 5th-generation tensor cores (3xTF32).
+//
+// Replaces dense::lskge3 / rskge3 (RandBLAS/skge.hh:154-202, 307-355) for float when the operator is not
+// materialised: the reference first fills a d x m host buffer (submatrix_as_blackbox, dense_skops.hh:677-688)
+// and then calls blas::gemm (skge.hh:200); here each 128 x 32 tile of S is regenerated from
+// (key, counter, ro_s, co_s) straight into shared memory in the K-major 128B-swizzled layout tcgen05 reads,
+// already split into its two TF32 terms, so S never touches HBM.
+//
+// Canonical problem (see kernels.h): C(P x Q) = alpha * X(P x K) * Y(K x Q) + beta * C with X = op(S window).
+// One CTA owns a 128 x 256 tile of C and one K range (split-K over blockIdx.z):
+//   warp 0      : TMA producer. Y tiles (256 columns x 32 k, K contiguous) land in shared memory, 128B swizzle.
+//   warp 1      : allocates 256 TMEM columns; one thread issues tcgen05.mma kind::tf32, cta_group::1, M=128,
+//                 N=256, K=8: per 8-deep slice three MMAs  X_lo*Y_hi + X_hi*Y_lo + X_hi*Y_hi  (3xTF32: fp32
+//                 operands are split x = hi + lo with hi, lo exactly representable in TF32; the dropped lo*lo
+//                 term is 2^-22 relative). The accumulator (128 lanes x 256 fp32 columns) lives in TMEM.
+//   warps 2..9  : generators. Per K step: Philox4x32-10 + uneg11/Box-Muller for the X tile -> (hi, lo) ->
+//                 swizzled st.shared; then Y_lo = Y - trunc_tf32(Y) for the tile TMA just delivered (the tensor
+//                 core ignores the 13 low mantissa bits of its 32-bit operands, so the raw tile IS Y_hi).
+//                 After the last K step the same warps run the epilogue: tcgen05.ld -> alpha/beta -> global.
+// Pipeline: 2 stages of {X_hi, X_lo, Y, Y_lo} = 96 KB each; mbarriers full_y (TMA -> consumers),
+// ready (generators -> MMA), empty (tcgen05.commit -> producers), accum (last commit -> epilogue).
+// Split-K partial tiles go to a workspace and are summed in a fixed order by a second small kernel, so the
+// result does not depend on the grid (the reference guarantees thread-count invariance, dense_skops.hh:90-94).
+//
+// Roofline: tensor. 2*P*Q*K algorithmic flops, 3 MMAs issued per product => peak = TF32 dense peak / 3.
+#include <cuda.h>
 #include "common.cuh"
 #include "kernels.h"
+
 namespace rb {
-int launch_dense_tc_f32(const DenseProblem<float>&, cudaStream_t) { return -1; }
+
+namespace {
+
+constexpr int BM = 128, BN = 256, BK = 32, STAGES = 2;
+constexpr int GEN_WARPS = 8;
+constexpr int TC_THREADS = 64 + 32 * GEN_WARPS;
+constexpr uint32_t X_BYTES = BM * BK * 4, Y_BYTES = BN * BK * 4;
+constexpr uint32_t STAGE_BYTES = 2 * X_BYTES + 2 * Y_BYTES;
+constexpr uint32_t BAR_OFFSET = STAGES * STAGE_BYTES;
+constexpr uint32_t TC_SMEM = BAR_OFFSET + 128 + 1024;   // barriers + TMEM slot + 1 KB alignment slack
+constexpr uint32_t TMEM_COLS = 512;      // two 128 x 256 fp32 accumulators: hi*hi and the two cross terms
+constexpr int MAX_CHAIN_STEPS = 40;       // K steps accumulated in TMEM before the partial sum leaves the tensor core
+
+struct TcArgs {
+    Ctr128 ctr;
+    PhiloxKey key;
+    int64_t R;
+    int64_t v0;        // first operator vector (row of X)
+    int64_t ublk0;     // Philox block that holds position k = 0 of a vector: u0 / 4
+    int kshift;        // u0 & 3: when non-zero every 4-wide chunk of X straddles two Philox blocks
+    int64_t P, Q;
+    int steps_total;   // ceil(K / 32)
+    int splits;
+    float alpha, beta;
+    float* C;
+    int64_t crs, ccs;
+    float* W;          // split-K workspace: W[split][j][i], i fastest, ld = P_pad; null when splits == 1
+    int64_t P_pad, Q_pad;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t) __cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(bar), "r"(bytes)
+                 : "memory");
+}
+// Bounded wait: a pipeline bug must end in a trap (a launch error the host sees), never in a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok = 0;
+    long long t0 = 0;
+    for (uint32_t spins = 0;; ++spins) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (ok) return;
+        if ((spins & 0xfff) == 0xfff) {
+            const long long now = clock64();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 4000000000LL) __trap();   // ~2 s at 1.9 GHz
+        }
+    }
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+        ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar)
+        : "memory");
+}
+
+// L2 prefetch of a tile that will be loaded a few steps later: with only two shared-memory stages the HBM
+// latency of the actual load would otherwise sit on the critical path of every K step.
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int c0, int c1) {
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(map), "r"(c0), "r"(c1) : "memory");
+}
+
+// K-major, 128B-swizzled shared-memory matrix descriptor: rows of 128 bytes, 8-row groups 1024 bytes apart.
+__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t addr) {
+    return (uint64_t) ((addr >> 4) & 0x3fffu) | (1ull << 16) | ((uint64_t) (1024u >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+// kind::tf32, fp32 accumulate, both operands K-major, M = 128, N = 256
+constexpr uint32_t IDESC_TF32 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t) (BN >> 3) << 17) | ((uint32_t) (BM >> 4) << 24);
+
+__device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t da, uint64_t db, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(da), "l"(db), "r"(IDESC_TF32), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void mma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// x = hi + lo with hi the TF32 value nearest to x (ties away from zero) and lo the exact remainder
+__device__ __forceinline__ void split_rn(float x, float& hi, float& lo) {
+    hi = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
+    lo = __fsub_rn(x, hi);
+}
+// remainder after the truncation the tensor core applies to a raw fp32 operand
+__device__ __forceinline__ float lo_trunc(float y) { return __fsub_rn(y, __uint_as_float(__float_as_uint(y) & 0xffffe000u)); }
+
+template <bool GAUSS>
+__global__ void __launch_bounds__(TC_THREADS, 1) skge3_tc_kernel(const __grid_constant__ CUtensorMap tmY, const TcArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(16) double logtab[32];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    uint8_t* smem = smem_raw + (base - raw);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    const uint32_t bar0 = base + BAR_OFFSET;
+    auto bar_full = [&](int s) { return bar0 + 8u * s; };
+    auto bar_ready = [&](int s) { return bar0 + 8u * (STAGES + s); };
+    auto bar_empty = [&](int s) { return bar0 + 8u * (2 * STAGES + s); };
+    const uint32_t bar_accum = bar0 + 8u * (3 * STAGES);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + BAR_OFFSET + 8 * (3 * STAGES + 1));
+
+    if constexpr (GAUSS) load_logf_table(logtab);
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(bar_full(s), 1);
+            mbar_init(bar_ready(s), GEN_WARPS);
+            mbar_init(bar_empty(s), 1);
+        }
+        mbar_init(bar_accum, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmY) : "memory");
+    } else if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "r"(TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int64_t i0 = (int64_t) blockIdx.y * BM, j0 = (int64_t) blockIdx.x * BN;
+    const int split = blockIdx.z;
+    const int per = a.steps_total / a.splits, rem = a.steps_total % a.splits;
+    const int s_begin = split * per + min(split, rem);
+    const int nsteps = per + (split < rem ? 1 : 0);
+
+    if (warp == 0) {
+        if (lane == 0) {
+            constexpr int PF = 6;
+            for (int it = 0; it < min(PF, nsteps); ++it) tma_prefetch_2d(&tmY, (s_begin + it) * BK, (int) j0);
+            for (int it = 0; it < nsteps; ++it) {
+                const int st = it % STAGES;
+                const uint32_t ph = (it / STAGES) & 1;
+                if (it + PF < nsteps) tma_prefetch_2d(&tmY, (s_begin + it + PF) * BK, (int) j0);
+                mbar_wait(bar_empty(st), ph ^ 1);
+                mbar_arrive_expect_tx(bar_full(st), Y_BYTES);
+                tma_load_2d(base + st * STAGE_BYTES + 2 * X_BYTES, &tmY, bar_full(st), (s_begin + it) * BK, (int) j0);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            for (int it = 0; it < nsteps; ++it) {
+                const int st = it % STAGES;
+                const uint32_t ph = (it / STAGES) & 1;
+                mbar_wait(bar_ready(st), ph);
+                mbar_wait(bar_full(st), ph);
+                tc_fence_after();
+                const uint32_t xh = base + st * STAGE_BYTES, xl = xh + X_BYTES, yh = xl + X_BYTES, yl = yh + Y_BYTES;
+#pragma unroll
+                for (int kk = 0; kk < BK / 8; ++kk) {
+                    const uint64_t dxh = smem_desc_sw128(xh + kk * 32), dxl = smem_desc_sw128(xl + kk * 32);
+                    const uint64_t dyh = smem_desc_sw128(yh + kk * 32), dyl = smem_desc_sw128(yl + kk * 32);
+                    const uint32_t acc = (it > 0 || kk > 0) ? 1u : 0u;
+                    mma_tf32(tmem_base + BN, dxl, dyh, acc);
+                    mma_tf32(tmem_base + BN, dxh, dyl, 1u);
+                    mma_tf32(tmem_base, dxh, dyh, acc);
+                }
+                mma_commit(bar_empty(st));
+            }
+            mma_commit(bar_accum);
+        }
+    } else {
+        // ---------------- generators ----------------
+        const int gt = threadIdx.x - 64;
+        const int c = gt & 7, r0 = gt >> 3;
+        const uint64_t seed_lo = ((uint64_t) a.ctr.c1 << 32) | a.ctr.c0, seed_hi = ((uint64_t) a.ctr.c3 << 32) | a.ctr.c2;
+        uint64_t off[4];
+#pragma unroll
+        for (int rr = 0; rr < 4; ++rr)
+            off[rr] = (uint64_t) ((a.v0 + i0 + r0 + 32 * rr) * a.R + a.ublk0 + c) + 8ull * (uint64_t) s_begin;
+        const uint32_t xoff = (uint32_t) r0 * 128u + (uint32_t) ((c ^ (r0 & 7)) << 4);
+        for (int it = 0; it < nsteps; ++it) {
+            const int st = it % STAGES;
+            const uint32_t ph = (it / STAGES) & 1;
+            uint8_t* stage = smem + st * STAGE_BYTES;
+            mbar_wait(bar_empty(st), ph ^ 1);
+#pragma unroll
+            for (int rr = 0; rr < 4; ++rr) {
+                const uint64_t lo = seed_lo + off[rr];
+                const uint64_t hi = seed_hi + (lo < seed_lo ? 1ull : 0ull);
+                off[rr] += 8;
+                const Ctr128 cc{(uint32_t) lo, (uint32_t) (lo >> 32), (uint32_t) hi, (uint32_t) (hi >> 32)};
+                float4 f = transform4<GAUSS>(philox4x32_10(cc, a.key), logtab);
+                if (a.kshift) {
+                    // window origin not on a Philox block boundary: the four positions straddle two blocks
+                    const float4 g = transform4<GAUSS>(philox4x32_10(ctr_add(cc, 1), a.key), logtab);
+                    if (a.kshift == 1) f = make_float4(f.y, f.z, f.w, g.x);
+                    else if (a.kshift == 2) f = make_float4(f.z, f.w, g.x, g.y);
+                    else f = make_float4(f.w, g.x, g.y, g.z);
+                }
+                float4 h, l;
+                split_rn(finish_sample<float, GAUSS>(f.x), h.x, l.x);
+                split_rn(finish_sample<float, GAUSS>(f.y), h.y, l.y);
+                split_rn(finish_sample<float, GAUSS>(f.z), h.z, l.z);
+                split_rn(finish_sample<float, GAUSS>(f.w), h.w, l.w);
+                *reinterpret_cast<float4*>(stage + xoff + rr * 4096) = h;
+                *reinterpret_cast<float4*>(stage + X_BYTES + xoff + rr * 4096) = l;
+            }
+            mbar_wait(bar_full(st), ph);
+            const uint8_t* ysrc = stage + 2 * X_BYTES;
+            uint8_t* ydst = stage + 2 * X_BYTES + Y_BYTES;
+#pragma unroll
+            for (int q = 0; q < (int) (Y_BYTES / 16) / (32 * GEN_WARPS); ++q) {
+                const uint32_t o = (uint32_t) (gt + 32 * GEN_WARPS * q) * 16u;
+                const float4 y = *reinterpret_cast<const float4*>(ysrc + o);
+                float4 l;
+                l.x = lo_trunc(y.x); l.y = lo_trunc(y.y); l.z = lo_trunc(y.z); l.w = lo_trunc(y.w);
+                *reinterpret_cast<float4*>(ydst + o) = l;
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_ready(st));
+        }
+        // ---------------- epilogue ----------------
+        mbar_wait(bar_accum, 0);
+        tc_fence_after();
+        const int q4 = warp & 3, half = (warp - 2) >> 2;
+        const int64_t i = i0 + q4 * 32 + lane;
+        for (int cb = 0; cb < 4; ++cb) {
+            const int col0 = half * 128 + cb * 32;
+            uint32_t v[32];
+            {
+                uint32_t vs[32];
+                tmem_ld32(tmem_base + ((uint32_t) (q4 * 32) << 16) + (uint32_t) col0, v);
+                tmem_ld32(tmem_base + ((uint32_t) (q4 * 32) << 16) + (uint32_t) (BN + col0), vs);
+#pragma unroll
+                for (int t = 0; t < 32; ++t) v[t] = __float_as_uint(__fadd_rn(__uint_as_float(v[t]), __uint_as_float(vs[t])));
+            }
+            if (a.W) {
+                float* w = a.W + ((int64_t) split * a.Q_pad + j0 + col0) * a.P_pad + i;
+#pragma unroll
+                for (int t = 0; t < 32; ++t) w[(int64_t) t * a.P_pad] = __uint_as_float(v[t]);
+            } else if (i < a.P) {
+#pragma unroll
+                for (int t = 0; t < 32; ++t) {
+                    const int64_t j = j0 + col0 + t;
+                    if (j < a.Q) {
+                        float* cp = a.C + i * a.crs + j * a.ccs;
+                        float r = a.alpha * __uint_as_float(v[t]);
+                        if (a.beta != 0.f) r += a.beta * (*cp);
+                        *cp = r;
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+// C = alpha * sum_s W[s] + beta * C, summed in split order (deterministic)
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ W, int splits, int64_t P, int64_t Q,
+                                                            int64_t P_pad, int64_t Q_pad, float alpha, float beta,
+                                                            float* __restrict__ C, int64_t crs, int64_t ccs) {
+    const int64_t total = P * Q;
+    for (int64_t e = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t) gridDim.x * blockDim.x) {
+        const int64_t j = e / P, i = e - j * P;
+        const float* w = W + j * P_pad + i;
+        float s = 0.f;
+#pragma unroll 8
+        for (int sp = 0; sp < splits; ++sp) s += w[(int64_t) sp * Q_pad * P_pad];
+        float* cp = C + i * crs + j * ccs;
+        float r = alpha * s;
+        if (beta != 0.f) r += beta * (*cp);
+        *cp = r;
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn) p;
+        else
+            cudaGetLastError();
+    }
+    return fn;
+}
+
+}  // namespace
+
+int launch_dense_tc_f32(const DenseProblem<float>& p, cudaStream_t st) {
+    // shapes / layouts this kernel takes; everything else goes to the generic kernel
+    if (p.S_buff != nullptr) return -1;
+    if (!(p.uk == 1 && p.vi == 1)) return -1;                 // Philox blocks must run along K
+    if (p.yrs != 1) return -1;                                // Y must be K-contiguous
+    if (p.K < 64 || p.P < 1 || p.Q < 1) return -1;
+    if (p.Q > 0x7fffffffLL || p.K > 0x7fffff00LL) return -1;
+    if ((reinterpret_cast<uintptr_t>(p.Y) & 15) != 0 || (p.ycs & 3) != 0) return -1;   // TMA alignment rules
+    if ((int64_t) p.P * p.Q < 128 * 64 && p.K < 4096) return -1;                       // tiny: launch cost dominates
+    EncodeTiledFn enc = encode_tiled();
+    if (!enc) return -1;
+
+    const int64_t tiles_p = (p.P + BM - 1) / BM, tiles_q = (p.Q + BN - 1) / BN;
+    if (tiles_p > 65535 || tiles_q > 0x7fffffff) return -1;
+    const int kshift = (int) (p.u0 & 3);
+    const int64_t steps = (p.K + BK - 1) / BK;
+    // Split K. Two constraints: (1) the tensor core adds into its fp32 accumulator with truncation, a bias that
+    // grows linearly with the number of accumulated MMAs (measured: 4.6e-4 relative after 2048 K steps, 1.9e-6
+    // after 8), so no partial sum stays in TMEM for more than MAX_CHAIN_STEPS steps; partial sums are added in
+    // round-to-nearest fp32 by the reduce kernel. (2) the grid should cover the SMs in whole waves.
+    const int64_t tiles = tiles_p * tiles_q;
+    const int sms = sm_count();
+    int64_t s_min = (steps + MAX_CHAIN_STEPS - 1) / MAX_CHAIN_STEPS;
+    int splits = (int) s_min;
+    {
+        int64_t ctas = tiles * s_min;
+        int64_t waves = (ctas + sms - 1) / sms;
+        int64_t s_fill = waves * sms / tiles;          // more splits that still fit the same number of waves
+        if (s_fill > steps / 4) s_fill = steps / 4;    // keep at least 4 steps per CTA
+        if (s_fill > s_min) splits = (int) s_fill;
+        if (splits < 1) splits = 1;
+    }
+    if (get_option("tc_splits") > 0) {
+        splits = (int) get_option("tc_splits");
+        if (splits > steps) splits = (int) steps;
+    }
+    CUtensorMap tm;
+    const cuuint64_t gdim[2] = {(cuuint64_t) p.K, (cuuint64_t) p.Q};
+    const cuuint64_t gstr[1] = {(cuuint64_t) p.ycs * 4ull};
+    const cuuint32_t box[2] = {BK, BN};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult cr = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(p.Y), gdim, gstr, box, estr,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) return -1;
+
+    TcArgs a;
+    a.ctr = p.gen.ctr; a.key = p.gen.key; a.R = p.gen.R;
+    a.v0 = p.v0;
+    a.kshift = kshift;
+    a.ublk0 = p.u0 >> 2;
+    a.P = p.P; a.Q = p.Q;
+    a.steps_total = (int) steps;
+    a.splits = splits;
+    a.alpha = p.alpha; a.beta = p.beta;
+    a.C = p.C; a.crs = p.crs; a.ccs = p.ccs;
+    a.P_pad = tiles_p * BM; a.Q_pad = tiles_q * BN;
+    a.W = nullptr;
+    if (splits > 1) {
+        a.W = (float*) workspace(6, (size_t) splits * a.P_pad * a.Q_pad * sizeof(float));
+        if (!a.W) return fail_cuda(cudaErrorMemoryAllocation, "split-K workspace");
+    }
+    static bool attr_done[2] = {false, false};
+    const bool gauss = p.family == 'G';
+    if (!attr_done[gauss]) {
+        cudaError_t e = gauss ? cudaFuncSetAttribute(skge3_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM)
+                              : cudaFuncSetAttribute(skge3_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM);
+        if (e != cudaSuccess) { cudaGetLastError(); return -1; }
+        attr_done[gauss] = true;
+    }
+    dim3 grid((unsigned) tiles_q, (unsigned) tiles_p, (unsigned) splits);
+    if (gauss) skge3_tc_kernel<true><<<grid, TC_THREADS, TC_SMEM, st>>>(tm, a);
+    else skge3_tc_kernel<false><<<grid, TC_THREADS, TC_SMEM, st>>>(tm, a);
+    count_launch();
+    count_tc_launch();
+    RB_CUDA(cudaGetLastError());
+    if (splits > 1) {
+        int64_t g = (p.P * p.Q + 255) / 256;
+        if (g > (int64_t) sms * 8) g = (int64_t) sms * 8;
+        splitk_reduce_kernel<<<(unsigned) g, 256, 0, st>>>(a.W, splits, p.P, p.Q, a.P_pad, a.Q_pad, p.alpha, p.beta, p.C,
+                                                          p.crs, p.ccs);
+        count_launch();
+        RB_CUDA(cudaGetLastError());
+    }
+    return 0;
+}
+
+}  // namespace rb
