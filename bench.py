@@ -462,6 +462,9 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    for kv in os.environ.get("RB_OPTIONS", "").split(","):      # debug knobs, e.g. RB_OPTIONS=tc_debug=1
+        if "=" in kv:
+            rb.set_option(kv.split("=")[0], int(kv.split("=")[1]))
     wl = WORKLOADS[args.workload]()
     wl.setup(rb, torch, rank, world)
     warm = max(args.warmup, 3)
@@ -481,6 +484,7 @@ def main():
     ev1.record()
     barrier()
     ms = ev0.elapsed_time(ev1)
+    ms_local_per_step = ms / args.steps
     launches = rb.counter("kernel_launches") - launches0
     clocks = sampler.stop() if rank == 0 else None
     t = torch.tensor([ms], dtype=torch.float64, device="cuda")
@@ -497,7 +501,10 @@ def main():
         a.record(); wl.step(); b.record(); torch.cuda.synchronize()
         kms.append(a.elapsed_time(b))
     pk = peaks()
-    roof = wl.roofline(float(np.mean(kms)), pk)
+    # per-launch duration of the hot kernel(s) of one step = CUDA-event time of the timed region / steps (this rank)
+    roof = wl.roofline(ms_local_per_step, pk)
+    roof["launch_ms"] = ms_local_per_step
+    roof["launch_ms_isolated"] = float(np.mean(kms))      # same step timed alone between two synchronisations
 
     # end to end through the C ABI with host buffers (copies inside the timed region)
     e2e = None

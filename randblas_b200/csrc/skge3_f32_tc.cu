@@ -9,18 +9,22 @@
 // Canonical problem (see kernels.h): C(P x Q) = alpha * X(P x K) * Y(K x Q) + beta * C with X = op(S window).
 // One CTA owns a 128 x 256 tile of C and one K range (split-K over blockIdx.z):
 //   warp 0      : TMA producer. Y tiles (256 columns x 32 k, K contiguous) land in shared memory, 128B swizzle.
-//   warp 1      : allocates 256 TMEM columns; one thread issues tcgen05.mma kind::tf32, cta_group::1, M=128,
-//                 N=256, K=8: per 8-deep slice three MMAs  X_lo*Y_hi + X_hi*Y_lo + X_hi*Y_hi  (3xTF32: fp32
-//                 operands are split x = hi + lo with hi, lo exactly representable in TF32; the dropped lo*lo
-//                 term is 2^-22 relative). The accumulator (128 lanes x 256 fp32 columns) lives in TMEM.
-//   warps 2..9  : generators. Per K step: Philox4x32-10 + uneg11/Box-Muller for the X tile -> (hi, lo) ->
+//   warp 1      : allocates all 512 TMEM columns; one thread issues tcgen05.mma kind::tf32, cta_group::1, M=128,
+//                 N=256, K=8: per 8-deep slice three MMAs  X_lo*Y_hi + X_hi*Y_lo -> accumulator "small",
+//                 X_hi*Y_hi -> accumulator "big"  (3xTF32: fp32 operands are split x = hi + lo with hi, lo exactly
+//                 representable in TF32; the dropped lo*lo term is 2^-22 relative). Two 128 x 256 fp32
+//                 accumulators live in TMEM: the tensor core adds into its accumulator with truncation, a bias that
+//                 grows with the number of MMAs added, so the cross terms (whose rounding does not matter) are
+//                 kept out of the accumulator that carries the leading term.
+//   warps 2..17 : generators. Per K step: Philox4x32-10 + uneg11/Box-Muller for the X tile -> (hi, lo) ->
 //                 swizzled st.shared; then Y_lo = Y - trunc_tf32(Y) for the tile TMA just delivered (the tensor
 //                 core ignores the 13 low mantissa bits of its 32-bit operands, so the raw tile IS Y_hi).
 //                 After the last K step the same warps run the epilogue: tcgen05.ld -> alpha/beta -> global.
 // Pipeline: 2 stages of {X_hi, X_lo, Y, Y_lo} = 96 KB each; mbarriers full_y (TMA -> consumers),
 // ready (generators -> MMA), empty (tcgen05.commit -> producers), accum (last commit -> epilogue).
-// Split-K partial tiles go to a workspace and are summed in a fixed order by a second small kernel, so the
-// result does not depend on the grid (the reference guarantees thread-count invariance, dense_skops.hh:90-94).
+// No partial sum stays in TMEM for more than MAX_CHAIN_STEPS K steps (accuracy, see launch_dense_tc_f32);
+// split-K partial tiles go to a workspace and are summed in a fixed order, in round-to-nearest fp32, by a
+// second small kernel, so the result does not depend on the grid (the reference guarantees thread-count invariance, dense_skops.hh:90-94).
 //
 // Roofline: tensor. 2*P*Q*K algorithmic flops, 3 MMAs issued per product => peak = TF32 dense peak / 3.
 #include <cuda.h>
@@ -32,7 +36,8 @@ namespace rb {
 namespace {
 
 constexpr int BM = 128, BN = 256, BK = 32, STAGES = 2;
-constexpr int GEN_WARPS = 8;
+constexpr int GEN_WARPS = 16;            // 4 per scheduler: the Philox chains need the thread-level parallelism
+constexpr int X_PER_THREAD = (BM * BK / 4) / (32 * GEN_WARPS);   // Philox blocks per generator thread per K step
 constexpr int TC_THREADS = 64 + 32 * GEN_WARPS;
 constexpr uint32_t X_BYTES = BM * BK * 4, Y_BYTES = BN * BK * 4;
 constexpr uint32_t STAGE_BYTES = 2 * X_BYTES + 2 * Y_BYTES;
@@ -228,10 +233,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) skge3_tc_kernel(const __grid_co
         const int gt = threadIdx.x - 64;
         const int c = gt & 7, r0 = gt >> 3;
         const uint64_t seed_lo = ((uint64_t) a.ctr.c1 << 32) | a.ctr.c0, seed_hi = ((uint64_t) a.ctr.c3 << 32) | a.ctr.c2;
-        uint64_t off[4];
+        constexpr int ROWS_PER_PASS = 4 * GEN_WARPS;      // rows of X covered by one pass of all generator threads
+        uint64_t off[X_PER_THREAD];
 #pragma unroll
-        for (int rr = 0; rr < 4; ++rr)
-            off[rr] = (uint64_t) ((a.v0 + i0 + r0 + 32 * rr) * a.R + a.ublk0 + c) + 8ull * (uint64_t) s_begin;
+        for (int rr = 0; rr < X_PER_THREAD; ++rr)
+            off[rr] = (uint64_t) ((a.v0 + i0 + r0 + ROWS_PER_PASS * rr) * a.R + a.ublk0 + c) + 8ull * (uint64_t) s_begin;
         const uint32_t xoff = (uint32_t) r0 * 128u + (uint32_t) ((c ^ (r0 & 7)) << 4);
         for (int it = 0; it < nsteps; ++it) {
             const int st = it % STAGES;
@@ -239,7 +245,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) skge3_tc_kernel(const __grid_co
             uint8_t* stage = smem + st * STAGE_BYTES;
             mbar_wait(bar_empty(st), ph ^ 1);
 #pragma unroll
-            for (int rr = 0; rr < 4; ++rr) {
+            for (int rr = 0; rr < X_PER_THREAD; ++rr) {
                 const uint64_t lo = seed_lo + off[rr];
                 const uint64_t hi = seed_hi + (lo < seed_lo ? 1ull : 0ull);
                 off[rr] += 8;
@@ -257,8 +263,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) skge3_tc_kernel(const __grid_co
                 split_rn(finish_sample<float, GAUSS>(f.y), h.y, l.y);
                 split_rn(finish_sample<float, GAUSS>(f.z), h.z, l.z);
                 split_rn(finish_sample<float, GAUSS>(f.w), h.w, l.w);
-                *reinterpret_cast<float4*>(stage + xoff + rr * 4096) = h;
-                *reinterpret_cast<float4*>(stage + X_BYTES + xoff + rr * 4096) = l;
+                *reinterpret_cast<float4*>(stage + xoff + rr * (ROWS_PER_PASS * 128)) = h;
+                *reinterpret_cast<float4*>(stage + X_BYTES + xoff + rr * (ROWS_PER_PASS * 128)) = l;
             }
             mbar_wait(bar_full(st), ph);
             const uint8_t* ysrc = stage + 2 * X_BYTES;
@@ -278,10 +284,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) skge3_tc_kernel(const __grid_co
         // ---------------- epilogue ----------------
         mbar_wait(bar_accum, 0);
         tc_fence_after();
-        const int q4 = warp & 3, half = (warp - 2) >> 2;
+        constexpr int COLS_PER_WARP = BN / (GEN_WARPS / 4);
+        const int q4 = warp & 3, part = (warp - 2) >> 2;
         const int64_t i = i0 + q4 * 32 + lane;
-        for (int cb = 0; cb < 4; ++cb) {
-            const int col0 = half * 128 + cb * 32;
+        for (int cb = 0; cb < COLS_PER_WARP / 32; ++cb) {
+            const int col0 = part * COLS_PER_WARP + cb * 32;
             uint32_t v[32];
             {
                 uint32_t vs[32];
