@@ -1,6 +1,270 @@
-// placeholder until the DMMA kernel lands
+// K2b: fused generate-and-multiply dense sketch for double on the FP64 tensor-core path (DMMA).
+//
+// Replaces dense::lskge3 / rskge3 (RandBLAS/skge.hh:154-202, 307-355) for double when the operator is not
+// materialised (the reference fills a d x m host buffer -- 131 GB at BASELINE config 3 -- and calls blas::gemm).
+// tcgen05.mma has no f64 kind (ptxas rejects kind::f64 for sm_100a), so the FP64 tensor path on Blackwell is the
+// warp-level mma.sync.m8n8k4.f64 (SASS DMMA.8x8x4) with register accumulators; DMMA is an IEEE fused
+// multiply-add chain, so unlike the TF32 path there is no accumulator-truncation issue and split-K is only used
+// to fill the SMs.
+//
+// Canonical problem (kernels.h): C(P x Q) = alpha * X(P x K) * Y(K x Q) + beta * C, X = op(S window).
+// CTA tile 128 x 128, 8 warps as 2 x 4, warp tile 64 x 32 = 8 x 4 DMMA tiles (64 accumulator doubles per
+// thread), K step 16. Per step every thread
+//   * issues the 16-byte cp.async copies of the next Y tile (columns of A are K-contiguous: ColMajor A),
+//   * runs the 128 DMMAs of the current tile from shared memory (rows padded to 20 doubles: conflict-free
+//     8-byte fragment loads),
+//   * regenerates its share (2 Philox blocks = 8 samples) of the next 128 x 16 tile of S from
+//     (key, counter, ro_s, co_s) -- Philox4x32-10, uneg11 or Box-Muller in float exactly as fill_dense, promoted
+//     to double -- while the tensor pipe drains; S never touches HBM.
+// Double-buffered shared memory, one __syncthreads per step.
+//
+// Roofline: FP64 tensor. 2*P*Q*K flops per launch.
 #include "common.cuh"
 #include "kernels.h"
+
 namespace rb {
-int launch_dense_dmma_f64(const DenseProblem<double>&, cudaStream_t) { return -1; }
+
+namespace {
+
+constexpr int DM = 128, DN = 128, DK = 16, DLD = DK + 4;     // DLD: padded row length in doubles
+constexpr int D_THREADS = 256;
+
+struct DmmaArgs {
+    Ctr128 ctr;
+    PhiloxKey key;
+    int64_t R, v0, ublk0;
+    int kshift;
+    int64_t P, Q, K;
+    int steps_total, splits;
+    double alpha, beta;
+    const double* Y;
+    int64_t ycs;          // column stride of Y in elements (rows are contiguous: yrs == 1)
+    double* C;
+    int64_t crs, ccs;
+    double* W;            // split-K workspace W[split][j][i] (i fastest, ld = P_pad) or null
+    int64_t P_pad, Q_pad;
+};
+
+__device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c[0]), "+d"(c[1])
+                 : "d"(a), "d"(b));
 }
+__device__ __forceinline__ void cp_async16(void* dst, const void* src, int src_bytes) {
+    const uint32_t d = (uint32_t) __cvta_generic_to_shared(dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(src_bytes) : "memory");
+}
+
+template <bool GAUSS>
+__global__ void __launch_bounds__(D_THREADS, 1) skge3_dmma_kernel(const DmmaArgs a) {
+    __shared__ __align__(16) double logtab[32];
+    extern __shared__ __align__(16) double dsm[];
+    double* Xs = dsm;                              // [2][DM][DLD]
+    double* Ys = dsm + 2 * DM * DLD;               // [2][DN][DLD]
+    if constexpr (GAUSS) load_logf_table(logtab);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int wi = warp >> 2, wj = warp & 3;       // 2 x 4 warps
+    const int g = lane >> 2, t4 = lane & 3;
+    const int64_t i0 = (int64_t) blockIdx.y * DM, j0 = (int64_t) blockIdx.x * DN;
+    const int split = blockIdx.z;
+    const int per = a.steps_total / a.splits, rem = a.steps_total % a.splits;
+    const int s_begin = split * per + min(split, rem);
+    const int nsteps = per + (split < rem ? 1 : 0);
+
+    // generator role: rows xr and xr + 64, 4-wide chunk xc of the 16-deep step
+    const int xc = tid & 3, xr = tid >> 2;
+    const uint64_t seed_lo = ((uint64_t) a.ctr.c1 << 32) | a.ctr.c0, seed_hi = ((uint64_t) a.ctr.c3 << 32) | a.ctr.c2;
+    uint64_t off[2];
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr)
+        off[rr] = (uint64_t) ((a.v0 + i0 + xr + 64 * rr) * a.R + a.ublk0 + xc) + 4ull * (uint64_t) s_begin;
+
+    auto gen_x = [&](int buf) {
+#pragma unroll
+        for (int rr = 0; rr < 2; ++rr) {
+            const uint64_t lo = seed_lo + off[rr];
+            const uint64_t hi = seed_hi + (lo < seed_lo ? 1ull : 0ull);
+            off[rr] += 4;
+            const Ctr128 cc{(uint32_t) lo, (uint32_t) (lo >> 32), (uint32_t) hi, (uint32_t) (hi >> 32)};
+            float4 f = transform4<GAUSS>(philox4x32_10(cc, a.key), logtab);
+            if (a.kshift) {
+                const float4 h = transform4<GAUSS>(philox4x32_10(ctr_add(cc, 1), a.key), logtab);
+                if (a.kshift == 1) f = make_float4(f.y, f.z, f.w, h.x);
+                else if (a.kshift == 2) f = make_float4(f.z, f.w, h.x, h.y);
+                else f = make_float4(f.w, h.x, h.y, h.z);
+            }
+            double* dst = Xs + ((size_t) buf * DM + xr + 64 * rr) * DLD + 4 * xc;
+            *reinterpret_cast<double2*>(dst) = make_double2(finish_sample<double, GAUSS>(f.x), finish_sample<double, GAUSS>(f.y));
+            *reinterpret_cast<double2*>(dst + 2) = make_double2(finish_sample<double, GAUSS>(f.z), finish_sample<double, GAUSS>(f.w));
+        }
+    };
+    // Y tile: 128 columns x 16 k = 1024 chunks of 2 doubles; thread handles chunks tid + 256 q
+    auto load_y = [&](int buf, int step) {
+        const int64_t k0 = (int64_t) (s_begin + step) * DK;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int ch = tid + D_THREADS * q;
+            const int jj = ch >> 3, kc = (ch & 7) * 2;
+            double* dst = Ys + ((size_t) buf * DN + jj) * DLD + kc;
+            const int64_t j = j0 + jj, k = k0 + kc;
+            if (j < a.Q && k + 1 < a.K) {
+                cp_async16(dst, a.Y + j * a.ycs + k, 16);
+            } else {
+                double y0 = 0.0, y1 = 0.0;
+                if (j < a.Q && k < a.K) y0 = a.Y[j * a.ycs + k];
+                dst[0] = y0; dst[1] = y1;
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+
+    double acc[8][4][2];
+#pragma unroll
+    for (int mi = 0; mi < 8; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+
+    __syncthreads();                  // logtab
+    if (nsteps > 0) {
+        load_y(0, 0);
+        gen_x(0);
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();
+    for (int step = 0; step < nsteps; ++step) {
+        const int cur = step & 1, nxt = cur ^ 1;
+        const bool more = step + 1 < nsteps;
+        if (more) load_y(nxt, step + 1);
+        const double* xb = Xs + ((size_t) cur * DM + wi * 64 + g) * DLD + t4;
+        const double* yb = Ys + ((size_t) cur * DN + wj * 32 + g) * DLD + t4;
+#pragma unroll
+        for (int k4 = 0; k4 < DK / 4; ++k4) {
+            double af[8], bf[4];
+#pragma unroll
+            for (int mi = 0; mi < 8; ++mi) af[mi] = xb[mi * 8 * DLD + k4 * 4];
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni) bf[ni] = yb[ni * 8 * DLD + k4 * 4];
+#pragma unroll
+            for (int mi = 0; mi < 8; ++mi)
+#pragma unroll
+                for (int ni = 0; ni < 4; ++ni) dmma(acc[mi][ni], af[mi], bf[ni]);
+        }
+        if (more) gen_x(nxt);
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();
+    }
+
+    // epilogue: c0 at (row g, col 2 t4), c1 at (row g, col 2 t4 + 1) of each 8 x 8 tile
+#pragma unroll
+    for (int mi = 0; mi < 8; ++mi) {
+        const int64_t i = i0 + wi * 64 + mi * 8 + g;
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) {
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int64_t j = j0 + wj * 32 + ni * 8 + 2 * t4 + e;
+                if (a.W) {
+                    a.W[((int64_t) split * a.Q_pad + j) * a.P_pad + i] = acc[mi][ni][e];
+                } else if (i < a.P && j < a.Q) {
+                    double* cp = a.C + i * a.crs + j * a.ccs;
+                    double r = a.alpha * acc[mi][ni][e];
+                    if (a.beta != 0.0) r += a.beta * (*cp);
+                    *cp = r;
+                }
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) splitk_reduce_f64_kernel(const double* __restrict__ W, int splits, int64_t P, int64_t Q,
+                                                                int64_t P_pad, int64_t Q_pad, double alpha, double beta,
+                                                                double* __restrict__ C, int64_t crs, int64_t ccs) {
+    const int64_t total = P * Q;
+    for (int64_t e = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t) gridDim.x * blockDim.x) {
+        const int64_t j = e / P, i = e - j * P;
+        const double* w = W + j * P_pad + i;
+        double s = 0.0;
+#pragma unroll 4
+        for (int sp = 0; sp < splits; ++sp) s += w[(int64_t) sp * Q_pad * P_pad];
+        double* cp = C + i * crs + j * ccs;
+        double r = alpha * s;
+        if (beta != 0.0) r += beta * (*cp);
+        *cp = r;
+    }
+}
+
+}  // namespace
+
+int launch_dense_dmma_f64(const DenseProblem<double>& p, cudaStream_t st) {
+    if (p.S_buff != nullptr) return -1;
+    if (!(p.uk == 1 && p.vi == 1)) return -1;                 // Philox blocks must run along K
+    if (p.yrs != 1) return -1;                                // Y must be K-contiguous
+    if (p.K < 32 || p.P < 1 || p.Q < 1) return -1;
+    if ((reinterpret_cast<uintptr_t>(p.Y) & 15) != 0 || (p.ycs & 1) != 0) return -1;   // 16-byte cp.async
+    if ((int64_t) p.P * p.Q < 64 * 64 && p.K < 4096) return -1;
+    const int64_t tiles_p = (p.P + DM - 1) / DM, tiles_q = (p.Q + DN - 1) / DN;
+    if (tiles_p > 65535 || tiles_q > 0x7fffffff) return -1;
+    const int64_t steps = (p.K + DK - 1) / DK;
+    if (steps > 0x7fffffff) return -1;
+    const int64_t tiles = tiles_p * tiles_q;
+    const int sms = sm_count();
+    // split K only to fill the SMs: pick the split count (<= 16) with the best wave efficiency
+    int splits = 1;
+    {
+        double best = 0;
+        for (int s = 1; s <= 16; ++s) {
+            if (s > 1 && steps / s < 64) break;
+            const int64_t ctas = tiles * s;
+            const int64_t waves = (ctas + sms - 1) / sms;
+            const double eff = (double) ctas / (double) (waves * sms);
+            if (eff > best + 0.03) { best = eff; splits = s; }
+        }
+    }
+    if (get_option("tc_splits") > 0) {
+        splits = (int) get_option("tc_splits");
+        if (splits > steps) splits = (int) steps;
+    }
+    DmmaArgs a;
+    a.ctr = p.gen.ctr; a.key = p.gen.key; a.R = p.gen.R;
+    a.v0 = p.v0;
+    a.kshift = (int) (p.u0 & 3);
+    a.ublk0 = p.u0 >> 2;
+    a.P = p.P; a.Q = p.Q; a.K = p.K;
+    a.steps_total = (int) steps; a.splits = splits;
+    a.alpha = p.alpha; a.beta = p.beta;
+    a.Y = p.Y; a.ycs = p.ycs;
+    a.C = p.C; a.crs = p.crs; a.ccs = p.ccs;
+    a.P_pad = tiles_p * DM; a.Q_pad = tiles_q * DN;
+    a.W = nullptr;
+    if (splits > 1) {
+        a.W = (double*) workspace(6, (size_t) splits * a.P_pad * a.Q_pad * sizeof(double));
+        if (!a.W) return fail_cuda(cudaErrorMemoryAllocation, "split-K workspace");
+    }
+    constexpr size_t smem = (size_t) 2 * (DM + DN) * DLD * sizeof(double);
+    static bool attr_done[2] = {false, false};
+    const bool gauss = p.family == 'G';
+    if (!attr_done[gauss]) {
+        cudaError_t e = gauss ? cudaFuncSetAttribute(skge3_dmma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)
+                              : cudaFuncSetAttribute(skge3_dmma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+        if (e != cudaSuccess) { cudaGetLastError(); return -1; }
+        attr_done[gauss] = true;
+    }
+    dim3 grid((unsigned) tiles_q, (unsigned) tiles_p, (unsigned) splits);
+    if (gauss) skge3_dmma_kernel<true><<<grid, D_THREADS, smem, st>>>(a);
+    else skge3_dmma_kernel<false><<<grid, D_THREADS, smem, st>>>(a);
+    count_launch();
+    count_tc_launch();
+    RB_CUDA(cudaGetLastError());
+    if (splits > 1) {
+        int64_t gr = (p.P * p.Q + 255) / 256;
+        if (gr > (int64_t) sms * 8) gr = (int64_t) sms * 8;
+        splitk_reduce_f64_kernel<<<(unsigned) gr, 256, 0, st>>>(a.W, splits, p.P, p.Q, a.P_pad, a.Q_pad, p.alpha, p.beta,
+                                                               p.C, p.crs, p.ccs);
+        count_launch();
+        RB_CUDA(cudaGetLastError());
+    }
+    return 0;
+}
+
+}  // namespace rb
