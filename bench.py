@@ -32,6 +32,28 @@ def peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
 
 
+def measured_gemm_tflops(torch, dtype, n=8192, reps=5):
+    """Library GEMM throughput measured on this GPU in this run: the denominator for the tensor-bound configs
+    (MEASURED_PEAKS.json only has bf16). torch.matmul = cuBLAS; TF32 enabled for float32."""
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        a = torch.randn(n, n, dtype=dtype, device="cuda")
+        b = torch.randn(n, n, dtype=dtype, device="cuda")
+        c = torch.empty(n, n, dtype=dtype, device="cuda")
+        torch.matmul(a, b, out=c)
+        torch.cuda.synchronize()
+        best = 1e30
+        for _ in range(reps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); torch.matmul(a, b, out=c); e1.record(); torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        del a, b, c
+        return 2.0 * n ** 3 / 1e12 / (best / 1e3)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
@@ -149,15 +171,18 @@ class C2FillDense(Workload):
     def e2e_units(self):
         return self.e2e_rows * self.cols / 1e9, 0, self.e2e_rows * self.cols * 8
 
-    def cpu_baseline(self, impl):
+    # CPU leg: a 64-row slice of the same operator per step (the full output is 65.5 GB)
+    cpu_sample = "64 x 1000000 row slice of the operator via fill_dense_unpacked per step"
+
+    def cpu_setup(self, impl, rng):
+        self.cpu_i = 0
+
+    def cpu_step(self, impl):
         rows = 64
-        ctr, key = self.seed.counter, self.seed.key
-        best = 1e30
-        for _ in range(3):
-            t0 = time.perf_counter()
-            impl.fill_dense_unpacked("R", self.rows, self.cols, "G", "L", rows, self.cols, 0, 0, ctr, key, np.float64)
-            best = min(best, time.perf_counter() - t0)
-        return rows * self.cols / 1e9 / best, f"{rows} x {self.cols} row slice via fill_dense_unpacked, best of 3"
+        impl.fill_dense_unpacked("R", self.rows, self.cols, "G", "L", rows, self.cols, (64 * self.cpu_i) % 8192, 0,
+                                 [0, 0, 0, 0], [1997, 0], np.float64)
+        self.cpu_i += 1
+        return rows * self.cols / 1e9
 
 
 class C1DenseSketchF32(Workload):
@@ -185,9 +210,12 @@ class C1DenseSketchF32(Workload):
 
     def roofline(self, kernel_ms, pk):
         tf = 2.0 * self.d * self.m * self.n / 1e12 / (kernel_ms / 1e3)
-        peak = pk["bf16_tflops"] / 2.0 / 3.0          # TF32 dense = bf16 / 2; 3xTF32 issues 3 MMAs per product
+        tf32 = measured_gemm_tflops(self.torch, self.torch.float32)
+        peak = tf32 / 3.0                              # 3xTF32 issues 3 MMAs per fp32 product
         return {"bound": "tensor", "achieved": tf, "peak": peak, "unit": "TFLOP/s", "frac": tf / peak, "traffic": None,
-                "kernel": "dense sketch (3xTF32)", "peak_source": pk["source"] + " (bf16 cuBLAS / 2 / 3)",
+                "kernel": "skge3_tc_kernel (tcgen05 3xTF32) + splitk_reduce_kernel",
+                "peak_source": f"measured in this run: cuBLAS TF32 GEMM 8192^3 = {tf32:.1f} TFLOP/s, / 3 "
+                               f"(MEASURED_PEAKS bf16 {pk['bf16_tflops']:.0f} / 2 / 3 = {pk['bf16_tflops'] / 6:.1f})",
                 "algorithmic_flops_per_launch": 2.0 * self.d * self.m * self.n,
                 "hbm_gbs_of_A": self.m * self.n * 4 / 1e9 / (kernel_ms / 1e3)}
 
@@ -205,17 +233,16 @@ class C1DenseSketchF32(Workload):
     def e2e_units(self):
         return self.m * self.n * 4 / 1e9, self.m * self.n * 4, self.d * self.n * 4
 
-    def cpu_baseline(self, impl):
-        A = self.A.cpu().numpy()
-        B = np.zeros(self.d * self.n, np.float32)
-        st = self.S.seed_state
-        best = 1e30
-        for _ in range(2):
-            t0 = time.perf_counter()
-            impl.lskge3("C", "N", "N", self.d, self.n, self.m, np.float32(1), (self.d, self.m, "U", "L"), st.counter,
-                        st.key, 0, 0, A, self.m, np.float32(0), B, self.d)
-            best = min(best, time.perf_counter() - t0)
-        return self.m * self.n * 4 / 1e9 / best, "full config (reference materialises S, then SGEMM), best of 2"
+    cpu_sample = "full config (the reference materialises the 1024 x 100000 operator, then SGEMM) per step"
+
+    def cpu_setup(self, impl, rng):
+        self.cA = rng.standard_normal(self.m * self.n, dtype=np.float32)
+        self.cB = np.zeros(self.d * self.n, np.float32)
+
+    def cpu_step(self, impl):
+        impl.lskge3("C", "N", "N", self.d, self.n, self.m, np.float32(1), (self.d, self.m, "U", "L"), [0, 0, 0, 0],
+                    [1997, 0], 0, 0, self.cA, self.m, np.float32(0), self.cB, self.d)
+        return self.m * self.n * 4 / 1e9
 
 
 class C4SasoApply(Workload):
@@ -261,16 +288,18 @@ class C4SasoApply(Workload):
     def e2e_units(self):
         return self.e2e_m * self.n * 4 / 1e9, self.e2e_m * self.n * 4, self.d * self.n * 4
 
-    def cpu_baseline(self, impl):
-        mm = 400000
-        A = self.A[: mm * self.n].cpu().numpy()
-        B = np.zeros(self.d * self.n, np.float32)
-        st = self.S.seed_state
-        t0 = time.perf_counter()
-        impl.lskges("R", "N", "N", self.d, self.n, mm, np.float32(1), (self.d, self.m, self.k, "S"), st.counter, st.key,
-                    0, 0, A, self.n, np.float32(0), B, self.n)
-        dt = time.perf_counter() - t0
-        return mm * self.n * 4 / 1e9 / dt, f"first {mm} rows of A (m/20) incl. fill_sparse of the full operator, 1 run"
+    cpu_m = 400000
+    cpu_sample = ("m/20 = 400000 rows of A with a 2048 x 400000 SASO operator (fill_sparse + COO->CSC sort + apply, "
+                  "as the reference does for an unsampled operator) per step")
+
+    def cpu_setup(self, impl, rng):
+        self.cA = rng.standard_normal(self.cpu_m * self.n, dtype=np.float32)
+        self.cB = np.zeros(self.d * self.n, np.float32)
+
+    def cpu_step(self, impl):
+        impl.lskges("R", "N", "N", self.d, self.n, self.cpu_m, np.float32(1), (self.d, self.cpu_m, self.k, "S"),
+                    [0, 0, 0, 0], [1997, 0], 0, 0, self.cA, self.n, np.float32(0), self.cB, self.n)
+        return self.cpu_m * self.n * 4 / 1e9
 
 
 class C3DenseSketchF64(Workload):
@@ -303,24 +332,27 @@ class C3DenseSketchF64(Workload):
 
     def roofline(self, kernel_ms, pk):
         tf = 2.0 * self.d * self.m_local * self.n / 1e12 / (kernel_ms / 1e3)
-        peak = 40.0
+        peak = measured_gemm_tflops(self.torch, self.torch.float64, n=6144, reps=3)
         return {"bound": "tensor", "achieved": tf, "peak": peak, "unit": "TFLOP/s", "frac": tf / peak, "traffic": None,
-                "kernel": "dense sketch (FP64 DMMA)", "peak_source": "nominal B200 FP64 (no measured entry)",
+                "kernel": "skge3_dmma_kernel (mma.sync m8n8k4 f64) + splitk_reduce_f64_kernel",
+                "peak_source": "measured in this run: cuBLAS DGEMM 6144^3 (nominal B200 FP64: 40 TFLOP/s)",
                 "algorithmic_flops_per_launch": 2.0 * self.d * self.m_local * self.n}
 
     def e2e_setup(self):
         return None
 
-    def cpu_baseline(self, impl):
-        mm = 20000
-        A = np.ascontiguousarray(self.A.view(self.n, self.m_local)[:, :mm].cpu().numpy()).ravel()
-        B = np.zeros(self.d * self.n, np.float64)
-        st = self.S.seed_state
-        t0 = time.perf_counter()
-        impl.lskge3("C", "N", "N", self.d, self.n, mm, 1.0, (self.d, self.m_local * self.world, "G", "L"), st.counter,
-                    st.key, 0, 0, A, mm, 0.0, B, self.d)
-        dt = time.perf_counter() - t0
-        return mm * self.n * 8 / 1e9 / dt, f"one row block of {mm} rows of A (blocked form, beta=1 accumulation), 1 run"
+    cpu_m = 10000
+    cpu_sample = ("one row block of 10000 rows of A (the reference's blocked form: operator columns [0, 10000) "
+                  "materialised, then DGEMM) per step")
+
+    def cpu_setup(self, impl, rng):
+        self.cA = rng.standard_normal(self.cpu_m * self.n)
+        self.cB = np.zeros(self.d * self.n, np.float64)
+
+    def cpu_step(self, impl):
+        impl.lskge3("C", "N", "N", self.d, self.n, self.cpu_m, 1.0, (self.d, 4000000, "G", "L"), [0, 0, 0, 0],
+                    [1997, 0], 0, 0, self.cA, self.cpu_m, 0.0, self.cB, self.d)
+        return self.cpu_m * self.n * 8 / 1e9
 
 
 class C5SketchSparse(Workload):
@@ -373,8 +405,29 @@ class C5SketchSparse(Workload):
     def e2e_setup(self):
         return None
 
-    def cpu_baseline(self, impl):
-        return None, "not run (reference materialises the 512 x 1e7 operator: 20 GB)"
+    cpu_m = 100000
+    cpu_sample = ("row block of 100000 rows of the CSR shard (100000 x 125000, ~12.5 nnz/row) against the matching "
+                  "512 x 100000 block of the operator (materialised by the reference, then right_spmm) per step")
+
+    def cpu_setup(self, impl, rng):
+        mm, nn = self.cpu_m, self.n_local
+        lens = rng.poisson(self.per_row, mm).astype(np.int64)
+        rowptr = np.zeros(mm + 1, np.int64)
+        np.cumsum(lens, out=rowptr[1:])
+        nnz = int(rowptr[-1])
+        cols = rng.integers(0, nn, nnz, dtype=np.int64)
+        # sort the column indices inside each row
+        order = np.lexsort((cols, np.repeat(np.arange(mm), lens)))
+        cols = np.ascontiguousarray(cols[order])
+        vals = rng.standard_normal(nnz, dtype=np.float32)
+        self.c_sp = (mm, nn, nnz, vals, rowptr, cols)
+        self.c_bytes = nnz * 12 + (mm + 1) * 8
+        self.cB = np.zeros(self.d * nn, np.float32)
+
+    def cpu_step(self, impl):
+        impl.lsksp3(0, "C", "N", "N", self.d, self.n_local, self.cpu_m, np.float32(1), (self.d, self.cpu_m, "G", "L"),
+                    [0, 0, 0, 0], [1997, 0], 0, 0, self.c_sp, np.float32(0), self.cB, self.d)
+        return self.c_bytes / 1e9
 
 
 WORKLOADS = {"c1": C1DenseSketchF32, "c2": C2FillDense, "c3": C3DenseSketchF64, "c4": C4SasoApply, "c5": C5SketchSparse}
@@ -388,44 +441,37 @@ def cpu_impl():
     return ol.port(), "port"
 
 
+def time_cpu(wl, impl, warmup, steps):
+    """Time the CPU implementation of the path on a bounded sample of the workload; returns (units/s, s/step)."""
+    rng = np.random.default_rng(99)
+    wl.cpu_setup(impl, rng)
+    for _ in range(warmup):
+        wl.cpu_step(impl)
+    tot_units, t0 = 0.0, time.perf_counter()
+    for _ in range(steps):
+        tot_units += wl.cpu_step(impl)
+    dt = time.perf_counter() - t0
+    return tot_units / dt, dt / steps
+
+
 def run_reference_arm(args, rank, world):
     """--impl reference: the reference's own CPU implementation of the path on the host cores (oracle/_ref when
-    it travelled with the checkout, else the C port), rank 0 only."""
+    it travelled with the checkout, else the C port), rank 0 only, on a bounded sample of the same workload."""
     if rank != 0:
         return
     impl, kind = cpu_impl()
     cores = os.cpu_count() or 1
     impl.set_threads(cores)
     wl = WORKLOADS[args.workload]()
-
-    class _Seed:
-        counter, key = [0, 0, 0, 0], [1997, 0]
-    wl.seed = _Seed()
-    wl.rows, wl.cols = getattr(wl, "rows", 0), getattr(wl, "cols", 0)
-    if args.workload != "c2":
-        print(json.dumps({"impl": "reference", "unavailable": f"reference arm implemented for c2 only, not {args.workload}"}))
-        return
-    vals = []
-    sample = ""
-    for i in range(args.warmup + args.steps):
-        t0 = time.perf_counter()
-        v, sample = wl.cpu_baseline(impl) if i == 0 else (None, sample)
-        if v is None:
-            ctr, key = wl.seed.counter, wl.seed.key
-            t0 = time.perf_counter()
-            impl.fill_dense_unpacked("R", wl.rows, wl.cols, "G", "L", 64, wl.cols, 64 * i, 0, ctr, key, np.float64)
-            v = 64 * wl.cols / 1e9 / (time.perf_counter() - t0)
-        if i >= args.warmup:
-            vals.append(v)
-    value = float(np.mean(vals))
+    value, sec = time_cpu(wl, impl, max(args.warmup, 1), args.steps)
     line = {"impl": "reference", "metric": wl.metric, "value": value, "unit": wl.unit, "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 64 * wl.cols / 1e9 / value * 1e3,
+            "steps": args.steps, "warmup": max(args.warmup, 1), "ms_per_step": sec * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": wl.dtype, "data": "synthetic",
-            "config": {"workload": wl.name, "reference_sample": "64 x 1000000 row slice per step (the full output, "
-                       "65.5 GB, does not fit the time budget on CPU)"},
+            "config": {"workload": wl.name, "reference_sample": wl.cpu_sample},
             "cpu_baseline": {"value": value, "unit": wl.unit, "cores": impl.get_threads(), "kind": kind,
-                             "sample": "64 x 1000000 row slice via fill_dense_unpacked per step"},
-            "e2e": {"value": value, "unit": wl.unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+                             "sample": wl.cpu_sample},
+            "e2e": {"value": value, "unit": wl.unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
     print(json.dumps(line))
 
 
@@ -531,11 +577,10 @@ def main():
         impl, kind = cpu_impl()
         cores = os.cpu_count() or 1
         impl.set_threads(cores)
-        v, sample = wl.cpu_baseline(impl)
-        if v is not None:
-            cpu = {"value": v, "unit": wl.unit, "cores": impl.get_threads(), "kind": kind, "sample": sample}
-        else:
-            cpu = {"value": None, "unit": wl.unit, "cores": impl.get_threads(), "kind": kind, "sample": sample}
+        n_cpu = {"c1": 3, "c2": 20, "c3": 2, "c4": 3, "c5": 3}[args.workload]
+        v, _ = time_cpu(wl, impl, 1, n_cpu)
+        cpu = {"value": v, "unit": wl.unit, "cores": impl.get_threads(), "kind": kind,
+               "sample": wl.cpu_sample + f" ({n_cpu} steps after 1 warm-up)"}
 
     if rank == 0:
         line = {"metric": wl.metric, "value": value, "unit": wl.unit, "n_gpus": world, "steps": args.steps,
