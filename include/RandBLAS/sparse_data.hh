@@ -1,0 +1,132 @@
+// randblas_b200 -- header-only drop-in layer, part 4: sparse matrix containers (views and owners).
+// Field names and constructor signatures follow RandBLAS/sparse_data/{base,coo_matrix,csr_matrix,csc_matrix}.hh;
+// conversions, sorting and the CPU SpMM kernels of the reference are outside the hot path.
+#pragma once
+#include "base.hh"
+
+namespace RandBLAS {
+namespace sparse_data {
+
+enum class IndexBase : char { Zero = 'Z', One = 'O' };                          // sparse_data/base.hh:52
+enum class NonzeroSort : char { CSC = 'C', CSR = 'R', None = 'N' };             // sparse_data/base.hh:108-118
+
+// csr_matrix.hh:73-245
+template <typename T, typename sint_t = int64_t>
+struct CSRMatrix {
+    using scalar_t = T;
+    using index_t = sint_t;
+    const int64_t n_rows;
+    const int64_t n_cols;
+    bool own_memory;
+    int64_t nnz;
+    IndexBase index_base;
+    T* vals;
+    sint_t* rowptr;
+    sint_t* colidxs;
+    CSRMatrix(int64_t n_rows, int64_t n_cols)
+        : n_rows(n_rows), n_cols(n_cols), own_memory(true), nnz(0), index_base(IndexBase::Zero), vals(nullptr),
+          rowptr(nullptr), colidxs(nullptr) {}
+    CSRMatrix(int64_t n_rows, int64_t n_cols, int64_t nnz, T* vals, sint_t* rowptr, sint_t* colidxs,
+              IndexBase index_base = IndexBase::Zero)
+        : n_rows(n_rows), n_cols(n_cols), own_memory(false), nnz(nnz), index_base(index_base), vals(vals), rowptr(rowptr),
+          colidxs(colidxs) {}
+    ~CSRMatrix() {
+        if (own_memory) { delete[] vals; delete[] rowptr; delete[] colidxs; }
+    }
+    void reserve(int64_t arg_nnz) {                                              // csr_matrix.hh:186-197
+        randblas_require(arg_nnz > 0 && own_memory && colidxs == nullptr && vals == nullptr);
+        if (rowptr == nullptr) rowptr = new sint_t[n_rows + 1]{};
+        nnz = arg_nnz;
+        colidxs = new sint_t[nnz]{};
+        vals = new T[nnz]{};
+    }
+};
+
+// csc_matrix.hh:74-244
+template <typename T, typename sint_t = int64_t>
+struct CSCMatrix {
+    using scalar_t = T;
+    using index_t = sint_t;
+    const int64_t n_rows;
+    const int64_t n_cols;
+    bool own_memory;
+    int64_t nnz;
+    IndexBase index_base;
+    T* vals;
+    sint_t* rowidxs;
+    sint_t* colptr;
+    CSCMatrix(int64_t n_rows, int64_t n_cols)
+        : n_rows(n_rows), n_cols(n_cols), own_memory(true), nnz(0), index_base(IndexBase::Zero), vals(nullptr),
+          rowidxs(nullptr), colptr(nullptr) {}
+    CSCMatrix(int64_t n_rows, int64_t n_cols, int64_t nnz, T* vals, sint_t* rowidxs, sint_t* colptr,
+              IndexBase index_base = IndexBase::Zero)
+        : n_rows(n_rows), n_cols(n_cols), own_memory(false), nnz(nnz), index_base(index_base), vals(vals),
+          rowidxs(rowidxs), colptr(colptr) {}
+    ~CSCMatrix() {
+        if (own_memory) { delete[] vals; delete[] rowidxs; delete[] colptr; }
+    }
+    void reserve(int64_t arg_nnz) {
+        randblas_require(arg_nnz > 0 && own_memory && rowidxs == nullptr && vals == nullptr);
+        if (colptr == nullptr) colptr = new sint_t[n_cols + 1]{};
+        nnz = arg_nnz;
+        rowidxs = new sint_t[nnz]{};
+        vals = new T[nnz]{};
+    }
+};
+
+// coo_matrix.hh:82-308
+template <typename T, typename sint_t = int64_t>
+struct COOMatrix {
+    using scalar_t = T;
+    using index_t = sint_t;
+    const int64_t n_rows;
+    const int64_t n_cols;
+    bool own_memory;
+    int64_t nnz;
+    IndexBase index_base;
+    T* vals;
+    sint_t* rows;
+    sint_t* cols;
+    NonzeroSort sort;
+    COOMatrix(int64_t n_rows, int64_t n_cols)
+        : n_rows(n_rows), n_cols(n_cols), own_memory(true), nnz(0), index_base(IndexBase::Zero), vals(nullptr),
+          rows(nullptr), cols(nullptr), sort(NonzeroSort::None) {}
+    // view constructor. The reference scans the arrays here to classify their sort order (coo_matrix.hh:188-189);
+    // the GPU kernels do not depend on the order, so the tag is left at None unless the caller sets it.
+    COOMatrix(int64_t n_rows, int64_t n_cols, int64_t nnz, T* vals, sint_t* rows, sint_t* cols, bool compute_sort_type = true,
+              IndexBase index_base = IndexBase::Zero)
+        : n_rows(n_rows), n_cols(n_cols), own_memory(false), nnz(nnz), index_base(index_base), vals(vals), rows(rows),
+          cols(cols), sort(NonzeroSort::None) {
+        (void) compute_sort_type;
+    }
+    ~COOMatrix() {
+        if (own_memory) { delete[] vals; delete[] rows; delete[] cols; }
+    }
+    void reserve(int64_t arg_nnz) {
+        randblas_require(arg_nnz > 0 && own_memory && vals == nullptr && rows == nullptr && cols == nullptr);
+        nnz = arg_nnz;
+        vals = new T[nnz]{};
+        rows = new sint_t[nnz]{};
+        cols = new sint_t[nnz]{};
+    }
+};
+
+}  // namespace sparse_data
+
+using sparse_data::COOMatrix;
+using sparse_data::CSCMatrix;
+using sparse_data::CSRMatrix;
+using sparse_data::IndexBase;
+using sparse_data::NonzeroSort;
+
+namespace internal {
+// (fmt, idx0, idx1) as the C ABI wants them (include/randblas_b200.h, K4)
+template <typename T, typename I>
+inline void sp_arrays(const CSRMatrix<T, I>& A, int& fmt, const void*& i0, const void*& i1) { fmt = 0; i0 = A.rowptr; i1 = A.colidxs; }
+template <typename T, typename I>
+inline void sp_arrays(const CSCMatrix<T, I>& A, int& fmt, const void*& i0, const void*& i1) { fmt = 1; i0 = A.rowidxs; i1 = A.colptr; }
+template <typename T, typename I>
+inline void sp_arrays(const COOMatrix<T, I>& A, int& fmt, const void*& i0, const void*& i1) { fmt = 2; i0 = A.rows; i1 = A.cols; }
+}  // namespace internal
+
+}  // namespace RandBLAS

@@ -40,6 +40,8 @@ int rb_version(void);                 /* 100 * major + minor */
 int rb_release_workspace(void);
 /* info[0] = SM count, info[1] = compute capability * 10 + minor, info[2] = total global memory (bytes) */
 int rb_device_info(int64_t info[3]);
+/* cudaStreamSynchronize(stream) (NULL = default stream): used by the synchronous drop-in header layer */
+int rb_sync_stream(void* stream);
 
 /* ---- RNG state arithmetic (host-side, pure integer; RandBLAS/base.hh:116-119, Random123 array.h incr) ---- */
 void rb_rngstate_from_u64(uint64_t k, uint32_t ctr[4], uint32_t key[2]);

@@ -529,6 +529,11 @@ int rb_device_info(int64_t info[3]) {
     return 0;
 }
 
+int rb_sync_stream(void* stream) {
+    RB_CUDA(cudaStreamSynchronize((cudaStream_t) stream));
+    return 0;
+}
+
 void rb_rngstate_from_u64(uint64_t k, uint32_t ctr[4], uint32_t key[2]) {
     ctr[0] = ctr[1] = ctr[2] = ctr[3] = 0;
     key[0] = (uint32_t) k;

@@ -1,0 +1,174 @@
+// Drop-in check of the header-only C++ layer (include/RandBLAS.hh) against librandblas_b200.so, written the way
+// the reference's own gtest suites use the API (test/test_datastructures/test_denseskop.cc,
+// test/test_matmul_cores/linop_common.hh:309-389, test_sparseskop.cc:64-117, test_sketch_vector.cc, test_r123.cc).
+//   test_dropin --host : host-side checks only (no GPU needed): state arithmetic, distributions, error behaviour
+//   test_dropin        : everything; needs a CUDA device. Buffers are plain host memory, as a caller of the CPU
+//                        reference would pass them.
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <set>
+#include <vector>
+#include "RandBLAS.hh"
+
+using namespace RandBLAS;
+static int failures = 0;
+#define CHECK(cond)                                                        \
+    do {                                                                   \
+        if (!(cond)) { std::printf("FAIL %s:%d: %s\n", __FILE__, __LINE__, #cond); ++failures; } \
+    } while (0)
+
+template <typename F>
+static bool throws_error(F f) {
+    try { f(); } catch (const RandBLAS::Error&) { return true; } catch (...) { return false; }
+    return false;
+}
+
+static void host_checks() {
+    // RNGState(uint64) puts the integer into the key, little-endian limbs (test_r123.cc:679-698)
+    RNGState<> s(0x100000002ull);
+    CHECK(s.key[0] == 2u && s.key[1] == 1u);
+    CHECK(s.counter[0] == 0u && s.counter[3] == 0u);
+    // counter carries (test_r123.cc:714-797)
+    RNGState<> t;
+    t.counter.v[0] = 0xffffffffu; t.counter.v[1] = 0xffffffffu;
+    t.counter.incr(1);
+    CHECK(t.counter[0] == 0u && t.counter[1] == 0u && t.counter[2] == 1u);
+    // DenseDist fields (dense_skops.hh:231-350)
+    DenseDist D(7, 20);
+    CHECK(D.dim_major == 20 && D.dim_minor == 7 && D.natural_layout == blas::Layout::RowMajor);
+    CHECK(D.family == ScalarDist::Gaussian && D.major_axis == Axis::Long);
+    CHECK(std::fabs(D.isometry_scale - 1.0 / std::sqrt(7.0)) < 1e-15);
+    DenseDist Dt(20, 7, ScalarDist::Uniform, Axis::Short);
+    CHECK(Dt.dim_major == 7 && Dt.natural_layout == blas::Layout::RowMajor);
+    CHECK(throws_error([] { DenseDist bad(0, 5); }));
+    // next_state of an operator = seed + dim_minor * ceil(dim_major / 4) (dense_skops.hh:172-185)
+    DenseSkOp<float> S(D, RNGState<>(42));
+    CHECK(S.next_state.counter[0] == 7u * 5u && S.next_state.key == S.seed_state.key);
+    CHECK(S.buff == nullptr && S.own_memory && S.layout == blas::Layout::RowMajor);
+    // SparseDist (sparse_skops.hh:131-246)
+    SparseDist Ds(15, 7, 3);
+    CHECK(Ds.major_axis == Axis::Short && Ds.dim_major == 7 && Ds.dim_minor == 15 && Ds.full_nnz == 45);
+    CHECK(throws_error([] { SparseDist bad(4, 9, 5); }));       // vec_nnz > dim_major
+    SparseSkOp<double, DefaultRNG, int32_t> Ss(Ds, RNGState<>(1));
+    CHECK(Ss.nnz < 0 && Ss.next_state.counter[0] == 45u);
+    // full-operator overloads check dimensions before anything else (skge.hh:1089-1095)
+    std::vector<float> A(20 * 3), B(8 * 3);
+    CHECK(throws_error([&] { sketch_general(blas::Layout::ColMajor, blas::Op::NoTrans, blas::Op::NoTrans, 8, 3, 20, 1.0f, S,
+                                            A.data(), 20, 0.0f, B.data(), 8); }));
+}
+
+template <typename T>
+static void device_checks() {
+    const T tol = sizeof(T) == 4 ? T(1e-5) : T(1e-12);
+    RNGState<> seed(1997);
+    // --- fill_dense(S): allocation on demand, submatrix == slice of the full matrix (test_denseskop.cc:162-298)
+    DenseDist D(11, 53, ScalarDist::Uniform);
+    DenseSkOp<T> S(D, seed);
+    fill_dense(S);
+    CHECK(S.buff != nullptr);
+    std::vector<T> sub(4 * 10);
+    RNGState<> nxt = fill_dense_unpacked(blas::Layout::RowMajor, D, 4, 10, 3, 7, sub.data(), seed);
+    bool same = true;
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 10; ++j) same = same && sub[i * 10 + j] == S.buff[(3 + i) * 53 + 7 + j];
+    CHECK(same);
+    (void) nxt;
+    T mx = 0;
+    for (int64_t i = 0; i < 11 * 53; ++i) mx = std::max(mx, std::fabs(S.buff[i]));
+    CHECK(mx <= T(1.7320509) && mx > T(1.5));          // uniform on [-sqrt 3, sqrt 3]
+    // fill_dense(D, buff, seed) returns the operator's next_state (test_denseskop.cc:443-465)
+    std::vector<T> full(11 * 53);
+    RNGState<> n2 = fill_dense(D, full.data(), seed);
+    CHECK(n2 == S.next_state);
+    CHECK(std::memcmp(full.data(), S.buff, full.size() * sizeof(T)) == 0);
+
+    // --- operator applied to the identity reproduces the operator (linop_common.hh:309-389), unfilled operator
+    const int64_t d = 11, m = 53;
+    DenseSkOp<T> S0(D, seed);
+    std::vector<T> I(m * m, T(0)), B(d * m, T(0));
+    for (int64_t i = 0; i < m; ++i) I[i * m + i] = T(1);
+    sketch_general(blas::Layout::RowMajor, blas::Op::NoTrans, blas::Op::NoTrans, d, m, m, T(1), S0, I.data(), m, T(0),
+                   B.data(), m);
+    CHECK(S0.buff == nullptr);                         // an unfilled operator is not modified (skge.hh:174-181)
+    double num = 0, den = 0;
+    for (int64_t i = 0; i < d * m; ++i) { num += (B[i] - full[i]) * (B[i] - full[i]); den += full[i] * full[i]; }
+    CHECK(std::sqrt(num / den) < tol);
+    // right sketch with the transposed operator: I * S^T (skge.hh:947-968)
+    std::vector<T> Bt(m * d, T(0));
+    sketch_general(blas::Layout::ColMajor, blas::Op::NoTrans, blas::Op::Trans, m, d, m, T(1), I.data(), m, S0, T(0),
+                   Bt.data(), m);
+    num = 0;
+    for (int64_t i = 0; i < d; ++i)
+        for (int64_t j = 0; j < m; ++j) { double e = Bt[j + i * m] - full[i * m + j]; num += e * e; }
+    CHECK(std::sqrt(num / den) < tol);
+
+    // --- sketch_vector == row sums of S applied to ones (skve.hh:141-164)
+    std::vector<T> x(m, T(1)), y(d, T(0));
+    sketch_vector(blas::Op::NoTrans, T(1), S0, x.data(), 1, T(0), y.data(), 1);
+    bool ok = true;
+    for (int64_t i = 0; i < d; ++i) {
+        double r = 0;
+        for (int64_t j = 0; j < m; ++j) r += full[i * m + j];
+        ok = ok && std::fabs(y[i] - r) <= 1e3 * tol * (1 + std::fabs(r));
+    }
+    CHECK(ok);
+
+    // --- SASO: exactly vec_nnz distinct row indices per column, values +-1 (test_sparseskop.cc:64-117)
+    SparseDist Ds(7, 200, 3);
+    SparseSkOp<T, DefaultRNG, int32_t> Ss(Ds, seed);
+    fill_sparse(Ss);
+    CHECK(Ss.nnz == 600);
+    ok = true;
+    for (int64_t c = 0; c < 200; ++c) {
+        std::set<int> rows;
+        for (int j = 0; j < 3; ++j) {
+            rows.insert(Ss.rows[3 * c + j]);
+            ok = ok && Ss.cols[3 * c + j] == c && std::fabs(Ss.vals[3 * c + j]) == T(1);
+            ok = ok && Ss.rows[3 * c + j] >= 0 && Ss.rows[3 * c + j] < 7;
+        }
+        ok = ok && rows.size() == 3;
+    }
+    CHECK(ok);
+    // sampled (COO arrays) and unsampled (regenerated in the kernel) operators give the same product
+    std::vector<T> A(200 * 5), B1(7 * 5, T(0)), B2(7 * 5, T(0));
+    for (size_t i = 0; i < A.size(); ++i) A[i] = T((int) (i * 2654435761u % 1000)) / T(500) - T(1);
+    SparseSkOp<T, DefaultRNG, int32_t> Su(Ds, seed);
+    sketch_general(blas::Layout::ColMajor, blas::Op::NoTrans, blas::Op::NoTrans, 7, 5, 200, T(1), Ss, A.data(), 200, T(0),
+                   B1.data(), 7);
+    sketch_general(blas::Layout::ColMajor, blas::Op::NoTrans, blas::Op::NoTrans, 7, 5, 200, T(1), Su, A.data(), 200, T(0),
+                   B2.data(), 7);
+    CHECK(Su.nnz < 0);
+    ok = true;
+    for (int i = 0; i < 35; ++i) ok = ok && std::fabs(B1[i] - B2[i]) <= 100 * tol;
+    CHECK(ok);
+
+    // --- sketch_sparse applied to a sparse identity reproduces S (test_sketch_sparse.cc, COO by design)
+    std::vector<T> ones(m, T(1));
+    std::vector<int64_t> idx(m);
+    for (int64_t i = 0; i < m; ++i) idx[i] = i;
+    COOMatrix<T> Isp(m, m, m, ones.data(), idx.data(), idx.data());
+    std::vector<T> Bs(d * m, T(0));
+    sketch_sparse(blas::Layout::RowMajor, blas::Op::NoTrans, blas::Op::NoTrans, d, m, m, T(1), S0, 0, 0, Isp, T(0), Bs.data(),
+                  m);
+    num = 0;
+    for (int64_t i = 0; i < d * m; ++i) num += (Bs[i] - full[i]) * (Bs[i] - full[i]);
+    CHECK(std::sqrt(num / den) < tol);
+
+    // --- argument errors surface as RandBLAS::Error before data is touched (skge.hh:183-192)
+    CHECK(throws_error([&] { sketch_general(blas::Layout::RowMajor, blas::Op::NoTrans, blas::Op::NoTrans, d, m, m, T(1), S0, 1,
+                                            0, I.data(), m, T(0), B.data(), m); }));
+    CHECK(throws_error([&] { sketch_general(blas::Layout::RowMajor, blas::Op::NoTrans, blas::Op::NoTrans, d, m, m, T(1), S0, 0,
+                                            0, I.data(), m - 1, T(0), B.data(), m); }));
+}
+
+int main(int argc, char** argv) {
+    host_checks();
+    if (!(argc > 1 && std::strcmp(argv[1], "--host") == 0)) {
+        device_checks<float>();
+        device_checks<double>();
+    }
+    std::printf(failures ? "test_dropin: %d FAILURES\n" : "test_dropin: all checks passed\n", failures);
+    return failures ? 1 : 0;
+}
