@@ -321,11 +321,11 @@ class C3DenseSketchF64(Workload):
         self.Bshard = torch.zeros(self.d * self.n // world, dtype=torch.float64, device="cuda")
 
     def step(self):
-        # ColMajor A (lda = m_local): rank g holds rows [g m_local, (g+1) m_local) => columns co_s.. of S
-        self.rb.sketch_general("C", "N", "N", self.d, self.n, self.m_local, 1.0, self.S, 0, self.m_local * self.rank,
-                               self.A, self.m_local, 0.0, self.B, self.d)
-        if self.world > 1:
-            self.torch.distributed.reduce_scatter_tensor(self.Bshard, self.B)
+        # ColMajor A (lda = m_local): rank g holds rows [g m_local, (g+1) m_local) of A <=> columns co_s.. of S;
+        # partial products are summed by one NCCL reduce-scatter (randblas_b200/sharding.py)
+        from randblas_b200.sharding import sketch_general_mshard
+        sketch_general_mshard("C", self.d, self.n, self.m_local * self.world, 1.0, self.S, self.A, self.m_local, self.B,
+                              self.Bshard, self.rank, self.world)
 
     def units_per_step(self):
         return self.m_local * self.n * 8 / 1e9
