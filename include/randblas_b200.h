@@ -63,6 +63,10 @@ int rb_sparse_next_state(int64_t n_rows, int64_t n_cols, int64_t vec_nnz, char m
  * as called at RandBLAS/random_gen.hh:107,135. */
 int rb_philox_words(const uint32_t ctr[4], const uint32_t key[2], int64_t n_blocks, uint32_t* out, void* stream);
 
+/* (g0[i], g1[i]) = boxmuller(w0[i], w1[i]): the float transform the Gaussian family applies to two Philox words
+ * (r123::boxmuller as called at RandBLAS/random_gen.hh:62-74). For checks of the device libm emulation on chosen words. */
+int rb_boxmuller_words(int64_t n, const uint32_t* w0, const uint32_t* w1, float* g0, float* g1, void* stream);
+
 /* ---- K1: fill_dense ----
  * Replaces RandBLAS::fill_dense_unpacked (RandBLAS/dense_skops.hh:563-606) and through it
  * fill_dense(D, buff, seed) (:623-626), fill_dense(S) (:649-658), dense::fill_dense_submat_impl (:96-170).

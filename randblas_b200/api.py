@@ -243,6 +243,13 @@ def philox_words(state, n_blocks, out):
     return out
 
 
+def boxmuller_words(w0, w1, g0, g1):
+    """(g0, g1) = r123::boxmuller(w0, w1) element-wise (RandBLAS/random_gen.hh:62-74); uint32 words as int32 if torch."""
+    n = int(w0.numel()) if hasattr(w0, "numel") else int(w0.size)
+    call("rb_boxmuller_words", "qppppp", n, _ptr(w0), _ptr(w1), _ptr(g0), _ptr(g1), _stream(g0))
+    return g0, g1
+
+
 def fill_dense_unpacked(layout, D, n_rows, n_cols, ro_s, co_s, buff, seed, ld=0):
     """RandBLAS/dense_skops.hh:563-606. Returns the advanced RNGState."""
     sfx, _ = _sfx(_dtype_of(buff))

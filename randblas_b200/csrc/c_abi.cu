@@ -40,6 +40,32 @@ int sm_count() {
     return cached[dev];
 }
 
+const double2* logf_table_device() {
+    static std::mutex mu;
+    static double2* tabs[64] = {nullptr};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    std::lock_guard<std::mutex> lk(mu);
+    if (!tabs[dev]) {
+        std::vector<double2> h(LOGF_TABLE_ENTRIES);
+        for (int k = -33; k <= 0; ++k)
+            for (int i = 0; i < 16; ++i) {
+                h[(k + 33) * 16 + i].x = h_logf_tab[2 * i];
+                h[(k + 33) * 16 + i].y = std::fma((double) k, 0x1.62e42fefa39efp-1, h_logf_tab[2 * i + 1]);
+            }
+        const double hpi = 0x1.921fb54442d18p+0;
+        double* q = reinterpret_cast<double*>(h.data()) + QUADRANT_TABLE_OFFSET;     // -n pi/2, n = -2..2
+        q[0] = 2 * hpi; q[1] = hpi; q[2] = 0.0; q[3] = -hpi; q[4] = -2 * hpi; q[5] = 0.0;
+        double2* d = nullptr;
+        if (cudaMalloc(&d, h.size() * sizeof(double2)) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        if (cudaMemcpy(d, h.data(), h.size() * sizeof(double2), cudaMemcpyHostToDevice) != cudaSuccess) {
+            cudaGetLastError(); cudaFree(d); return nullptr;
+        }
+        tabs[dev] = d;
+    }
+    return tabs[dev];
+}
+
 int64_t get_option(const char* name) {
     if (!std::strcmp(name, "dense_path")) return g_dense_path.load();
     if (!std::strcmp(name, "tc_splits")) return g_tc_splits.load();
@@ -588,6 +614,25 @@ int rb_philox_words(const uint32_t ctr[4], const uint32_t key[2], int64_t n_bloc
     rc = launch_philox_words(load_ctr(ctr), PhiloxKey{key[0], key[1]}, n_blocks, (uint32_t*) so.dev, (cudaStream_t) stream);
     int rc2 = so.close();
     return rc ? rc : rc2;
+}
+
+int rb_boxmuller_words(int64_t n, const uint32_t* w0, const uint32_t* w1, float* g0, float* g1, void* stream) {
+    RB_REQUIRE(n >= 0);
+    if (n == 0) return 0;
+    RB_REQUIRE(w0 != nullptr && w1 != nullptr && g0 != nullptr && g1 != nullptr);
+    cudaStream_t st = (cudaStream_t) stream;
+    Staged s0, s1, o0, o1;
+    int rc = s0.open(w0, 4, 1, n, n, true, false, st); if (rc) return rc;
+    rc = s1.open(w1, 4, 1, n, n, true, false, st); if (rc) return rc;
+    rc = o0.open(g0, 4, 1, n, n, false, true, st); if (rc) return rc;
+    rc = o1.open(g1, 4, 1, n, n, false, true, st); if (rc) return rc;
+    rc = launch_boxmuller_words(n, (const uint32_t*) s0.dev, (const uint32_t*) s1.dev, (float*) o0.dev, (float*) o1.dev, st);
+    int rc2;
+    rc2 = s0.close(); if (!rc) rc = rc2;
+    rc2 = s1.close(); if (!rc) rc = rc2;
+    rc2 = o0.close(); if (!rc) rc = rc2;
+    rc2 = o1.close(); if (!rc) rc = rc2;
+    return rc;
 }
 
 int rb_fill_dense_f32(char layout, int64_t D_rows, int64_t D_cols, char family, char major_axis, int64_t n_rows,

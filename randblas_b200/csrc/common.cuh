@@ -68,6 +68,8 @@ inline void store_ctr(Ctr128 c, uint32_t* out) {
 }
 
 int sm_count();   // SMs of the current device (cached)
+// device copy of the folded logf table (philox.cuh), built once per device; nullptr on failure
+const double2* logf_table_device();
 
 // How a DenseSkOp window is addressed by the fused kernels: element (i, j) of the operator
 // (absolute row/col indices into the full D.n_rows x D.n_cols sample).
@@ -76,6 +78,7 @@ struct DenseGen {
     PhiloxKey key;
     int64_t R;         // Philox blocks per major-axis vector = ceil(dim_major / 4)
     int nat_row;       // 1: natural layout RowMajor => (v,u) = (row,col); 0: (v,u) = (col,row)
+    const double2* logtab;   // folded logf table in global memory (Gaussian family)
 };
 inline DenseGen make_dense_gen(const DenseDistInfo& D, const uint32_t* ctr, const uint32_t* key) {
     DenseGen g;
@@ -83,6 +86,7 @@ inline DenseGen make_dense_gen(const DenseDistInfo& D, const uint32_t* ctr, cons
     g.key = PhiloxKey{key[0], key[1]};
     g.R = (D.dim_major + 3) / 4;
     g.nat_row = D.natural_layout == 'R';
+    g.logtab = (D.family == 'G') ? logf_table_device() : nullptr;
     return g;
 }
 

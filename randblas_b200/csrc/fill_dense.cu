@@ -29,6 +29,7 @@ struct FillArgs {
     int64_t sv, su;     // destination strides (elements) per vector step / per position step
     int64_t total;      // nv * nblk
     int64_t q_step, r_step;  // grid stride decomposed: stride = q_step * nblk + r_step
+    const double2* logtab;
 };
 
 template <typename T>
@@ -45,9 +46,9 @@ __device__ __forceinline__ void store4_vec<double>(double* p, double a, double b
 
 template <typename T, bool GAUSS, bool WALK_V>
 __global__ void __launch_bounds__(256) fill_dense_kernel(const FillArgs a, T* __restrict__ dst) {
-    __shared__ __align__(16) double logtab[32];
+    __shared__ __align__(16) double2 logtab[GAUSS ? LOGF_TABLE_ENTRIES : 1];
     if constexpr (GAUSS) {
-        load_logf_table(logtab);
+        load_logf_table(logtab, a.logtab);
         __syncthreads();
     }
     int64_t L = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
@@ -101,13 +102,14 @@ struct FillTileArgs {
     int64_t R, v0, nv, u0, nu, blk_first, nblk, sv;
     int64_t tiles_per_vec, total_tiles;
     int64_t q_step, r_step;     // gridDim.x = q_step * tiles_per_vec + r_step
+    const double2* logtab;
 };
 
 template <typename T, bool GAUSS>
-__global__ void __launch_bounds__(256, 3) fill_dense_tiled_kernel(const FillTileArgs a, T* __restrict__ dst) {
-    __shared__ __align__(16) double logtab[32];
+__global__ void __launch_bounds__(256, 4) fill_dense_tiled_kernel(const FillTileArgs a, T* __restrict__ dst) {
+    __shared__ __align__(16) double2 logtab[GAUSS ? LOGF_TABLE_ENTRIES : 1];
     if constexpr (GAUSS) {
-        load_logf_table(logtab);
+        load_logf_table(logtab, a.logtab);
         __syncthreads();
     }
     int64_t t = blockIdx.x;
@@ -119,19 +121,18 @@ __global__ void __launch_bounds__(256, 3) fill_dense_tiled_kernel(const FillTile
         const int64_t b0 = ch * TILE;                                  // first block of the tile (window-relative)
         const Ctr128 base = ctr_add(a.ctr, (uint64_t) ((a.v0 + vl) * a.R + a.blk_first + b0));
         const uint64_t base_lo = ((uint64_t) base.c1 << 32) | base.c0;
-        const uint64_t base_hi = ((uint64_t) base.c3 << 32) | base.c2;
         const int64_t ur0 = (a.blk_first + b0) * 4 - a.u0;             // position of the tile's first sample
         T* p0 = dst + vl * a.sv + ur0;
         const int64_t nb = min((int64_t) TILE, a.nblk - b0);           // blocks in this tile
         const bool interior = (ur0 >= 0) && (ur0 + 4 * nb <= a.nu) &&
                               ((reinterpret_cast<uintptr_t>(p0) & (4 * sizeof(T) - 1)) == 0);
-        if (interior && nb == TILE) {
+        // predicate-free path: whole interior tile whose block counters do not carry out of the low 64 bits
+        if (interior && nb == TILE && base_lo + (uint64_t) TILE >= base_lo) {
 #pragma unroll
             for (int j = 0; j < FILL_UNROLL; ++j) {
                 const uint32_t off = j * 256 + threadIdx.x;
                 const uint64_t lo = base_lo + off;
-                const uint64_t hi = base_hi + (lo < base_lo ? 1ull : 0ull);
-                const Ctr128 c{(uint32_t) lo, (uint32_t) (lo >> 32), (uint32_t) hi, (uint32_t) (hi >> 32)};
+                const Ctr128 c{(uint32_t) lo, (uint32_t) (lo >> 32), base.c2, base.c3};
                 const float4 f = transform4<GAUSS>(philox4x32_10(c, a.key), logtab);
                 store4_vec<T>(p0 + 4 * off, finish_sample<T, GAUSS>(f.x), finish_sample<T, GAUSS>(f.y),
                               finish_sample<T, GAUSS>(f.z), finish_sample<T, GAUSS>(f.w));
@@ -167,6 +168,32 @@ __global__ void philox_words_kernel(Ctr128 ctr, PhiloxKey key, int64_t n_blocks,
         out[i] = philox4x32_10(ctr_add(ctr, (uint64_t) i), key);
 }
 
+__global__ void __launch_bounds__(256) boxmuller_words_kernel(int64_t n, const uint32_t* __restrict__ w0,
+                                                              const uint32_t* __restrict__ w1, float* __restrict__ g0,
+                                                              float* __restrict__ g1, const double2* __restrict__ gtab) {
+    __shared__ __align__(16) double2 logtab[LOGF_TABLE_ENTRIES];
+    load_logf_table(logtab, gtab);
+    __syncthreads();
+    for (int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t) gridDim.x * blockDim.x) {
+        float a, b;
+        boxmuller(w0[i], w1[i], logtab, a, b);
+        g0[i] = a;
+        g1[i] = b;
+    }
+}
+
+int launch_boxmuller_words(int64_t n, const uint32_t* w0, const uint32_t* w1, float* g0, float* g1, cudaStream_t st) {
+    if (n <= 0) return 0;
+    const double2* tab = logf_table_device();
+    if (!tab) return fail_cuda(cudaErrorMemoryAllocation, "logf table");
+    int64_t grid = (n + 255) / 256;
+    if (grid > (int64_t) sm_count() * 8) grid = (int64_t) sm_count() * 8;
+    boxmuller_words_kernel<<<(unsigned) grid, 256, 0, st>>>(n, w0, w1, g0, g1, tab);
+    count_launch();
+    RB_CUDA(cudaGetLastError());
+    return 0;
+}
+
 int launch_philox_words(Ctr128 ctr, PhiloxKey key, int64_t n_blocks, uint32_t* out, cudaStream_t st) {
     if (n_blocks <= 0) return 0;
     int64_t grid = (n_blocks + 255) / 256;
@@ -184,8 +211,9 @@ template <typename T>
 int launch_fill_dense(const DenseGen& g, char family, int64_t v0, int64_t nv, int64_t u0, int64_t nu, T* dst,
                       int64_t sv, int64_t su, cudaStream_t st) {
     if (nv <= 0 || nu <= 0) return 0;
+    if (family == 'G' && !g.logtab) return fail_cuda(cudaErrorMemoryAllocation, "logf table");
     FillArgs a;
-    a.ctr = g.ctr; a.key = g.key; a.R = g.R;
+    a.ctr = g.ctr; a.key = g.key; a.R = g.R; a.logtab = g.logtab;
     a.v0 = v0; a.nv = nv; a.u0 = u0; a.nu = nu;
     a.blk_first = u0 / 4;
     a.nblk = (u0 + nu - 1) / 4 - a.blk_first + 1;
@@ -196,12 +224,12 @@ int launch_fill_dense(const DenseGen& g, char family, int64_t v0, int64_t nv, in
     const bool gauss_ = family == 'G';
     if (!walk_v && su == 1 && a.nblk >= 2 * 256 * FILL_UNROLL) {
         FillTileArgs t;
-        t.ctr = g.ctr; t.key = g.key; t.R = g.R; t.v0 = v0; t.nv = nv; t.u0 = u0; t.nu = nu;
+        t.ctr = g.ctr; t.key = g.key; t.R = g.R; t.logtab = g.logtab; t.v0 = v0; t.nv = nv; t.u0 = u0; t.nu = nu;
         t.blk_first = a.blk_first; t.nblk = a.nblk; t.sv = sv;
         t.tiles_per_vec = (a.nblk + 256 * FILL_UNROLL - 1) / (256 * FILL_UNROLL);
         t.total_tiles = nv * t.tiles_per_vec;
         int64_t tgrid = t.total_tiles;
-        const int64_t tcap = (int64_t) sm_count() * 6;
+        const int64_t tcap = (int64_t) sm_count() * 8;
         if (tgrid > tcap) tgrid = tcap;
         t.q_step = tgrid / t.tiles_per_vec;
         t.r_step = tgrid % t.tiles_per_vec;

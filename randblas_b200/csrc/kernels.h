@@ -12,6 +12,8 @@ void count_tc_launch();
 
 int launch_philox_words(Ctr128 ctr, PhiloxKey key, int64_t n_blocks, uint32_t* out, cudaStream_t st);
 
+int launch_boxmuller_words(int64_t n, const uint32_t* w0, const uint32_t* w1, float* g0, float* g1, cudaStream_t st);
+
 template <typename T>
 int launch_fill_dense(const DenseGen& g, char family, int64_t v0, int64_t nv, int64_t u0, int64_t nu, T* dst,
                       int64_t sv, int64_t su, cudaStream_t st);

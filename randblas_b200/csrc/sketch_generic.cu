@@ -19,10 +19,10 @@ constexpr int TI = 64, TJ = 64, TK = 16, NT = 256;
 
 template <typename T, bool GAUSS, bool FROM_MEM>
 __global__ void __launch_bounds__(NT) dense_generic_kernel(const DenseProblem<T> p) {
-    __shared__ __align__(16) double logtab[32];
+    __shared__ __align__(16) double2 logtab[(GAUSS && !FROM_MEM) ? LOGF_TABLE_ENTRIES : 1];
     __shared__ T Xs[TK][TI + 4];
     __shared__ T Ys[TK][TJ + 4];
-    if constexpr (GAUSS && !FROM_MEM) load_logf_table(logtab);
+    if constexpr (GAUSS && !FROM_MEM) load_logf_table(logtab, p.gen.logtab);
 
     const int tid = threadIdx.x;
     const int64_t i0 = (int64_t) blockIdx.y * TI, j0 = (int64_t) blockIdx.x * TJ;

@@ -49,6 +49,7 @@ constexpr int MAX_CHAIN_STEPS = 40;       // K steps accumulated in TMEM before 
 struct TcArgs {
     Ctr128 ctr;
     PhiloxKey key;
+    const double2* logtab;
     int64_t R;
     int64_t v0;        // first operator vector (row of X)
     int64_t ublk0;     // Philox block that holds position k = 0 of a vector: u0 / 4
@@ -153,7 +154,7 @@ __device__ __forceinline__ float lo_trunc(float y) { return __fsub_rn(y, __uint_
 template <bool GAUSS>
 __global__ void __launch_bounds__(TC_THREADS, 1) skge3_tc_kernel(const __grid_constant__ CUtensorMap tmY, const TcArgs a) {
     extern __shared__ uint8_t smem_raw[];
-    __shared__ __align__(16) double logtab[32];
+    __shared__ __align__(16) double2 logtab[GAUSS ? LOGF_TABLE_ENTRIES : 1];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
     uint8_t* smem = smem_raw + (base - raw);
@@ -166,7 +167,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) skge3_tc_kernel(const __grid_co
     const uint32_t bar_accum = bar0 + 8u * (3 * STAGES);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + BAR_OFFSET + 8 * (3 * STAGES + 1));
 
-    if constexpr (GAUSS) load_logf_table(logtab);
+    if constexpr (GAUSS) load_logf_table(logtab, a.logtab);
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(bar_full(s), 1);
@@ -366,6 +367,7 @@ EncodeTiledFn encode_tiled() {
 int launch_dense_tc_f32(const DenseProblem<float>& p, cudaStream_t st) {
     // shapes / layouts this kernel takes; everything else goes to the generic kernel
     if (p.S_buff != nullptr) return -1;
+    if (p.family == 'G' && !p.gen.logtab) return -1;
     if (!(p.uk == 1 && p.vi == 1)) return -1;                 // Philox blocks must run along K
     if (p.yrs != 1) return -1;                                // Y must be K-contiguous
     if (p.K < 64 || p.P < 1 || p.Q < 1) return -1;
@@ -410,7 +412,7 @@ int launch_dense_tc_f32(const DenseProblem<float>& p, cudaStream_t st) {
     if (cr != CUDA_SUCCESS) return -1;
 
     TcArgs a;
-    a.ctr = p.gen.ctr; a.key = p.gen.key; a.R = p.gen.R;
+    a.ctr = p.gen.ctr; a.key = p.gen.key; a.R = p.gen.R; a.logtab = p.gen.logtab;
     a.v0 = p.v0;
     a.kshift = kshift;
     a.ublk0 = p.u0 >> 2;

@@ -32,6 +32,7 @@ constexpr int D_THREADS = 256;
 struct DmmaArgs {
     Ctr128 ctr;
     PhiloxKey key;
+    const double2* logtab;
     int64_t R, v0, ublk0;
     int kshift;
     int64_t P, Q, K;
@@ -57,11 +58,11 @@ __device__ __forceinline__ void cp_async16(void* dst, const void* src, int src_b
 
 template <bool GAUSS>
 __global__ void __launch_bounds__(D_THREADS, 1) skge3_dmma_kernel(const DmmaArgs a) {
-    __shared__ __align__(16) double logtab[32];
+    __shared__ __align__(16) double2 logtab[GAUSS ? LOGF_TABLE_ENTRIES : 1];
     extern __shared__ __align__(16) double dsm[];
     double* Xs = dsm;                              // [2][DM][DLD]
     double* Ys = dsm + 2 * DM * DLD;               // [2][DN][DLD]
-    if constexpr (GAUSS) load_logf_table(logtab);
+    if constexpr (GAUSS) load_logf_table(logtab, a.logtab);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int wi = warp >> 2, wj = warp & 3;       // 2 x 4 warps
@@ -198,6 +199,7 @@ __global__ void __launch_bounds__(256) splitk_reduce_f64_kernel(const double* __
 
 int launch_dense_dmma_f64(const DenseProblem<double>& p, cudaStream_t st) {
     if (p.S_buff != nullptr) return -1;
+    if (p.family == 'G' && !p.gen.logtab) return -1;
     if (!(p.uk == 1 && p.vi == 1)) return -1;                 // Philox blocks must run along K
     if (p.yrs != 1) return -1;                                // Y must be K-contiguous
     if (p.K < 32 || p.P < 1 || p.Q < 1) return -1;
@@ -226,7 +228,7 @@ int launch_dense_dmma_f64(const DenseProblem<double>& p, cudaStream_t st) {
         if (splits > steps) splits = (int) steps;
     }
     DmmaArgs a;
-    a.ctr = p.gen.ctr; a.key = p.gen.key; a.R = p.gen.R;
+    a.ctr = p.gen.ctr; a.key = p.gen.key; a.R = p.gen.R; a.logtab = p.gen.logtab;
     a.v0 = p.v0;
     a.kshift = (int) (p.u0 & 3);
     a.ublk0 = p.u0 >> 2;

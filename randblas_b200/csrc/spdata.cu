@@ -25,7 +25,7 @@ namespace {
 
 // one operator entry from natural coordinates (v, u)
 template <typename T, bool GAUSS>
-__device__ __forceinline__ T gen_entry(const DenseGen& g, int64_t v, int64_t u, const double* logtab) {
+__device__ __forceinline__ T gen_entry(const DenseGen& g, int64_t v, int64_t u, const double2* logtab) {
     const uint4 w = philox4x32_10(ctr_add(g.ctr, (uint64_t) (v * g.R + (u >> 2))), g.key);
     const int lane = (int) (u & 3);
     float f;
@@ -47,8 +47,8 @@ __global__ void __launch_bounds__(256) spdata_colowner_kernel(const SpDataProble
                                                               const IDX* __restrict__ ptrN, const IDX* __restrict__ kidx,
                                                               const T* __restrict__ vals, int64_t seg_off,
                                                               int64_t k_off, int u_blocked) {
-    __shared__ __align__(16) double logtab[32];
-    if constexpr (GAUSS) { load_logf_table(logtab); __syncthreads(); }
+    __shared__ __align__(16) double2 logtab[GAUSS ? LOGF_TABLE_ENTRIES : 1];
+    if constexpr (GAUSS) { load_logf_table(logtab, p.gen.logtab); __syncthreads(); }
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t) blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t) gridDim.x * blockDim.x) >> 5;

@@ -77,6 +77,31 @@ def test_philox_words_bit_exact(gpu, port, gold):
             assert list(got[i]) == list(port.philox(port.ctr_incr(ctr, i), [42, 7]))
 
 
+def test_boxmuller_edge_words_and_random_words_bit_exact(port):
+    """The device's libm emulation (philox.cuh) against the oracle's r123::boxmuller restatement on chosen words:
+    every quadrant boundary of the angle, the largest and smallest radii (u01 == 1 gives r = -0: the signs of the
+    zeros must match), and 2^18 random word pairs. Bit-exact on this image's glibc; the contract is <= 2 ulp."""
+    import randblas_b200 as rb
+    rng = np.random.default_rng(3)
+    special = [0, 1, 0x7FFFFFFF, 0x80000000, 0x80000001, 0xFFFFFFFF, 0xFFFFFF80, 0xFFFFFF7F, 0x20000000, 0x1FFFFFE0,
+               0x20000020, 0x60000000, 0x5FFFFFC0, 0xA0000000, 0xE0000000, 0xDFFFFFE0, 0x40000000, 0xC0000000, 0x3FFFFFFF]
+    w0 = np.array([a for a in special for _ in special], np.uint32)
+    w1 = np.array([b for _ in special for b in special], np.uint32)
+    w0 = np.concatenate([w0, rng.integers(0, 1 << 32, 1 << 18, dtype=np.uint64).astype(np.uint32)])
+    w1 = np.concatenate([w1, rng.integers(0, 1 << 32, 1 << 18, dtype=np.uint64).astype(np.uint32)])
+    g0 = np.zeros(w0.size, np.float32)
+    g1 = np.zeros(w0.size, np.float32)
+    rb.boxmuller_words(w0, w1, g0, g1)          # host buffers: staged by the C ABI
+    want = np.array([port.boxmuller(int(a), int(b)) for a, b in zip(w0, w1)], np.float32)
+    d0 = ulp_diff_f32(g0, want[:, 0])
+    d1 = ulp_diff_f32(g1, want[:, 1])
+    assert max(d0, d1) <= 2, (d0, d1)
+    print("boxmuller max ulp:", max(d0, d1))
+    # bit patterns, including the sign of zero, on this image
+    assert np.array_equal(g0.view(np.uint32), want[:, 0].copy().view(np.uint32))
+    assert np.array_equal(g1.view(np.uint32), want[:, 1].copy().view(np.uint32))
+
+
 # ------------------------------------------------------------------------------------ fill_dense
 def test_fill_dense_goldens(gpu, gold):
     worst = 0
