@@ -18,6 +18,7 @@ static std::atomic<int64_t> g_launches{0};
 static std::atomic<int64_t> g_dense_path{0};
 static std::atomic<int64_t> g_tc_launches{0};
 static std::atomic<int64_t> g_tc_splits{0};
+static std::atomic<int64_t> g_saso_path{0};     // 0 auto, 1 force the atomic kernel, 2 force the owner kernel
 
 void set_error(const std::string& m) { g_err = m; }
 int fail(const std::string& m) { g_err = m; return RB_ERR_ARG; }
@@ -27,6 +28,8 @@ int fail_cuda(cudaError_t e, const char* what) {
 }
 void count_launch(int n) { g_launches += n; }
 void count_tc_launch() { g_tc_launches += 1; }
+static std::atomic<int64_t> g_owner_launches{0};
+void count_owner_launch() { g_owner_launches += 1; }
 
 int sm_count() {
     static int cached[64] = {0};
@@ -69,6 +72,7 @@ const double2* logf_table_device() {
 int64_t get_option(const char* name) {
     if (!std::strcmp(name, "dense_path")) return g_dense_path.load();
     if (!std::strcmp(name, "tc_splits")) return g_tc_splits.load();
+    if (!std::strcmp(name, "saso_path")) return g_saso_path.load();
     return 0;
 }
 
@@ -734,12 +738,14 @@ int rb_set_option(const char* name, int64_t value) {
     RB_REQUIRE(name != nullptr);
     if (!std::strcmp(name, "dense_path")) { g_dense_path = value; return 0; }
     if (!std::strcmp(name, "tc_splits")) { g_tc_splits = value; return 0; }
+    if (!std::strcmp(name, "saso_path")) { g_saso_path = value; return 0; }
     return fail(std::string("unknown option ") + name);
 }
 int64_t rb_get_counter(const char* name) {
     if (!name) return -1;
     if (!std::strcmp(name, "kernel_launches")) return g_launches.load();
     if (!std::strcmp(name, "tensor_core_launches")) return g_tc_launches.load();
+    if (!std::strcmp(name, "saso_owner_launches")) return g_owner_launches.load();
     return -1;
 }
 

@@ -9,6 +9,7 @@ namespace rb {
 
 void count_launch(int n = 1);
 void count_tc_launch();
+void count_owner_launch();
 
 int launch_philox_words(Ctr128 ctr, PhiloxKey key, int64_t n_blocks, uint32_t* out, cudaStream_t st);
 
@@ -73,6 +74,8 @@ struct SasoProblem {
 };
 template <typename T>
 int launch_saso_apply(const SasoProblem<T>& p, cudaStream_t st);
+// fast path (saso_owner.cu): 0 = done, -1 = shape/layout not taken, >0 error. C already beta-scaled.
+int launch_saso_owner_f32(const SasoProblem<float>& p, cudaStream_t st);
 
 // generic COO x dense: C(P x Q) += alpha * X * Y with X given by triplets inside a window
 template <typename T>

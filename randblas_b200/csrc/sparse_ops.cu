@@ -218,6 +218,10 @@ int launch_saso_apply(const SasoProblem<T>& p, cudaStream_t st) {
     int rc = launch_scale<T>(p.P, p.Q, p.beta, p.C, p.crs, p.ccs, st);
     if (rc) return rc;
     if (p.K <= 0 || p.alpha == (T) 0) return 0;
+    if constexpr (sizeof(T) == 4) {
+        rc = launch_saso_owner_f32(p, st);      // register-resident output, no atomics in the loop (saso_owner.cu)
+        if (rc >= 0) return rc;
+    }
     // only minor-axis vectors that intersect the window are visited
     const int64_t w0 = p.major_is_rows ? p.co_s : p.ro_s;
     const int64_t wn = p.major_is_rows ? p.cs : p.rs;

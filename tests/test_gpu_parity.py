@@ -373,6 +373,57 @@ def test_sparse_operator_sketch_all_variants_vs_oracle(gpu, port, dt):
     assert relerr(B1, B2) < tol
 
 
+def test_saso_owner_kernel_vs_oracle_and_vs_atomic_kernel(gpu, port):
+    """The register-resident SASO apply (saso_owner.cu) forced on shapes that cross tile boundaries: two row
+    tiles of C (d > 1024), ragged column slices (n % 32 != 0), ragged last chunk of A, windows of the operator,
+    every sub-warp group size of the entry generator, alpha/beta. Checked against the oracle, and at a larger
+    shape against the atomic kernel (same operator, different summation order)."""
+    import randblas_b200 as rb
+    import torch
+    rng = np.random.default_rng(5)
+    ctr, key = ol.state_from_u64(1997)
+    dt = np.float32
+    try:
+        rb.set_option("saso_path", 2)
+        before = rb.counter("saso_owner_launches")
+        for (d, n, m, vn, ro, co) in ((45, 29, 2111, 3, 2, 5), (1500, 64, 3000, 8, 0, 0), (1100, 100, 1537, 17, 7, 3),
+                                      (300, 36, 900, 32, 0, 1), (64, 32, 5000, 1, 1, 0), (2048, 40, 777, 5, 0, 0)):
+            for opS in "NT":
+                Dr, Dc = (d + ro + 3, m + co + 6) if opS == "N" else (m + ro + 6, d + co + 3)
+                A, lda = _mk(rng, m, n, "R", 4 - n % 4 if n % 4 else 0, dt)      # lda % 4 == 0: TMA-addressable
+                B0, ldb = _mk(rng, d, n, "R", 1, dt)
+                for alpha, beta in ((1.0, 0.0), (0.5, -1.5)):
+                    B1, B2 = B0.copy(), B0.copy()
+                    gpu.lskges("R", opS, "N", d, n, m, dt(alpha), (Dr, Dc, vn, "S"), ctr, key, ro, co, A, lda, dt(beta), B1, ldb)
+                    port.lskges("R", opS, "N", d, n, m, dt(alpha), (Dr, Dc, vn, "S"), ctr, key, ro, co, A, lda, dt(beta), B2, ldb)
+                    assert relerr(B1, B2) < 1e-5, ("owner lskges", d, n, m, vn, opS, alpha, relerr(B1, B2))
+        # right sketch in ColMajor is the same canonical problem (C^T = S^T-window applied to A^T)
+        mm, dd, nn = 37, 1200, 2500
+        A, lda = _mk(rng, mm, nn, "C", 3, dt)
+        B0, ldb = _mk(rng, mm, dd, "C", 3, dt)
+        B1, B2 = B0.copy(), B0.copy()
+        gpu.rskges("C", "N", "N", mm, dd, nn, dt(0.5), A, lda, (nn + 2, dd + 3, 4, "S"), ctr, key, 1, 2, dt(-1.5), B1, ldb)
+        port.rskges("C", "N", "N", mm, dd, nn, dt(0.5), A, lda, (nn + 2, dd + 3, 4, "S"), ctr, key, 1, 2, dt(-1.5), B2, ldb)
+        assert relerr(B1, B2) < 1e-5, relerr(B1, B2)
+        assert rb.counter("saso_owner_launches") > before, "the owner kernel did not run"
+        # benchmark-like shape (slice of C4): owner kernel vs atomic kernel vs fp64 product of the sampled operator
+        d, n, m, vn = 2048, 256, 100000, 8
+        S = rb.SparseSkOp(rb.SparseDist(d, m, vn), rb.RNGState(1997), dtype=dt)
+        A = torch.randn(m * n, dtype=torch.float32, device="cuda")
+        Bo = torch.full((d * n,), 7.0, dtype=torch.float32, device="cuda")
+        Ba = Bo.clone()
+        rb.sketch_general("R", "N", "N", d, n, m, 1.0, S, 0, 0, A, n, 0.0, Bo, n)
+        rb.set_option("saso_path", 1)
+        rb.sketch_general("R", "N", "N", d, n, m, 1.0, S, 0, 0, A, n, 0.0, Ba, n)
+        rb.fill_sparse(S)
+        Sd = torch.sparse_coo_tensor(torch.stack([S.rows, S.cols]), S.vals.double(), (d, m))
+        want = torch.sparse.mm(Sd, A.double().view(m, n)).view(-1)
+        assert float(torch.linalg.norm(Bo.double() - want) / torch.linalg.norm(want)) < 1e-5
+        assert float(torch.linalg.norm(Ba.double() - want) / torch.linalg.norm(want)) < 1e-5
+    finally:
+        rb.set_option("saso_path", 0)
+
+
 def _sp(mat, fmt, dt):
     if fmt == 0:
         m = mat.tocsr()
