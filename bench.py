@@ -398,9 +398,9 @@ class C5SketchSparse(Workload):
     def roofline(self, kernel_ms, pk):
         gbs = (self.bytes_A() + self.d * self.n_local * 4) / 1e9 / (kernel_ms / 1e3)
         return {"bound": "hbm", "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gbs / pk["hbm_gbs"],
-                "traffic": None, "kernel": "spdata_colowner_kernel<float>", "peak_source": pk["source"],
+                "traffic": None, "kernel": "spdata_kgroup_kernel<float> (+ zero-fill of B)", "peak_source": pk["source"],
                 "algorithmic_bytes_per_launch": self.bytes_A() + self.d * self.n_local * 4,
-                "note": "issue-bound on regenerating S (512 Philox blocks per nonzero), see DESIGN.md"}
+                "note": "bound by L2 reductions into B (512 B of red.v4 per nonzero), see DESIGN.md"}
 
     def e2e_setup(self):
         return None

@@ -18,6 +18,7 @@ static std::atomic<int64_t> g_launches{0};
 static std::atomic<int64_t> g_dense_path{0};
 static std::atomic<int64_t> g_tc_launches{0};
 static std::atomic<int64_t> g_tc_splits{0};
+static std::atomic<int64_t> g_spdata_path{0};   // 0 auto (k-group kernel), 1 force the column-owner kernel (no atomics)
 static std::atomic<int64_t> g_saso_path{0};     // 0 auto, 1 force the atomic kernel, 2 force the owner kernel
 
 void set_error(const std::string& m) { g_err = m; }
@@ -73,6 +74,7 @@ int64_t get_option(const char* name) {
     if (!std::strcmp(name, "dense_path")) return g_dense_path.load();
     if (!std::strcmp(name, "tc_splits")) return g_tc_splits.load();
     if (!std::strcmp(name, "saso_path")) return g_saso_path.load();
+    if (!std::strcmp(name, "spdata_path")) return g_spdata_path.load();
     return 0;
 }
 
@@ -739,6 +741,7 @@ int rb_set_option(const char* name, int64_t value) {
     if (!std::strcmp(name, "dense_path")) { g_dense_path = value; return 0; }
     if (!std::strcmp(name, "tc_splits")) { g_tc_splits = value; return 0; }
     if (!std::strcmp(name, "saso_path")) { g_saso_path = value; return 0; }
+    if (!std::strcmp(name, "spdata_path")) { g_spdata_path = value; return 0; }
     return fail(std::string("unknown option ") + name);
 }
 int64_t rb_get_counter(const char* name) {

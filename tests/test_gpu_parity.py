@@ -468,6 +468,36 @@ def test_sketch_sparse_all_variants_vs_oracle(gpu, port, dt):
             assert relerr(B1, B2) < tol, ("rsksp3", fmt, lay, opS, opA, relerr(B1, B2))
 
 
+def test_sketch_sparse_kgroup_and_colowner_kernels_vs_oracle(gpu, port):
+    """Both sketch_sparse kernels (input-stationary with vector reductions = default, output-stationary =
+    spdata_path 1) against the oracle, on shapes that take the red.v4 path (d % 4 == 0, ColMajor, ldb % 4 == 0)
+    with operator windows that are / are not aligned to Philox blocks, and empty rows in the data."""
+    import scipy.sparse as sp
+    import randblas_b200 as rb
+    rng = np.random.default_rng(5)
+    ctr, key = ol.state_from_u64(1997)
+    dt = np.float32
+    d, n, m = 256, 70, 1031
+    M = sp.random(m, n, density=0.03, random_state=3, dtype=np.float64).tolil()
+    M[5:40, :] = 0          # whole k-groups without nonzeros
+    M = M.tocsr()
+    try:
+        for path in (0, 1):
+            rb.set_option("spdata_path", path)
+            for fmt in (0, 1, 2):
+                spA = _sp(M, fmt, dt)
+                for fam, ax, co_s in (("G", "L", 0), ("G", "L", 4), ("U", "L", 3), ("G", "S", 0), ("U", "S", 2)):
+                    for lay, ldb in (("C", d), ("C", d + 4), ("R", n + 1)):
+                        B0 = rng.standard_normal(ldb * (n if lay == "C" else d)).astype(dt)
+                        B1, B2 = B0.copy(), B0.copy()
+                        dist = (d + 3, m + 5, fam, ax)
+                        gpu.lsksp3(fmt, lay, "N", "N", d, n, m, dt(1.0), dist, ctr, key, 0 if ax == "L" else co_s, co_s, spA, dt(0.0), B1, ldb)
+                        port.lsksp3(fmt, lay, "N", "N", d, n, m, dt(1.0), dist, ctr, key, 0 if ax == "L" else co_s, co_s, spA, dt(0.0), B2, ldb)
+                        assert relerr(B1, B2) < TOL[np.dtype(dt)], (path, fmt, fam, ax, co_s, lay, ldb, relerr(B1, B2))
+    finally:
+        rb.set_option("spdata_path", 0)
+
+
 def test_sketch_with_host_buffers(gpu, gpu_host):
     rng = np.random.default_rng(8)
     ctr, key = ol.state_from_u64(2)
