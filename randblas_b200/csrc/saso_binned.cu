@@ -1,0 +1,439 @@
+// K3b (second generation): SASO apply with a register-resident output tile and a ONE-TIME binning pre-pass.
+// Fast path of sparse::lskges / rskges (RandBLAS/skge.hh:465-492, 598-626) when the short axis of the operator
+// indexes the rows of the result:
+//     C(P x Q) += alpha * X(P x K) * Y(K x Q),   X = window of a SASO operator with vec_nnz entries per column.
+// The reference deep-copies the operator's COO arrays, std::sorts them into CSC and does one axpy of length Q per
+// nonzero (sparse_data/coo_spmm_impl.hh:53-105, csc_spmm_impl.hh:99-209). Here:
+//
+//   1. saso_bin_kernel (one CTA per chunk of Kc columns of X = Kc rows of Y): regenerates the chunk's nonzeros
+//      (Fisher-Yates exactly as sparse_skops.hh:72-102, one sub-warp group of lanes per column), counting-sorts
+//      them by target row in shared memory and writes, per chunk, the sorted list (one 32-bit word per nonzero:
+//      byte offset of the Y row inside the chunk's shared-memory image | sign << 31) and the row offsets (u16).
+//      This is the only form of S that ever exists (4 B + ~6/vec_nnz B per nonzero instead of the 20 B of the
+//      reference's COO triplets), and it is built once -- the first-generation kernel (saso_owner.cu) re-sorted
+//      every chunk in each of the ns x np CTAs that needed it.
+//   2. saso_binned_kernel: a CTA owns a 1024 x 32 tile of C in REGISTERS for the whole kernel (every 8-lane group
+//      owns 8 rows x 32 columns, 4 columns per lane) and walks over its share of the chunks. A two-stage
+//      TMA pipeline brings in, per chunk, the 32 columns it needs of the Kc rows of Y (2D tensor map, 128-byte
+//      rows), the part of the sorted list that targets its rows and the matching offsets (bulk copies). Warps
+//      run decoupled: full[] mbarriers signal arrival, the last warp to finish a stage (elected through a
+//      shared-memory counter, ordered by an empty[] mbarrier) re-arms it with the next chunk. No __syncthreads
+//      in the loop, no atomics on C, one conflict-free 128-byte shared-memory read per (entry, group).
+//
+// Roofline: HBM, bytes of Y (the data matrix A) read once. The inner loop itself is bound by shared-memory read
+// bandwidth and issue slots: every element of A is added into vec_nnz accumulators, i.e. vec_nnz * 4 B of
+// shared-memory reads per 4 B of HBM.
+#include "common.cuh"
+#include "kernels.h"
+#include "tma.cuh"
+
+namespace rb {
+
+namespace {
+
+constexpr int BN_THREADS = 1024;
+constexpr int BN_W = 32;                        // columns of C per CTA = one 128-byte row of Y per 8-lane group
+constexpr int BN_RPG = 8;                       // rows of C per 8-lane group
+constexpr int BN_PT = (BN_THREADS / 8) * BN_RPG;   // 1024 rows of C per CTA
+constexpr int BN_KMAX = 704;                    // rows of Y per chunk
+constexpr int BN_BOXR = 64;                     // rows per TMA box
+constexpr int BN_ENT = 5632;                    // nonzeros per chunk (Kc * vec_nnz <= BN_ENT)
+constexpr int BN_ENT_CAP = BN_ENT + 8;          // per-chunk stride of the sorted list in global memory (entries)
+constexpr int BN_PMAX = 8192;                   // rows of C the binning kernel can count in shared memory
+constexpr uint32_t BN_YBYTES = BN_KMAX * BN_W * 4;          // 90112
+constexpr uint32_t BN_LBYTES = BN_ENT * 4 + 16;             // list + slack for the 16-byte aligned start
+constexpr uint32_t BN_OCOUNT = BN_PT + 8;                   // u16 offsets copied per chunk and row tile (1025 used)
+constexpr uint32_t BN_OBYTES = BN_OCOUNT * 2;               // 2064
+constexpr uint32_t BN_OFF_LIST = BN_YBYTES;
+constexpr uint32_t BN_OFF_OFFS = BN_OFF_LIST + BN_LBYTES;
+constexpr uint32_t BN_STAGE = ((BN_OFF_OFFS + BN_OBYTES + 127u) / 128u) * 128u;   // 114816
+constexpr uint32_t BN_OFF_BAR = 2 * BN_STAGE;               // full[2], empty[2], cnt[2]
+constexpr uint32_t BN_SMEM = BN_OFF_BAR + 64 + 128;         // + alignment slack
+
+constexpr int BIN_THREADS = 512;
+
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+// One list word: (byte offset of the Y row in the chunk image) / 2 | negative << 31. The address is base + (p << 1)
+// (the shift drops the sign bit), the multiplier +-1.0f is (p & 0x80000000) | 0x3f800000: one LOP3.
+__device__ __forceinline__ float word_sign(uint32_t p) {
+    uint32_t s;
+    asm("lop3.b32 %0, %1, 0x80000000, 0x3f800000, 0xEA;" : "=r"(s) : "r"(p));
+    return __uint_as_float(s);
+}
+
+struct BinArgs {
+    Ctr128 ctr;
+    PhiloxKey key;
+    int k;                 // entries per column of X
+    uint32_t dim_major;
+    int64_t vec_lo;        // first column of X in operator coordinates
+    int64_t nvec;          // columns of X in this launch
+    int64_t m0;            // first row of X in operator coordinates
+    int64_t P;             // rows of X
+    int Kc;                // columns per chunk
+    int64_t nchunks;
+    int Prows;             // np * BN_PT
+    int Ppad;              // Prows + 8: per-chunk stride of offs16
+    uint32_t* sorted;      // [nchunks][BN_ENT_CAP]
+    uint16_t* offs16;      // [nchunks][Ppad]
+};
+
+// G lanes per column of X (power of two >= k). All index arithmetic in 32 bits: dim_major < 2^31 on this path.
+template <int G>
+__global__ void __launch_bounds__(BIN_THREADS) saso_bin_kernel(const BinArgs a) {
+    extern __shared__ uint32_t bsm[];
+    uint32_t* cnt = bsm;                               // [Prows + 1] counters, then running offsets
+    uint32_t* raw = cnt + a.Prows + 32;                // [BN_ENT] (row << 1 | negative), ~0 = outside the window
+    uint32_t* srt = raw + BN_ENT;                      // [BN_ENT] sorted words
+    __shared__ uint32_t wsum[BIN_THREADS / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, sub = lane & (G - 1);
+    constexpr int VPP = BIN_THREADS / G;               // columns per pass
+    const int per_thr = a.Prows / BIN_THREADS;         // counters scanned per thread (Prows is a multiple of 1024)
+
+    for (int64_t c = blockIdx.x; c < a.nchunks; c += gridDim.x) {
+        const int64_t v0 = c * a.Kc;
+        const int nv = (int) min((int64_t) a.Kc, a.nvec - v0);
+        for (int i = tid; i < a.Prows; i += BIN_THREADS) cnt[i] = 0;
+        __syncthreads();
+        // ---- generate the chunk's nonzeros, count them per target row ----
+        for (int vb = 0; vb < nv; vb += VPP) {
+            const int vl = vb + tid / G;
+            const bool live = vl < nv && sub < a.k;
+            uint32_t piv = 0, w1 = 0;
+            if (live) {
+                const uint4 w = philox4x32_10(ctr_add(a.ctr, (uint64_t) ((a.vec_lo + v0 + vl) * a.k + sub)), a.key);
+                piv = (uint32_t) sub + w.x % (a.dim_major - (uint32_t) sub);      // sparse_skops.hh:78
+                w1 = w.y;
+            }
+            // value at position piv after swaps 0..sub-1 of an identity permutation: walk the swaps backwards
+            uint32_t pos = piv;
+            for (int t = a.k - 2; t >= 0; --t) {
+                const uint32_t pt = __shfl_sync(0xffffffffu, piv, t, G);
+                if (t < sub) {
+                    if (pos == (uint32_t) t) pos = pt;
+                    else if (pos == pt) pos = (uint32_t) t;
+                }
+            }
+            if (live) {
+                const int64_t r = (int64_t) pos - a.m0;
+                const bool in = r >= 0 && r < a.P;
+                raw[vl * a.k + sub] = in ? (((uint32_t) r << 1) | (w1 & 1u)) : 0xffffffffu;   // :84-88
+                if (in) atomicAdd(&cnt[r], 1u);
+            }
+        }
+        __syncthreads();
+        // ---- exclusive scan of the counters (per_thr consecutive counters per thread) ----
+        {
+            uint32_t loc = 0;
+            for (int i = 0; i < per_thr; ++i) loc += cnt[tid * per_thr + i];
+            uint32_t incl = loc;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            if (lane == 31) wsum[warp] = incl;
+            __syncthreads();
+            if (warp == 0) {
+                const uint32_t s = (lane < BIN_THREADS / 32) ? wsum[lane] : 0u;
+                uint32_t si = s;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t t = __shfl_up_sync(0xffffffffu, si, o);
+                    if (lane >= o) si += t;
+                }
+                if (lane < BIN_THREADS / 32) wsum[lane] = si - s;
+            }
+            __syncthreads();
+            uint32_t run = incl - loc + wsum[warp];
+            for (int i = 0; i < per_thr; ++i) {
+                const uint32_t v = cnt[tid * per_thr + i];
+                cnt[tid * per_thr + i] = run;
+                run += v;
+            }
+        }
+        __syncthreads();
+        // ---- scatter: after this pass cnt[r] is the END of row r's list ----
+        const int ne = nv * a.k;
+        for (int e = tid; e < ne; e += BIN_THREADS) {
+            const uint32_t w = raw[e];
+            if (w != 0xffffffffu) {
+                const uint32_t dst = atomicAdd(&cnt[w >> 1], 1u);
+                const uint32_t vl = (uint32_t) e / (uint32_t) a.k;
+                srt[dst] = (vl * (uint32_t) (BN_W * 2)) | ((w & 1u) << 31);
+            }
+        }
+        __syncthreads();
+        // ---- write out: sorted words (coalesced) and u16 row offsets (offs[0] = 0, offs[r + 1] = end of row r) ----
+        const uint32_t total = cnt[a.Prows - 1];
+        uint32_t* gs = a.sorted + c * BN_ENT_CAP;
+        for (uint32_t e = tid; e < ((total + 3u) & ~3u); e += BIN_THREADS) gs[e] = (e < total) ? srt[e] : 0u;
+        uint16_t* go = a.offs16 + c * a.Ppad;
+        for (int i = tid; i < a.Ppad; i += BIN_THREADS)
+            go[i] = (uint16_t) (i == 0 ? 0u : (i <= a.Prows ? cnt[i - 1] : total));
+        __syncthreads();
+    }
+}
+
+struct BinnedArgs {
+    const uint32_t* sorted;
+    const uint16_t* offs16;
+    int nchunks;
+    int Kc;              // rows of Y per chunk, a multiple of BN_BOXR
+    int Ppad;
+    int G;               // CTAs that share one tile of C (they split the chunks)
+    int64_t P, Q;
+    float alpha;
+    float* C;
+    int64_t crs;
+    int c_vec4;          // rows of C are 16-byte aligned
+};
+
+__global__ void __launch_bounds__(BN_THREADS, 1) saso_binned_kernel(const __grid_constant__ CUtensorMap tmY,
+                                                                    const BinnedArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = tma::smem_u32(smem_raw);
+    const uint32_t sbase = (raw + 127u) & ~127u;
+    uint8_t* smem = smem_raw + (sbase - raw);
+    const uint32_t bar_full = sbase + BN_OFF_BAR;          // 2 x 8 B
+    const uint32_t bar_empty = bar_full + 16;              // 2 x 8 B
+    uint32_t* cnt = reinterpret_cast<uint32_t*>(smem + BN_OFF_BAR + 32);   // 2 counters
+
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int gi = tid >> 3, l8 = tid & 7;
+    const int col0 = (int) blockIdx.x * BN_W;
+    const int64_t row0 = (int64_t) blockIdx.y * BN_PT;
+    const int g = (int) blockIdx.z;
+    const int nbox = a.Kc / BN_BOXR;
+    const uint32_t ybytes = (uint32_t) a.Kc * BN_W * 4;
+
+    if (tid == 0) {
+        tma::mbar_init(bar_full, 1);
+        tma::mbar_init(bar_full + 8, 1);
+        tma::mbar_init(bar_empty, BN_THREADS / 32);
+        tma::mbar_init(bar_empty + 8, BN_THREADS / 32);
+        cnt[0] = 0;
+        cnt[1] = 0;
+        tma::mbar_fence_init();
+    }
+    __syncthreads();
+
+    // one thread: Y slice + this row tile's part of the sorted list + its offsets -> stage b
+    auto issue = [&](int c, int b) {
+        const uint16_t* go = a.offs16 + (int64_t) c * a.Ppad + row0;
+        const uint32_t lo = __ldg(go), hi = __ldg(go + BN_PT);
+        const uint32_t lo4 = lo & ~3u, hi4 = (hi + 3u) & ~3u;
+        const uint32_t lbytes = (hi4 - lo4) * 4u;
+        const uint32_t bar = bar_full + 8u * (uint32_t) b;
+        const uint32_t dst = sbase + (uint32_t) b * BN_STAGE;
+        tma::mbar_arrive_expect_tx(bar, ybytes + lbytes + BN_OBYTES);
+        for (int x = 0; x < nbox; ++x)
+            tma::load_2d(dst + (uint32_t) x * (BN_BOXR * BN_W * 4), &tmY, bar, col0, c * a.Kc + x * BN_BOXR);
+        if (lbytes) bulk_g2s(dst + BN_OFF_LIST, a.sorted + (int64_t) c * BN_ENT_CAP + lo4, lbytes, bar);
+        bulk_g2s(dst + BN_OFF_OFFS, go, BN_OBYTES, bar);
+    };
+
+    float acc[BN_RPG][4];
+#pragma unroll
+    for (int q = 0; q < BN_RPG; ++q) acc[q][0] = acc[q][1] = acc[q][2] = acc[q][3] = 0.f;
+
+    if (tid == 0) {
+        if (g < a.nchunks) issue(g, 0);
+        if (g + a.G < a.nchunks) issue(g + a.G, 1);
+    }
+
+    int it = 0;
+    for (int c = g; c < a.nchunks; c += a.G, ++it) {
+        const int b = it & 1;
+        const uint32_t par = (uint32_t) ((it >> 1) & 1);
+        const uint32_t stage = sbase + (uint32_t) b * BN_STAGE;
+        tma::mbar_wait(bar_full + 8u * (uint32_t) b, par);
+
+        // offsets of this group's 8 rows (relative to the chunk's list), 16-byte aligned in shared memory
+        const uint32_t oaddr = stage + BN_OFF_OFFS + (uint32_t) gi * (BN_RPG * 2);
+        uint32_t o01, o23, o45, o67;
+        asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(o01), "=r"(o23), "=r"(o45), "=r"(o67) : "r"(oaddr));
+        uint32_t o8;
+        asm volatile("ld.shared.u16 %0, [%1];" : "=r"(o8) : "r"(oaddr + 16));
+        uint32_t lo;
+        asm volatile("ld.shared.u16 %0, [%1];" : "=r"(lo) : "r"(stage + BN_OFF_OFFS));
+        // list word e sits at lbase + 4 * e
+        const uint32_t lbase = stage + BN_OFF_LIST - 4u * (lo & ~3u);
+        uint32_t o[BN_RPG + 1];
+        o[0] = o01 & 0xffffu; o[1] = o01 >> 16; o[2] = o23 & 0xffffu; o[3] = o23 >> 16;
+        o[4] = o45 & 0xffffu; o[5] = o45 >> 16; o[6] = o67 & 0xffffu; o[7] = o67 >> 16; o[8] = o8;
+        const uint32_t ybase = stage + (uint32_t) l8 * 16;
+#pragma unroll
+        for (int q = 0; q < BN_RPG; ++q) {
+            const uint32_t pe = lbase + 4u * o[q + 1];
+#pragma unroll 2
+            for (uint32_t pa = lbase + 4u * o[q]; pa < pe; pa += 4) {
+                const uint32_t p = lds32(pa);
+                const float4 y = lds128(ybase + (p << 1));
+                const float s = word_sign(p);
+                acc[q][0] = fmaf(y.x, s, acc[q][0]);
+                acc[q][1] = fmaf(y.y, s, acc[q][1]);
+                acc[q][2] = fmaf(y.z, s, acc[q][2]);
+                acc[q][3] = fmaf(y.w, s, acc[q][3]);
+            }
+        }
+        // release the stage; the last warp to leave re-arms it with chunk c + 2G
+        __syncwarp();
+        if (lane == 0) {
+            mbar_arrive(bar_empty + 8u * (uint32_t) b);
+            const uint32_t old = atomicAdd(&cnt[b], 1u);
+            if ((old & (BN_THREADS / 32 - 1)) == (BN_THREADS / 32 - 1) && c + 2 * a.G < a.nchunks) {
+                tma::mbar_wait(bar_empty + 8u * (uint32_t) b, par);
+                issue(c + 2 * a.G, b);
+            }
+        }
+    }
+
+    // ---- add the tile into C (beta was applied beforehand; G CTAs share the tile) ----
+    const int64_t col = (int64_t) col0 + l8 * 4;
+#pragma unroll
+    for (int q = 0; q < BN_RPG; ++q) {
+        const int64_t row = row0 + (int64_t) gi * BN_RPG + q;
+        if (row >= a.P || col >= a.Q) continue;
+        float* cp = a.C + row * a.crs + col;
+        const float v0 = a.alpha * acc[q][0], v1 = a.alpha * acc[q][1], v2 = a.alpha * acc[q][2], v3 = a.alpha * acc[q][3];
+        if (a.c_vec4 && col + 3 < a.Q) {
+            asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(cp), "f"(v0), "f"(v1), "f"(v2), "f"(v3) : "memory");
+        } else {
+            atomicAdd(cp, v0);
+            if (col + 1 < a.Q) atomicAdd(cp + 1, v1);
+            if (col + 2 < a.Q) atomicAdd(cp + 2, v2);
+            if (col + 3 < a.Q) atomicAdd(cp + 3, v3);
+        }
+    }
+}
+
+template <int G>
+int launch_bin(const BinArgs& a, size_t smem, cudaStream_t st) {
+    static bool attr_done = false;
+    if (!attr_done) {
+        if (cudaFuncSetAttribute(saso_bin_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024) != cudaSuccess) {
+            cudaGetLastError();
+            return -1;
+        }
+        attr_done = true;
+    }
+    int64_t grid = a.nchunks;
+    const int64_t cap = (int64_t) sm_count() * 2;
+    if (grid > cap) grid = cap;
+    saso_bin_kernel<G><<<(unsigned) grid, BIN_THREADS, smem, st>>>(a);
+    return 0;
+}
+
+}  // namespace
+
+// Returns 0 if the product was computed, -1 if this path does not take the problem (caller falls back), >0 on error.
+// C must have been beta-scaled by the caller.
+int launch_saso_binned_f32(const SasoProblem<float>& p, cudaStream_t st) {
+    const int64_t path = get_option("saso_path");
+    if (path == 1 || path == 3) return -1;                    // 1 = atomic kernel, 3 = first-generation owner kernel
+    const bool scatter = p.major_is_rows ? !p.x_is_transposed : p.x_is_transposed;   // short axis <-> rows of C
+    if (!scatter) return -1;
+    if (p.ycs != 1 || p.ccs != 1) return -1;
+    if ((reinterpret_cast<uintptr_t>(p.Y) & 15) != 0 || (p.yrs & 3) != 0) return -1;   // TMA alignment rules
+    if (p.vec_nnz > 32 || p.dim_major >= 0x7fffffffLL || p.P > BN_PMAX) return -1;
+    if (p.Q > 0x7fffffffLL || p.yrs > 0x3fffffffLL) return -1;
+    const int64_t w0 = p.major_is_rows ? p.co_s : p.ro_s;      // first column of X in operator coordinates
+    const int64_t m0 = p.major_is_rows ? p.ro_s : p.co_s;      // first row of X
+    const int64_t nvec = p.K;
+    if (path != 2 && nvec * p.vec_nnz < 32768) return -1;      // small: one launch of the atomic kernel wins
+    tma::EncodeTiledFn enc = tma::encode_tiled_fn();
+    if (!enc) return -1;
+    {
+        static bool attr_done = false;
+        if (!attr_done) {
+            if (cudaFuncSetAttribute(saso_binned_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BN_SMEM) != cudaSuccess) {
+                cudaGetLastError();
+                return -1;
+            }
+            attr_done = true;
+        }
+    }
+    const int k = (int) p.vec_nnz;
+    int Kc = (BN_ENT / k) / BN_BOXR * BN_BOXR;
+    if (Kc > BN_KMAX) Kc = BN_KMAX;
+    const int64_t ns = (p.Q + BN_W - 1) / BN_W, np = (p.P + BN_PT - 1) / BN_PT;
+    if (ns > 0x7fffffffLL || np > 65535) return -1;
+    const int Prows = (int) np * BN_PT, Ppad = Prows + 8;
+    const size_t bin_smem = ((size_t) Prows + 32 + 2 * BN_ENT) * 4;
+    const int sms = sm_count();
+    // segments bound the workspace (sorted list + offsets) to about 1 GiB
+    const int64_t per_chunk = (int64_t) BN_ENT_CAP * 4 + (int64_t) Ppad * 2;
+    int64_t seg_chunks = ((int64_t) 1 << 30) / per_chunk;
+    if (seg_chunks < 1) seg_chunks = 1;
+    const int64_t seg_vecs = seg_chunks * Kc;
+    for (int64_t v0 = 0; v0 < nvec; v0 += seg_vecs) {
+        const int64_t nv = (nvec - v0 < seg_vecs) ? nvec - v0 : seg_vecs;
+        const int64_t nchunks = (nv + Kc - 1) / Kc;
+        uint32_t* sorted = (uint32_t*) workspace(7, (size_t) nchunks * BN_ENT_CAP * 4);
+        uint16_t* offs16 = (uint16_t*) workspace(6, (size_t) nchunks * Ppad * 2 + 64);
+        if (!sorted || !offs16) return fail_cuda(cudaErrorMemoryAllocation, "SASO binning workspace");
+
+        BinArgs b;
+        b.ctr = p.ctr; b.key = p.key; b.k = k; b.dim_major = (uint32_t) p.dim_major;
+        b.vec_lo = w0 + v0; b.nvec = nv; b.m0 = m0; b.P = p.P; b.Kc = Kc; b.nchunks = nchunks;
+        b.Prows = Prows; b.Ppad = Ppad; b.sorted = sorted; b.offs16 = offs16;
+        int rc;
+        if (k <= 1) rc = launch_bin<1>(b, bin_smem, st);
+        else if (k <= 2) rc = launch_bin<2>(b, bin_smem, st);
+        else if (k <= 4) rc = launch_bin<4>(b, bin_smem, st);
+        else if (k <= 8) rc = launch_bin<8>(b, bin_smem, st);
+        else if (k <= 16) rc = launch_bin<16>(b, bin_smem, st);
+        else rc = launch_bin<32>(b, bin_smem, st);
+        if (rc) return v0 == 0 ? -1 : fail("SASO binning kernel could not be configured");
+        count_launch();
+        RB_CUDA(cudaGetLastError());
+
+        CUtensorMap tm;
+        const cuuint64_t gdim[2] = {(cuuint64_t) p.Q, (cuuint64_t) nv};
+        const cuuint64_t gstr[1] = {(cuuint64_t) p.yrs * 4ull};
+        const cuuint32_t box[2] = {BN_W, BN_BOXR};
+        const cuuint32_t estr[2] = {1, 1};
+        CUresult cr = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(p.Y + v0 * p.yrs), gdim, gstr, box,
+                          estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                          CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (cr != CUDA_SUCCESS) return v0 == 0 ? -1 : fail("cuTensorMapEncodeTiled failed for the SASO apply");
+
+        BinnedArgs a;
+        a.sorted = sorted; a.offs16 = offs16; a.nchunks = (int) nchunks; a.Kc = Kc; a.Ppad = Ppad;
+        int64_t G = sms / (ns * np);
+        if (G < 1) G = 1;
+        if (G > nchunks) G = nchunks;
+        if (G > 65535) G = 65535;
+        a.G = (int) G;
+        a.P = p.P; a.Q = p.Q;
+        a.alpha = p.alpha;
+        a.C = p.C; a.crs = p.crs;
+        a.c_vec4 = ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0 && (p.crs & 3) == 0) ? 1 : 0;
+        dim3 grid((unsigned) ns, (unsigned) np, (unsigned) G);
+        saso_binned_kernel<<<grid, BN_THREADS, BN_SMEM, st>>>(tm, a);
+        count_launch();
+        count_owner_launch();
+        RB_CUDA(cudaGetLastError());
+    }
+    return 0;
+}
+
+}  // namespace rb

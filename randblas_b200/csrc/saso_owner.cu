@@ -266,7 +266,7 @@ int launch_saso_owner_f32(const SasoProblem<float>& p, cudaStream_t st) {
     const int64_t w0 = p.major_is_rows ? p.co_s : p.ro_s;      // first column of X in operator coordinates
     const int64_t m0 = p.major_is_rows ? p.ro_s : p.co_s;      // first row of X
     const int64_t nvec = p.K;
-    if (get_option("saso_path") != 2 && nvec * p.vec_nnz < 32768) return -1;   // small: one launch of the atomic kernel wins
+    if (get_option("saso_path") < 2 && nvec * p.vec_nnz < 32768) return -1;   // small: one launch of the atomic kernel wins
     tma::EncodeTiledFn enc = tma::encode_tiled_fn();
     if (!enc) return -1;
     {

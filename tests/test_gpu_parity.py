@@ -384,10 +384,12 @@ def test_saso_owner_kernel_vs_oracle_and_vs_atomic_kernel(gpu, port):
     ctr, key = ol.state_from_u64(1997)
     dt = np.float32
     try:
-        rb.set_option("saso_path", 2)
         before = rb.counter("saso_owner_launches")
-        for (d, n, m, vn, ro, co) in ((45, 29, 2111, 3, 2, 5), (1500, 64, 3000, 8, 0, 0), (1100, 100, 1537, 17, 7, 3),
-                                      (300, 36, 900, 32, 0, 1), (64, 32, 5000, 1, 1, 0), (2048, 40, 777, 5, 0, 0)):
+        # saso_path 2 = binned kernel (saso_binned.cu, the default for large problems), 3 = first-generation owner kernel
+        for path, (d, n, m, vn, ro, co) in [(pp, sh) for pp in (2, 3) for sh in (
+                (45, 29, 2111, 3, 2, 5), (1500, 64, 3000, 8, 0, 0), (1100, 100, 1537, 17, 7, 3),
+                (300, 36, 900, 32, 0, 1), (64, 32, 5000, 1, 1, 0), (2048, 40, 777, 5, 0, 0), (3000, 33, 1409, 2, 1, 1))]:
+            rb.set_option("saso_path", path)
             for opS in "NT":
                 Dr, Dc = (d + ro + 3, m + co + 6) if opS == "N" else (m + ro + 6, d + co + 3)
                 A, lda = _mk(rng, m, n, "R", 4 - n % 4 if n % 4 else 0, dt)      # lda % 4 == 0: TMA-addressable
@@ -398,6 +400,7 @@ def test_saso_owner_kernel_vs_oracle_and_vs_atomic_kernel(gpu, port):
                     port.lskges("R", opS, "N", d, n, m, dt(alpha), (Dr, Dc, vn, "S"), ctr, key, ro, co, A, lda, dt(beta), B2, ldb)
                     assert relerr(B1, B2) < 1e-5, ("owner lskges", d, n, m, vn, opS, alpha, relerr(B1, B2))
         # right sketch in ColMajor is the same canonical problem (C^T = S^T-window applied to A^T)
+        rb.set_option("saso_path", 2)
         mm, dd, nn = 37, 1200, 2500
         A, lda = _mk(rng, mm, nn, "C", 3, dt)
         B0, ldb = _mk(rng, mm, dd, "C", 3, dt)
@@ -406,6 +409,7 @@ def test_saso_owner_kernel_vs_oracle_and_vs_atomic_kernel(gpu, port):
         port.rskges("C", "N", "N", mm, dd, nn, dt(0.5), A, lda, (nn + 2, dd + 3, 4, "S"), ctr, key, 1, 2, dt(-1.5), B2, ldb)
         assert relerr(B1, B2) < 1e-5, relerr(B1, B2)
         assert rb.counter("saso_owner_launches") > before, "the owner kernel did not run"
+        rb.set_option("saso_path", 0)
         # benchmark-like shape (slice of C4): owner kernel vs atomic kernel vs fp64 product of the sampled operator
         d, n, m, vn = 2048, 256, 100000, 8
         S = rb.SparseSkOp(rb.SparseDist(d, m, vn), rb.RNGState(1997), dtype=dt)
