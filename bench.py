@@ -270,7 +270,8 @@ class C4SasoApply(Workload):
     def roofline(self, kernel_ms, pk):
         gbs = self.m * self.n * 4 / 1e9 / (kernel_ms / 1e3)
         return {"bound": "hbm", "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gbs / pk["hbm_gbs"],
-                "traffic": None, "kernel": "saso_apply_kernel<float>", "peak_source": pk["source"],
+                "traffic": None, "kernel": "saso_bin_kernel<8> + saso_binned_kernel (saso_binned.cu)",
+                "peak_source": pk["source"],
                 "algorithmic_bytes_per_launch": self.m * self.n * 4}
 
     def e2e_setup(self):
@@ -339,7 +340,22 @@ class C3DenseSketchF64(Workload):
                 "algorithmic_flops_per_launch": 2.0 * self.d * self.m_local * self.n}
 
     def e2e_setup(self):
-        return None
+        # bounded sample: 50,000 rows of this rank's shard, A and B in pinned host memory, no collective
+        torch = self.torch
+        self.e2e_m = 50000
+        hA = self.A.view(self.n, self.m_local)[:, : self.e2e_m].contiguous()       # ColMajor, lda = e2e_m
+        self.hA = torch.empty(self.e2e_m * self.n, dtype=torch.float64, pin_memory=True)
+        self.hA.copy_(hA.view(-1))
+        self.hB = torch.zeros(self.d * self.n, dtype=torch.float64, pin_memory=True)
+        return {"sample": "first 50,000 rows of the rank's shard of A (m_local/10) per step, pinned host A and B, "
+                          "no reduce-scatter"}
+
+    def e2e_step(self):
+        self.rb.sketch_general("C", "N", "N", self.d, self.n, self.e2e_m, 1.0, self.S, 0, 0, self.hA.numpy(),
+                               self.e2e_m, 0.0, self.hB.numpy(), self.d)
+
+    def e2e_units(self):
+        return self.e2e_m * self.n * 8 / 1e9, self.e2e_m * self.n * 8, self.d * self.n * 8
 
     cpu_m = 10000
     cpu_sample = ("one row block of 10000 rows of A (the reference's blocked form: operator columns [0, 10000) "
@@ -403,7 +419,26 @@ class C5SketchSparse(Workload):
                 "note": "bound by L2 reductions into B (512 B of red.v4 per nonzero), see DESIGN.md"}
 
     def e2e_setup(self):
-        return None
+        # bounded sample: the first 1,000,000 rows of the CSR shard, all arrays and B in pinned host memory
+        torch = self.torch
+        self.e2e_m = 1000000
+        rp = self.A.rowptr[: self.e2e_m + 1]
+        nnz = int(rp[-1].item())
+        pin = lambda t: torch.empty(t.shape, dtype=t.dtype, pin_memory=True).copy_(t)
+        self.h_sp = (pin(rp), pin(self.A.colidxs[:nnz]), pin(self.A.vals[:nnz]))
+        self.e2e_nnz = nnz
+        self.hB = torch.zeros(self.d * self.n_local, dtype=torch.float32, pin_memory=True)
+        self.hAm = self.rb.CSRMatrix(self.e2e_m, self.n_local, nnz, self.h_sp[2].numpy(), self.h_sp[0].numpy(),
+                                     self.h_sp[1].numpy())
+        return {"sample": "first 1,000,000 rows of the CSR shard (m/10) per step, pinned host CSR arrays and B"}
+
+    def e2e_step(self):
+        self.rb.sketch_sparse("C", "N", "N", self.d, self.n_local, self.e2e_m, 1.0, self.S, 0, 0, self.hAm, 0.0,
+                              self.hB.numpy(), self.d)
+
+    def e2e_units(self):
+        b = self.e2e_nnz * 12 + (self.e2e_m + 1) * 8
+        return b / 1e9, b, self.d * self.n_local * 4
 
     cpu_m = 100000
     cpu_sample = ("row block of 100000 rows of the CSR shard (100000 x 125000, ~12.5 nnz/row) against the matching "

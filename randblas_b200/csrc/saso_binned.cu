@@ -283,15 +283,18 @@ __global__ void __launch_bounds__(BN_THREADS, 1) saso_binned_kernel(const __grid
 #pragma unroll
         for (int q = 0; q < BN_RPG; ++q) {
             const uint32_t pe = lbase + 4u * o[q + 1];
-#pragma unroll 2
-            for (uint32_t pa = lbase + 4u * o[q]; pa < pe; pa += 4) {
+            uint32_t pa = lbase + 4u * o[q];
+            // deliberately not unrolled: the lists are ~3 entries long, and the unrolled-by-2 form with its remainder
+            // handling measured 5% slower (more code per row than work)
+#pragma unroll 1
+            for (; pa < pe; pa += 4) {
                 const uint32_t p = lds32(pa);
                 const float4 y = lds128(ybase + (p << 1));
-                const float s = word_sign(p);
-                acc[q][0] = fmaf(y.x, s, acc[q][0]);
-                acc[q][1] = fmaf(y.y, s, acc[q][1]);
-                acc[q][2] = fmaf(y.z, s, acc[q][2]);
-                acc[q][3] = fmaf(y.w, s, acc[q][3]);
+                const float sg = word_sign(p);
+                acc[q][0] = fmaf(y.x, sg, acc[q][0]);
+                acc[q][1] = fmaf(y.y, sg, acc[q][1]);
+                acc[q][2] = fmaf(y.z, sg, acc[q][2]);
+                acc[q][3] = fmaf(y.w, sg, acc[q][3]);
             }
         }
         // release the stage; the last warp to leave re-arms it with chunk c + 2G
@@ -336,7 +339,7 @@ int launch_bin(const BinArgs& a, size_t smem, cudaStream_t st) {
         attr_done = true;
     }
     int64_t grid = a.nchunks;
-    const int64_t cap = (int64_t) sm_count() * 2;
+    const int64_t cap = (int64_t) sm_count() * 4;
     if (grid > cap) grid = cap;
     saso_bin_kernel<G><<<(unsigned) grid, BIN_THREADS, smem, st>>>(a);
     return 0;
