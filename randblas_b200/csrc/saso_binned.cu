@@ -280,21 +280,26 @@ __global__ void __launch_bounds__(BN_THREADS, 1) saso_binned_kernel(const __grid
         o[0] = o01 & 0xffffu; o[1] = o01 >> 16; o[2] = o23 & 0xffffu; o[3] = o23 >> 16;
         o[4] = o45 & 0xffffu; o[5] = o45 >> 16; o[6] = o67 & 0xffffu; o[7] = o67 >> 16; o[8] = o8;
         const uint32_t ybase = stage + (uint32_t) l8 * 16;
+        // The lists of the group's 8 rows are back to back, so one pointer walks all of them and the NEXT list word is
+        // always in flight while the current one is being used (one shared-memory latency per nonzero instead of two
+        // on the dependent chain). The read one word past the end lands in the buffer's slack and is never used.
+        uint32_t pa = lbase + 4u * o[0];
+        uint32_t p = lds32(pa);
 #pragma unroll
         for (int q = 0; q < BN_RPG; ++q) {
             const uint32_t pe = lbase + 4u * o[q + 1];
-            uint32_t pa = lbase + 4u * o[q];
             // deliberately not unrolled: the lists are ~3 entries long, and the unrolled-by-2 form with its remainder
             // handling measured 5% slower (more code per row than work)
 #pragma unroll 1
             for (; pa < pe; pa += 4) {
-                const uint32_t p = lds32(pa);
+                const uint32_t pn = lds32(pa + 4);
                 const float4 y = lds128(ybase + (p << 1));
                 const float sg = word_sign(p);
                 acc[q][0] = fmaf(y.x, sg, acc[q][0]);
                 acc[q][1] = fmaf(y.y, sg, acc[q][1]);
                 acc[q][2] = fmaf(y.z, sg, acc[q][2]);
                 acc[q][3] = fmaf(y.w, sg, acc[q][3]);
+                p = pn;
             }
         }
         // release the stage; the last warp to leave re-arms it with chunk c + 2G

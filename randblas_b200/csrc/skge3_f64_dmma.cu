@@ -9,18 +9,24 @@
 //
 // Canonical problem (kernels.h): C(P x Q) = alpha * X(P x K) * Y(K x Q) + beta * C, X = op(S window).
 // CTA tile 128 x 128, 8 warps as 2 x 4, warp tile 64 x 32 = 8 x 4 DMMA tiles (64 accumulator doubles per
-// thread), K step 16. Per step every thread
+// thread), K step 16. (16 warps with 32 x 32 warp tiles -- D_THREADS 512, D_WM 4 -- measured the same: the DMMA
+// pipe stays ~70% busy with two or four warps per scheduler.) Per step every thread
 //   * issues the 16-byte cp.async copies of the next Y tile (columns of A are K-contiguous: ColMajor A),
 //   * runs the 128 DMMAs of the current tile from shared memory (rows padded to 20 doubles: conflict-free
 //     8-byte fragment loads),
 //   * regenerates its share (2 Philox blocks = 8 samples) of the next 128 x 16 tile of S from
 //     (key, counter, ro_s, co_s) -- Philox4x32-10, uneg11 or Box-Muller in float exactly as fill_dense, promoted
-//     to double -- while the tensor pipe drains; S never touches HBM.
-// Double-buffered shared memory, one __syncthreads per step.
+//     to double; S never touches HBM.
+// Three shared-memory stages and mbarriers (full[]: one arrival per thread + one per thread's cp.async completions,
+// empty[]: one arrival per warp) instead of a __syncthreads per step, and the two warps that share a scheduler run OUT OF PHASE: warps 0-3
+// do [DMMAs of step s][generate step s+2], warps 4-7 do [generate step s+2][DMMAs of step s] (3% faster). A warp issues in
+// order, so while it generates (~350 instructions per step) it feeds no DMMAs; with the lockstep version both warps
+// of a scheduler generated at the same time and the FP64 tensor pipe idled for that part of every step.
 //
 // Roofline: FP64 tensor. 2*P*Q*K flops per launch.
 #include "common.cuh"
 #include "kernels.h"
+#include "tma.cuh"
 
 namespace rb {
 
@@ -28,6 +34,10 @@ namespace {
 
 constexpr int DM = 128, DN = 128, DK = 16, DLD = DK + 4;     // DLD: padded row length in doubles
 constexpr int D_THREADS = 256;
+constexpr int D_STAGES = 3;
+constexpr int D_WM = 2, D_WN = 4;                             // warp grid
+constexpr int D_MI = DM / (D_WM * 8), D_NI = DN / (D_WN * 8);   // DMMA tiles per warp: 8 x 4 (64 x 32 elements)
+constexpr int D_GR = DM / (D_THREADS / 4);                    // rows of the S tile generated per thread and step
 
 struct DmmaArgs {
     Ctr128 ctr;
@@ -60,12 +70,14 @@ template <bool GAUSS>
 __global__ void __launch_bounds__(D_THREADS, 1) skge3_dmma_kernel(const DmmaArgs a) {
     __shared__ __align__(16) double2 logtab[GAUSS ? LOGF_TABLE_ENTRIES : 1];
     extern __shared__ __align__(16) double dsm[];
-    double* Xs = dsm;                              // [2][DM][DLD]
-    double* Ys = dsm + 2 * DM * DLD;               // [2][DN][DLD]
+    double* Xs = dsm;                              // [D_STAGES][DM][DLD]
+    double* Ys = dsm + D_STAGES * DM * DLD;        // [D_STAGES][DN][DLD]
+    __shared__ __align__(8) unsigned long long bars[2 * D_STAGES];
+    const uint32_t bar_full = tma::smem_u32(bars), bar_empty = bar_full + 8 * D_STAGES;
     if constexpr (GAUSS) load_logf_table(logtab, a.logtab);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int wi = warp >> 2, wj = warp & 3;       // 2 x 4 warps
+    const int wi = warp / D_WN, wj = warp % D_WN;  // 4 x 4 warps
     const int g = lane >> 2, t4 = lane & 3;
     const int64_t i0 = (int64_t) blockIdx.y * DM, j0 = (int64_t) blockIdx.x * DN;
     const int split = blockIdx.z;
@@ -73,17 +85,17 @@ __global__ void __launch_bounds__(D_THREADS, 1) skge3_dmma_kernel(const DmmaArgs
     const int s_begin = split * per + min(split, rem);
     const int nsteps = per + (split < rem ? 1 : 0);
 
-    // generator role: rows xr and xr + 64, 4-wide chunk xc of the 16-deep step
+    // generator role: rows xr + (D_THREADS / 4) rr, 4-wide chunk xc of the 16-deep step
     const int xc = tid & 3, xr = tid >> 2;
     const uint64_t seed_lo = ((uint64_t) a.ctr.c1 << 32) | a.ctr.c0, seed_hi = ((uint64_t) a.ctr.c3 << 32) | a.ctr.c2;
-    uint64_t off[2];
+    uint64_t off[D_GR];
 #pragma unroll
-    for (int rr = 0; rr < 2; ++rr)
-        off[rr] = (uint64_t) ((a.v0 + i0 + xr + 64 * rr) * a.R + a.ublk0 + xc) + 4ull * (uint64_t) s_begin;
+    for (int rr = 0; rr < D_GR; ++rr)
+        off[rr] = (uint64_t) ((a.v0 + i0 + xr + (D_THREADS / 4) * rr) * a.R + a.ublk0 + xc) + 4ull * (uint64_t) s_begin;
 
     auto gen_x = [&](int buf) {
 #pragma unroll
-        for (int rr = 0; rr < 2; ++rr) {
+        for (int rr = 0; rr < D_GR; ++rr) {
             const uint64_t lo = seed_lo + off[rr];
             const uint64_t hi = seed_hi + (lo < seed_lo ? 1ull : 0ull);
             off[rr] += 4;
@@ -95,16 +107,16 @@ __global__ void __launch_bounds__(D_THREADS, 1) skge3_dmma_kernel(const DmmaArgs
                 else if (a.kshift == 2) f = make_float4(f.z, f.w, h.x, h.y);
                 else f = make_float4(f.w, h.x, h.y, h.z);
             }
-            double* dst = Xs + ((size_t) buf * DM + xr + 64 * rr) * DLD + 4 * xc;
+            double* dst = Xs + ((size_t) buf * DM + xr + (D_THREADS / 4) * rr) * DLD + 4 * xc;
             *reinterpret_cast<double2*>(dst) = make_double2(finish_sample<double, GAUSS>(f.x), finish_sample<double, GAUSS>(f.y));
             *reinterpret_cast<double2*>(dst + 2) = make_double2(finish_sample<double, GAUSS>(f.z), finish_sample<double, GAUSS>(f.w));
         }
     };
-    // Y tile: 128 columns x 16 k = 1024 chunks of 2 doubles; thread handles chunks tid + 256 q
+    // Y tile: 128 columns x 16 k = 1024 chunks of 2 doubles; thread handles chunks tid + D_THREADS q
     auto load_y = [&](int buf, int step) {
         const int64_t k0 = (int64_t) (s_begin + step) * DK;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
+        for (int q = 0; q < (DN * DK / 2) / D_THREADS; ++q) {
             const int ch = tid + D_THREADS * q;
             const int jj = ch >> 3, kc = (ch & 7) * 2;
             double* dst = Ys + ((size_t) buf * DN + jj) * DLD + kc;
@@ -117,54 +129,81 @@ __global__ void __launch_bounds__(D_THREADS, 1) skge3_dmma_kernel(const DmmaArgs
                 dst[0] = y0; dst[1] = y1;
             }
         }
-        asm volatile("cp.async.commit_group;" ::: "memory");
+        // the stage's full barrier gets one more arrival when this thread's copies have landed
+        asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar_full + 8u * (uint32_t) buf) : "memory");
     };
 
-    double acc[8][4][2];
+    double acc[D_MI][D_NI][2];
 #pragma unroll
-    for (int mi = 0; mi < 8; ++mi)
+    for (int mi = 0; mi < D_MI; ++mi)
 #pragma unroll
-        for (int ni = 0; ni < 4; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+        for (int ni = 0; ni < D_NI; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
 
-    __syncthreads();                  // logtab
-    if (nsteps > 0) {
-        load_y(0, 0);
-        gen_x(0);
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
+    if (tid == 0) {
+#pragma unroll
+        for (int i = 0; i < D_STAGES; ++i) {
+            tma::mbar_init(bar_full + 8u * i, 2 * D_THREADS);
+            tma::mbar_init(bar_empty + 8u * i, D_THREADS / 32);
+        }
+        tma::mbar_fence_init();
     }
-    __syncthreads();
-    for (int step = 0; step < nsteps; ++step) {
-        const int cur = step & 1, nxt = cur ^ 1;
-        const bool more = step + 1 < nsteps;
-        if (more) load_y(nxt, step + 1);
-        const double* xb = Xs + ((size_t) cur * DM + wi * 64 + g) * DLD + t4;
-        const double* yb = Ys + ((size_t) cur * DN + wj * 32 + g) * DLD + t4;
+    __syncthreads();                  // logtab, barriers
+    auto arrive = [&](uint32_t bar) {
+        asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(bar) : "memory");
+    };
+    // produce this thread's share of stage (step % D_STAGES): its Y copies and its 8 samples of the S tile
+    auto produce = [&](int step) {
+        const int buf = step % D_STAGES;
+        if (step >= D_STAGES) tma::mbar_wait(bar_empty + 8u * (uint32_t) buf, (uint32_t) ((step / D_STAGES - 1) & 1));
+        load_y(buf, step);
+        gen_x(buf);
+        arrive(bar_full + 8u * (uint32_t) buf);
+    };
+    auto consume = [&](int step) {
+        const int buf = step % D_STAGES;
+        tma::mbar_wait(bar_full + 8u * (uint32_t) buf, (uint32_t) ((step / D_STAGES) & 1));
+        const double* xb = Xs + ((size_t) buf * DM + wi * (D_MI * 8) + g) * DLD + t4;
+        const double* yb = Ys + ((size_t) buf * DN + wj * (D_NI * 8) + g) * DLD + t4;
 #pragma unroll
         for (int k4 = 0; k4 < DK / 4; ++k4) {
-            double af[8], bf[4];
+            double af[D_MI], bf[D_NI];
 #pragma unroll
-            for (int mi = 0; mi < 8; ++mi) af[mi] = xb[mi * 8 * DLD + k4 * 4];
+            for (int mi = 0; mi < D_MI; ++mi) af[mi] = xb[mi * 8 * DLD + k4 * 4];
 #pragma unroll
-            for (int ni = 0; ni < 4; ++ni) bf[ni] = yb[ni * 8 * DLD + k4 * 4];
+            for (int ni = 0; ni < D_NI; ++ni) bf[ni] = yb[ni * 8 * DLD + k4 * 4];
 #pragma unroll
-            for (int mi = 0; mi < 8; ++mi)
+            for (int mi = 0; mi < D_MI; ++mi)
 #pragma unroll
-                for (int ni = 0; ni < 4; ++ni) dmma(acc[mi][ni], af[mi], bf[ni]);
+                for (int ni = 0; ni < D_NI; ++ni) dmma(acc[mi][ni], af[mi], bf[ni]);
         }
-        if (more) gen_x(nxt);
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
-        __syncthreads();
+        __syncwarp();
+        if (lane == 0) arrive(bar_empty + 8u * (uint32_t) buf);
+    };
+    // prologue: stages 0 and 1; then step s consumes stage s and produces stage s + 2, in opposite order for the two
+    // warps of a scheduler (warp w and w + 4)
+    if (nsteps > 0) produce(0);
+    if (nsteps > 1) produce(1);
+    if ((wi & 1) == 0) {
+        for (int step = 0; step < nsteps; ++step) {
+            consume(step);
+            if (step + 2 < nsteps) produce(step + 2);
+        }
+    } else {
+        for (int step = 0; step < nsteps; ++step) {
+            if (step + 2 < nsteps) produce(step + 2);
+            consume(step);
+        }
     }
 
     // epilogue: c0 at (row g, col 2 t4), c1 at (row g, col 2 t4 + 1) of each 8 x 8 tile
 #pragma unroll
-    for (int mi = 0; mi < 8; ++mi) {
-        const int64_t i = i0 + wi * 64 + mi * 8 + g;
+    for (int mi = 0; mi < D_MI; ++mi) {
+        const int64_t i = i0 + wi * (D_MI * 8) + mi * 8 + g;
 #pragma unroll
-        for (int ni = 0; ni < 4; ++ni) {
+        for (int ni = 0; ni < D_NI; ++ni) {
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
-                const int64_t j = j0 + wj * 32 + ni * 8 + 2 * t4 + e;
+                const int64_t j = j0 + wj * (D_NI * 8) + ni * 8 + 2 * t4 + e;
                 if (a.W) {
                     a.W[((int64_t) split * a.Q_pad + j) * a.P_pad + i] = acc[mi][ni][e];
                 } else if (i < a.P && j < a.Q) {
@@ -243,7 +282,7 @@ int launch_dense_dmma_f64(const DenseProblem<double>& p, cudaStream_t st) {
         a.W = (double*) workspace(6, (size_t) splits * a.P_pad * a.Q_pad * sizeof(double));
         if (!a.W) return fail_cuda(cudaErrorMemoryAllocation, "split-K workspace");
     }
-    constexpr size_t smem = (size_t) 2 * (DM + DN) * DLD * sizeof(double);
+    constexpr size_t smem = (size_t) D_STAGES * (DM + DN) * DLD * sizeof(double);
     static bool attr_done[2] = {false, false};
     const bool gauss = p.family == 'G';
     if (!attr_done[gauss]) {
