@@ -428,6 +428,32 @@ def test_saso_owner_kernel_vs_oracle_and_vs_atomic_kernel(gpu, port):
         rb.set_option("saso_path", 0)
 
 
+def test_saso_apply_full_size_exact_on_all_ones(gpu):
+    """BASELINE config 4 at its full size (d=2048, m=8,000,000, n=256, vec_nnz=8). With A = all ones every entry of
+    row r of B is the sum of the signs in row r of S: an integer far below 2^24, so float accumulation is exact in
+    any order and B must EQUAL the row sums of the sampled operator (whose index/sign arrays are checked bit for bit
+    against the oracle elsewhere). Also checks that the operator passed unfilled stays unfilled."""
+    import randblas_b200 as rb
+    import torch
+    d, n, m, vn = 2048, 256, 8000000, 8
+    S = rb.SparseSkOp(rb.SparseDist(d, m, vn), rb.RNGState(1997), dtype=np.float32)
+    A = torch.ones(m * n, dtype=torch.float32, device="cuda")
+    B = torch.full((d * n,), 3.0, dtype=torch.float32, device="cuda")
+    before = rb.counter("saso_owner_launches")
+    rb.sketch_general("R", "N", "N", d, n, m, 1.0, S, 0, 0, A, n, 0.0, B, n)
+    assert rb.counter("saso_owner_launches") > before, "the binned SASO kernel did not run at the benchmark shape"
+    assert S.nnz < 0 and S.rows is None, "sketch_general must not sample the caller's operator"
+    del A
+    rb.fill_sparse(S)
+    assert S.nnz == vn * m
+    rowsum = torch.zeros(d, dtype=torch.float32, device="cuda").index_add_(0, S.rows, S.vals)
+    Bm = B.view(d, n)
+    assert torch.equal(Bm, rowsum[:, None].expand(d, n)), float((Bm - rowsum[:, None]).abs().max())
+    # every column of S holds vec_nnz distinct rows (Fisher-Yates without replacement)
+    r = S.rows.view(m, vn)[:200000]
+    assert int((r.sort(dim=1).values.diff(dim=1) == 0).sum()) == 0
+
+
 def _sp(mat, fmt, dt):
     if fmt == 0:
         m = mat.tocsr()
