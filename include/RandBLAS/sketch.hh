@@ -81,7 +81,12 @@ template <typename T, typename RNG, typename sint_t>
 inline void sketch_general(blas::Layout layout, blas::Op opS, blas::Op opA, int64_t d, int64_t n, int64_t m, T alpha,
                            const SparseSkOp<T, RNG, sint_t>& S, int64_t ro_s, int64_t co_s, const T* A, int64_t lda, T beta,
                            T* B, int64_t ldb) {
-    randblas_require(S.dist.major_axis == Axis::Short);
+    if (S.dist.major_axis != Axis::Short && S.nnz < 0) {
+        // LASO, not yet sampled: a temporary is sampled and dropped, as in the reference (skge.hh:483-488)
+        SparseSkOp<T, RNG, sint_t> tmp(S.dist, S.seed_state);
+        fill_sparse(tmp);
+        return sketch_general(layout, opS, opA, d, n, m, alpha, tmp, ro_s, co_s, A, lda, beta, B, ldb);
+    }
     internal::finish(internal::skges_c(true, internal::to_char(layout), internal::to_char(opS), internal::to_char(opA), d, n,
                                        m, alpha, S, ro_s, co_s, A, lda, beta, B, ldb),
                      __func__);
@@ -116,7 +121,11 @@ template <typename T, typename RNG, typename sint_t>
 inline void sketch_general(blas::Layout layout, blas::Op opA, blas::Op opS, int64_t m, int64_t d, int64_t n, T alpha,
                            const T* A, int64_t lda, const SparseSkOp<T, RNG, sint_t>& S, int64_t ro_s, int64_t co_s, T beta,
                            T* B, int64_t ldb) {
-    randblas_require(S.dist.major_axis == Axis::Short);
+    if (S.dist.major_axis != Axis::Short && S.nnz < 0) {
+        SparseSkOp<T, RNG, sint_t> tmp(S.dist, S.seed_state);
+        fill_sparse(tmp);
+        return sketch_general(layout, opA, opS, m, d, n, alpha, A, lda, tmp, ro_s, co_s, beta, B, ldb);
+    }
     internal::finish(internal::skges_c(false, internal::to_char(layout), internal::to_char(opS), internal::to_char(opA), d, n,
                                        m, alpha, S, ro_s, co_s, A, lda, beta, B, ldb),
                      __func__);

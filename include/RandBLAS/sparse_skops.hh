@@ -1,6 +1,6 @@
 // randblas_b200 -- header-only drop-in layer, part 3: SparseDist, SparseSkOp, fill_sparse.
-// Mirrors RandBLAS/sparse_skops.hh of the reference (file:line cited per item). Only short-axis-sparse
-// operators (SASO, Axis::Short) are on the hot path; sampling a long-axis-sparse operator raises Error.
+// Mirrors RandBLAS/sparse_skops.hh of the reference (file:line cited per item). Short-axis-sparse operators (SASO,
+// Axis::Short) are on the hot path; long-axis-sparse ones (LASO) are sampled by rb_fill_sparse_laso and applied as COO.
 #pragma once
 #include <algorithm>
 #include <cmath>
@@ -149,12 +149,16 @@ RNGState<RNG> repeated_fisher_yates(int64_t k, int64_t n, int64_t r, sint_t* sam
 template <typename T, typename sint_t, typename RNG>
 RNGState<RNG> fill_sparse_unpacked_nosub(const SparseDist& D, int64_t& nnz, T* vals, sint_t* rows, sint_t* cols,
                                          const RNGState<RNG>& seed_state) {
-    randblas_require(D.major_axis == Axis::Short);   // LASO sampling is not built
     uint32_t next[4];
     int64_t got = 0;
-    internal::check(rb_fill_sparse_saso(D.n_rows, D.n_cols, D.vec_nnz, seed_state.counter.v, seed_state.key.v, vals,
-                                        (int) sizeof(T), rows, cols, (int) sizeof(sint_t), &got, next, nullptr),
-                    __func__);
+    if (D.major_axis == Axis::Short)     // :526-533
+        internal::check(rb_fill_sparse_saso(D.n_rows, D.n_cols, D.vec_nnz, seed_state.counter.v, seed_state.key.v, vals,
+                                            (int) sizeof(T), rows, cols, (int) sizeof(sint_t), &got, next, nullptr),
+                        __func__);
+    else                                 // :534-564
+        internal::check(rb_fill_sparse_laso(D.n_rows, D.n_cols, D.vec_nnz, seed_state.counter.v, seed_state.key.v, vals,
+                                            (int) sizeof(T), rows, cols, (int) sizeof(sint_t), &got, next, nullptr),
+                        __func__);
     nnz = got;
     return internal::with_counter(seed_state, next);
 }

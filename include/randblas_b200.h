@@ -86,6 +86,15 @@ int rb_fill_dense_f64(char layout, int64_t D_rows, int64_t D_cols, char family, 
 int rb_fill_sparse_saso(int64_t D_rows, int64_t D_cols, int64_t vec_nnz, const uint32_t ctr[4], const uint32_t key[2],
                         void* vals, int val_bytes, void* rows, void* cols, int idx_bytes, int64_t* nnz,
                         uint32_t next_ctr[4], void* stream);
+/* ---- K3c: LASO (Axis::Long) generation ----
+ * Replaces the long-axis branch of RandBLAS::fill_sparse_unpacked_nosub (RandBLAS/sparse_skops.hh:534-564) with
+ * sample_indices_iid_uniform (RandBLAS/util.hh:515-547) and laso_merge_long_axis_vector_coo_data
+ * (sparse_skops.hh:453-491). vals/rows/cols hold full_nnz = vec_nnz * dim_minor entries; *nnz (host) receives the
+ * number actually written (repeated indices inside a vector are merged). Entries of a vector come in
+ * first-occurrence order (the reference's order for vectors with repeats is std::unordered_map's). Synchronises. */
+int rb_fill_sparse_laso(int64_t D_rows, int64_t D_cols, int64_t vec_nnz, const uint32_t ctr[4], const uint32_t key[2],
+                        void* vals, int val_bytes, void* rows, void* cols, int idx_bytes, int64_t* nnz,
+                        uint32_t next_ctr[4], void* stream);
 /* public repeated_fisher_yates(k, n, r, samples, state) (RandBLAS/sparse_skops.hh:259-264) */
 int rb_repeated_fisher_yates(int64_t k, int64_t n, int64_t r, void* samples, int idx_bytes, const uint32_t ctr[4],
                              const uint32_t key[2], uint32_t next_ctr[4], void* stream);

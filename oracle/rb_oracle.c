@@ -259,6 +259,62 @@ int rbo_fill_sparse_saso(int64_t D_rows, int64_t D_cols, int64_t vec_nnz, const 
     return rc;
 }
 
+/* fill_sparse_unpacked_nosub, LASO branch (Axis::Long), RandBLAS/sparse_skops.hh:534-564, with
+ * sample_indices_iid_uniform<T, sint_t, WriteRademachers = true> (RandBLAS/util.hh:515-547) and
+ * laso_merge_long_axis_vector_coo_data (sparse_skops.hh:453-491).
+ * The state runs sequentially through the vectors: per vector, pairs of uneg11 floats are consumed from
+ * consecutive Philox blocks (len_c = 4 -> two (index, sign) pairs per block); a partially used block is skipped
+ * at the end of the vector (util.hh:545), so vector i starts at seed + i * ceil(vec_nnz / 2).
+ * Repeated indices: one entry, value sqrt(count) * (sign of the first occurrence), in T arithmetic.
+ * ORDER: the reference rewrites a vector that has repeats in std::unordered_map iteration order (a property of
+ * the C++ library, sparse_skops.hh:484-488); this restatement uses first-occurrence order, callers compare such
+ * vectors as sets. Vectors without repeats keep draw order in both. */
+int rbo_fill_sparse_laso(int64_t D_rows, int64_t D_cols, int64_t vec_nnz, const uint32_t ctr[4], const uint32_t key[2],
+                         void* vals, int val_bytes, void* rows, void* cols, int idx_bytes, int64_t* nnz,
+                         uint32_t next_ctr[4]) {
+    int64_t info[3]; double iso;
+    if (rbo_sparse_dist_info(D_rows, D_cols, vec_nnz, 'L', info, &iso)) return 1;
+    const int64_t dim_major = info[0], dim_minor = info[1];
+    void* idxs_short = (D_rows <= D_cols) ? rows : cols;
+    void* idxs_long = (D_rows <= D_cols) ? cols : rows;
+    int64_t* idx = (int64_t*) malloc(sizeof(int64_t) * (size_t) vec_nnz);
+    int* neg = (int*) malloc(sizeof(int) * (size_t) vec_nnz);
+    uint32_t c[4];
+    memcpy(c, ctr, 16);
+    const double dN = (double) dim_major;
+    int64_t total = 0;
+    for (int64_t i = 0; i < dim_minor; ++i) {
+        uint32_t w[4];
+        rbo_philox4x32_10(c, key, w);
+        int rv_index = 0;
+        for (int64_t j = 0; j < vec_nnz; ++j) {                       /* util.hh:530-544 */
+            const double u01 = ((double) rbo_uneg11_f32(w[rv_index]) + 1.0) / 2.0;
+            idx[j] = (int64_t) ((double) (int64_t) dN * u01);
+            rv_index += 1;
+            neg[j] = (rbo_uneg11_f32(w[rv_index]) >= 0) ? 0 : 1;
+            rv_index += 1;
+            if (rv_index == 4) { rbo_ctr_incr(c, 1); rbo_philox4x32_10(c, key, w); rv_index = 0; }
+        }
+        if (rv_index > 0) rbo_ctr_incr(c, 1);                         /* util.hh:545 */
+        for (int64_t j = 0; j < vec_nnz; ++j) {                       /* merge, first-occurrence order */
+            int first = 1;
+            for (int64_t t = 0; t < j; ++t) if (idx[t] == idx[j]) { first = 0; break; }
+            if (!first) continue;
+            int64_t count = 1;
+            for (int64_t t = j + 1; t < vec_nnz; ++t) if (idx[t] == idx[j]) ++count;
+            store_idx(idxs_long, idx_bytes, total, idx[j]);
+            store_idx(idxs_short, idx_bytes, total, i);
+            if (val_bytes == 4) ((float*) vals)[total] = sqrtf((float) count) * (neg[j] ? -1.0f : 1.0f);
+            else ((double*) vals)[total] = sqrt((double) count) * (neg[j] ? -1.0 : 1.0);
+            ++total;
+        }
+    }
+    *nnz = total;
+    if (next_ctr) memcpy(next_ctr, c, 16);
+    free(idx); free(neg);
+    return 0;
+}
+
 int rbo_set_threads(int n) {
 #ifdef _OPENMP
     omp_set_num_threads(n);

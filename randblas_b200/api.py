@@ -276,11 +276,11 @@ def fill_dense(*args):
 
 
 def fill_sparse_unpacked_nosub(D, vals, rows, cols, seed_state):
-    """RandBLAS/sparse_skops.hh:515-565 (SASO). Returns (nnz, next_state)."""
-    _require(D.major_axis == Axis.Short, "D.major_axis == Axis::Short (LASO is not built yet)")
+    """RandBLAS/sparse_skops.hh:515-565 (SASO: :526-533, LASO: :534-564). Returns (nnz, next_state)."""
     nnz = ctypes.c_int64(-1)
     nxt = (ctypes.c_uint32 * 4)()
-    call("rb_fill_sparse_saso", "qqqpppippippp", D.n_rows, D.n_cols, D.vec_nnz, _addr(seed_state._c()),
+    fn = "rb_fill_sparse_saso" if D.major_axis == Axis.Short else "rb_fill_sparse_laso"
+    call(fn, "qqqpppippippp", D.n_rows, D.n_cols, D.vec_nnz, _addr(seed_state._c()),
          _addr(seed_state._k()), _ptr(vals), np.dtype(_dtype_of(vals)).itemsize, _ptr(rows), _ptr(cols),
          np.dtype(_dtype_of(rows)).itemsize, _addr(nnz), _addr(nxt), _stream(vals, rows, cols))
     return nnz.value, RNGState(counter=list(nxt), key=seed_state.key)
@@ -372,7 +372,11 @@ def _skge(left, layout, opS, opA, d, n, m, alpha, S, ro_s, co_s, A, lda, beta, B
              d, n, m, alpha, S.n_rows, S.n_cols, S.nnz, _ptr(S.vals), _ptr(S.rows), _ptr(S.cols),
              S.index_dtype.itemsize, ro_s, co_s, _ptr(A), lda, beta, _ptr(B), ldb, st)
         return
-    _require(D.major_axis == Axis.Short, "S.dist.major_axis == Axis::Short (LASO is not built yet)")
+    if D.major_axis != Axis.Short:
+        # LASO, not yet sampled: sample a temporary and drop it (the reference does the same, skge.hh:483-488)
+        tmp = SparseSkOp(D, seed, dtype=S.dtype, index_dtype=S.index_dtype)
+        fill_sparse(tmp)
+        return _skge(left, layout, opS, opA, d, n, m, alpha, tmp, ro_s, co_s, A, lda, beta, B, ldb)
     if left:       # sparse::lskges, skge.hh:465-492
         call(f"rb_lskges_{sfx}", "cccqqq" + t + "qqqpp" + "qqpq" + t + "pqp", layout, opS, opA, d, n, m, alpha,
              D.n_rows, D.n_cols, D.vec_nnz, _addr(seed._c()), _addr(seed._k()), ro_s, co_s, _ptr(A), lda, beta,

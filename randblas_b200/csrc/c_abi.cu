@@ -352,6 +352,38 @@ static int fill_sparse_impl(int64_t D_rows, int64_t D_cols, int64_t vec_nnz, con
     return rc;
 }
 
+// LASO generation (Axis::Long): fill_sparse_unpacked_nosub, sparse_skops.hh:534-564
+static int fill_sparse_laso_impl(int64_t D_rows, int64_t D_cols, int64_t vec_nnz, const uint32_t* ctr, const uint32_t* key,
+                                 void* vals, int val_bytes, void* rows, void* cols, int idx_bytes, int64_t* nnz,
+                                 uint32_t* next_ctr, void* stream) {
+    cudaStream_t st = (cudaStream_t) stream;
+    SparseDistInfo D = make_sparse_dist(D_rows, D_cols, vec_nnz, 'L');
+    RB_REQUIRE(D.ok);                          // sparse_skops.hh:219-223
+    RB_REQUIRE(ctr != nullptr && key != nullptr);
+    RB_REQUIRE(idx_bytes == 4 || idx_bytes == 8);
+    RB_REQUIRE(val_bytes == 4 || val_bytes == 8);
+    RB_REQUIRE(rows != nullptr);               // sparse_skops.hh:597
+    RB_REQUIRE(cols != nullptr);               // sparse_skops.hh:598
+    RB_REQUIRE(vals != nullptr);               // sparse_skops.hh:599
+    RB_REQUIRE(nnz != nullptr);
+    if (idx_bytes == 4) RB_REQUIRE(D.dim_minor <= 2147483647LL && D.dim_major <= 2147483647LL);
+    const Ctr128 c = load_ctr(ctr);
+    store_ctr(ctr_add(c, (uint64_t) (D.dim_minor * ((vec_nnz + 1) / 2))), next_ctr);      // sparse_skops.hh:274-279
+    Staged sv, sr, sc;
+    int rc = sv.open(vals, (size_t) val_bytes, 1, D.full_nnz, D.full_nnz, false, true, st); if (rc) return rc;
+    rc = sr.open(rows, (size_t) idx_bytes, 1, D.full_nnz, D.full_nnz, false, true, st); if (rc) return rc;
+    rc = sc.open(cols, (size_t) idx_bytes, 1, D.full_nnz, D.full_nnz, false, true, st); if (rc) return rc;
+    // short-axis index array is `rows` when n_rows <= n_cols (sparse_skops.hh:524-525)
+    void* idx_short = (D_rows <= D_cols) ? sr.dev : sc.dev;
+    void* idx_long = (D_rows <= D_cols) ? sc.dev : sr.dev;
+    rc = launch_laso(c, PhiloxKey{key[0], key[1]}, vec_nnz, D.dim_major, D.dim_minor, idx_long, idx_short, idx_bytes, sv.dev,
+                     val_bytes, nnz, st);
+    int rc2 = sv.close(); if (!rc) rc = rc2;
+    rc2 = sr.close(); if (!rc) rc = rc2;
+    rc2 = sc.close(); if (!rc) rc = rc2;
+    return rc;
+}
+
 // sparse operator applied to dense data [skge.hh:465-492, 598-626; spmm_dispatch.hh:52-219]
 template <typename T>
 static int skges_impl(bool left, char layout, char opS, char opA, int64_t d, int64_t n, int64_t m, T alpha,
@@ -659,6 +691,13 @@ int rb_fill_sparse_saso(int64_t D_rows, int64_t D_cols, int64_t vec_nnz, const u
                         uint32_t next_ctr[4], void* stream) {
     return fill_sparse_impl(D_rows, D_cols, vec_nnz, ctr, key, vals, val_bytes, rows, cols, idx_bytes, nnz, next_ctr,
                             stream);
+}
+
+int rb_fill_sparse_laso(int64_t D_rows, int64_t D_cols, int64_t vec_nnz, const uint32_t ctr[4], const uint32_t key[2],
+                        void* vals, int val_bytes, void* rows, void* cols, int idx_bytes, int64_t* nnz,
+                        uint32_t next_ctr[4], void* stream) {
+    return fill_sparse_laso_impl(D_rows, D_cols, vec_nnz, ctr, key, vals, val_bytes, rows, cols, idx_bytes, nnz, next_ctr,
+                                 stream);
 }
 
 int rb_repeated_fisher_yates(int64_t k, int64_t n, int64_t r, void* samples, int idx_bytes, const uint32_t ctr[4],

@@ -23,6 +23,10 @@ int launch_fill_dense(const DenseGen& g, char family, int64_t v0, int64_t nv, in
 int launch_saso(Ctr128 ctr, PhiloxKey key, int64_t vec_nnz, int64_t dim_major, int64_t dim_minor, void* idxs_major,
                 void* idxs_minor, int idx_bytes, void* vals, int val_bytes, cudaStream_t st);
 
+// LASO generation (laso.cu): compacted COO arrays in first-occurrence order, entry count to *nnz_host (synchronises)
+int launch_laso(Ctr128 ctr, PhiloxKey key, int64_t vec_nnz, int64_t dim_major, int64_t dim_minor, void* idxs_long,
+                void* idxs_short, int idx_bytes, void* vals, int val_bytes, int64_t* nnz_host, cudaStream_t st);
+
 // Canonical dense problem: C(P x Q) = alpha * X(P x K) * Y(K x Q) + beta * C where X = op(S window) and
 // Y, C are strided views (element (k,j) of Y at Y + k*yrs + j*ycs; element (i,j) of C at C + i*crs + j*ccs).
 // Right sketches are mapped to this form by transposition in the C-ABI layer.

@@ -144,6 +144,32 @@ static void device_checks() {
     for (int i = 0; i < 35; ++i) ok = ok && std::fabs(B1[i] - B2[i]) <= 100 * tol;
     CHECK(ok);
 
+    // --- LASO (Axis::Long): every row of a wide operator holds at most vec_nnz entries, values +-sqrt(count),
+    //     and sampled / unsampled operators give the same product (test_sparseskop.cc:119-146)
+    SparseDist Dl(7, 200, 4, Axis::Long);
+    SparseSkOp<T, DefaultRNG, int64_t> Sl(Dl, seed);
+    fill_sparse(Sl);
+    CHECK(Sl.nnz > 0 && Sl.nnz <= 28);
+    ok = true;
+    double sumsq = 0;
+    for (int64_t e = 0; e < Sl.nnz; ++e) {
+        ok = ok && Sl.rows[e] >= 0 && Sl.rows[e] < 7 && Sl.cols[e] >= 0 && Sl.cols[e] < 200;
+        if (e > 0) ok = ok && Sl.rows[e] >= Sl.rows[e - 1];
+        sumsq += (double) Sl.vals[e] * (double) Sl.vals[e];
+    }
+    CHECK(ok);
+    CHECK(std::fabs(sumsq - 28.0) < 1e-4);                        // sqrt(count)^2 summed = draws = vec_nnz * dim_minor
+    std::vector<T> B3(7 * 5, T(0)), B4(7 * 5, T(0));
+    SparseSkOp<T, DefaultRNG, int64_t> Slu(Dl, seed);
+    sketch_general(blas::Layout::ColMajor, blas::Op::NoTrans, blas::Op::NoTrans, 7, 5, 200, T(1), Sl, A.data(), 200, T(0),
+                   B3.data(), 7);
+    sketch_general(blas::Layout::ColMajor, blas::Op::NoTrans, blas::Op::NoTrans, 7, 5, 200, T(1), Slu, A.data(), 200, T(0),
+                   B4.data(), 7);
+    CHECK(Slu.nnz < 0);
+    ok = true;
+    for (int i = 0; i < 35; ++i) ok = ok && std::fabs(B3[i] - B4[i]) <= 100 * tol;
+    CHECK(ok);
+
     // --- sketch_sparse applied to a sparse identity reproduces S (test_sketch_sparse.cc, COO by design)
     std::vector<T> ones(m, T(1));
     std::vector<int64_t> idx(m);

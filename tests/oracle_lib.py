@@ -186,14 +186,13 @@ class Port(_Base):
         return buff, nxt
 
     def fill_sparse(self, D_rows, D_cols, vec_nnz, axis, ctr, key, dtype, idx_dtype=np.int64):
-        assert axis == "S", "the port restates SASO only"
-        nnz_full = vec_nnz * max(D_rows, D_cols)
+        nnz_full = vec_nnz * (max(D_rows, D_cols) if axis == "S" else min(D_rows, D_cols))
         vals = np.zeros(nnz_full, dtype)
         rows = np.zeros(nnz_full, idx_dtype)
         cols = np.zeros(nnz_full, idx_dtype)
         nnz = np.zeros(1, np.int64)
         nxt = np.zeros(4, np.uint32)
-        rc = _call(self.lib.rbo_fill_sparse_saso, "qqqpppippipp",
+        rc = _call(self.lib.rbo_fill_sparse_saso if axis == "S" else self.lib.rbo_fill_sparse_laso, "qqqpppippipp",
                    (D_rows, D_cols, vec_nnz, u32(ctr), u32(key), vals, vals.itemsize, rows, cols, rows.itemsize, nnz, nxt))
         self._check(rc, "fill_sparse")
         return vals, rows, cols, int(nnz[0]), nxt

@@ -13,7 +13,7 @@ import pytest
 
 import oracle_lib as ol
 from golden_util import dense_data
-from test_oracle_pins import run_sketch_case, sketch_case_inputs
+from test_oracle_pins import _laso_vectors, laso_golden_cases, run_sketch_case, sketch_case_inputs
 
 pytestmark = pytest.mark.gpu
 
@@ -242,6 +242,61 @@ def test_saso_sweep_vs_oracle(gpu, port):
 
 
 # --------------------------------------------------------------------------------------- sketches
+def test_laso_fill_vs_oracle_and_goldens(gpu, port):
+    """LASO (Axis::Long) sampling on the device: element for element equal to the oracle (both emit first-occurrence
+    order), and equal as per-vector sets to the fixtures generated from the compiled reference; nnz and next state
+    exact. vec_nnz 33 exercises the thread-per-vector kernel, everything else the warp kernel."""
+    n = 0
+    for t, r, c, vn, k, idt, z in laso_golden_cases():
+        ctr, key = ol.state_from_u64(k)
+        for dt, vtag in ((np.float32, "_v32"), (np.float64, "_v64")):
+            gv, gr, gc, gn, gx = gpu.fill_sparse(r, c, vn, "L", ctr, key, dt, idt)
+            pv, pr, pc, pn, px = port.fill_sparse(r, c, vn, "L", ctr, key, dt, idt)
+            assert gn == pn == len(z[t + "_rows"]), (t, gn, pn)
+            assert list(gx) == list(px) == list(z[t + "_next"]), t
+            assert np.array_equal(gr[:gn], pr[:pn]) and np.array_equal(gc[:gn], pc[:pn]), t
+            assert np.array_equal(gv[:gn], pv[:pn]), t
+            assert _laso_vectors(gr[:gn], gc[:gn], gv[:gn], r, c) == \
+                _laso_vectors(z[t + "_rows"], z[t + "_cols"], z[t + vtag], r, c), t
+        n += 1
+    assert n >= 80
+    # a larger operator against the oracle: wide and tall, int64
+    for (r, c, vn) in ((300, 20000, 8), (20000, 300, 5)):
+        ctr, key = ol.state_from_u64(7)
+        gv, gr, gc, gn, gx = gpu.fill_sparse(r, c, vn, "L", ctr, key, np.float32, np.int64)
+        pv, pr, pc, pn, px = port.fill_sparse(r, c, vn, "L", ctr, key, np.float32, np.int64)
+        assert gn == pn and list(gx) == list(px)
+        assert np.array_equal(gr[:gn], pr[:pn]) and np.array_equal(gc[:gn], pc[:pn]) and np.array_equal(gv[:gn], pv[:pn])
+
+
+def test_laso_operator_sketch(gpu):
+    """sketch_general with a LASO operator, unsampled (a temporary is sampled and dropped, skge.hh:483-488) and
+    sampled, left and right, against a dense product built from the operator's own COO arrays (checked against the
+    oracle above)."""
+    import randblas_b200 as rb
+    import torch
+    rng = np.random.default_rng(11)
+    for (d, m, vn) in ((40, 900, 6), (900, 40, 3)):
+        D = rb.SparseDist(d, m, vn, rb.Axis.Long)
+        S = rb.SparseSkOp(D, rb.RNGState(5), dtype=np.float64)
+        n = 17
+        A = rng.standard_normal((m, n))
+        B0 = rng.standard_normal((d, n))
+        Bd = torch.from_numpy(B0.copy()).cuda().view(-1)
+        rb.sketch_general("R", "N", "N", d, n, m, 0.5, S, 0, 0, torch.from_numpy(A).cuda().view(-1), n, -1.5, Bd, n)
+        assert S.nnz < 0, "the caller's operator must stay unsampled"
+        rb.fill_sparse(S)
+        dense = np.zeros((d, m))
+        np.add.at(dense, (S.rows[: S.nnz].cpu().numpy(), S.cols[: S.nnz].cpu().numpy()), S.vals[: S.nnz].cpu().numpy())
+        want = 0.5 * dense @ A - 1.5 * B0
+        assert relerr(Bd.cpu().numpy().reshape(d, n), want) < 1e-12
+        # sampled operator, right sketch with the transposed operator: C = A2 * S^T
+        A2 = rng.standard_normal((n, m))
+        Cd = torch.zeros(n * d, dtype=torch.float64, device="cuda")
+        rb.sketch_general("R", "N", "T", n, d, m, 1.0, torch.from_numpy(A2).cuda().view(-1), m, S, 0, 0, 0.0, Cd, d)
+        assert relerr(Cd.cpu().numpy().reshape(n, d), A2 @ dense.T) < 1e-12
+
+
 def test_sketch_goldens(gpu, port, gold):
     for c in gold.m["sketch"]:
         A, lda, B, ldb = sketch_case_inputs(port.fill_dense_unpacked, c)
@@ -620,4 +675,6 @@ def test_argument_errors_on_gpu(gpu):
         rb.sketch_general("R", "N", "N", 8, 4, 64, 1.0, S, 0, 0, A, 3, 0.0, B, 4)       # lda < cols_A
     Ssp = rb.SparseSkOp(rb.SparseDist(8, 64, 4, rb.Axis.Long), rb.RNGState(0))
     with pytest.raises(rb.RandBLASError):
-        rb.sketch_general("C", "N", "N", 8, 4, 64, 1.0, Ssp, 0, 0, A, 64, 0.0, B, 8)    # LASO not built
+        rb.sketch_general("C", "N", "N", 8, 4, 64, 1.0, Ssp, 0, 1, A, 64, 0.0, B, 8)    # window leaves the LASO operator
+    with pytest.raises(rb.RandBLASError):
+        rb.SparseDist(8, 64, 9, rb.Axis.Short)                                          # vec_nnz > dim_major

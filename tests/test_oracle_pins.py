@@ -176,6 +176,42 @@ def run_sketch_case(impl, c, A, lda, B, ldb):
         raise KeyError(c["kind"])
 
 
+def _laso_vectors(rows, cols, vals, n_rows, n_cols):
+    """(short index, long index, value) triples sorted inside each long-axis vector: the order-free view."""
+    sh, lg = (rows, cols) if n_rows <= n_cols else (cols, rows)
+    return sorted(zip(sh.tolist(), lg.tolist(), vals.tolist()))
+
+
+def laso_golden_cases():
+    import os
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_laso.npz"))
+    tags = sorted({k[: -len("_rows")] for k in z.files if k.endswith("_rows")})
+    for t in tags:
+        shape, kk, key, itag = t[len("laso_"):].split("_")
+        r, c = map(int, shape.split("x"))
+        yield t, r, c, int(kk[1:]), int(key[3:]), (np.int32 if itag == "i32" else np.int64), z
+
+
+def test_golden_laso(port):
+    """LASO operators (RandBLAS/sparse_skops.hh:534-564) against fixtures generated from the compiled reference:
+    nnz, next state, per-vector (index, value) sets identical; draw order identical where a vector has no repeats
+    (the reference's order for vectors with repeats is std::unordered_map's and is not part of the contract)."""
+    n = 0
+    for t, r, c, vn, k, idt, z in laso_golden_cases():
+        ctr, key = ol.state_from_u64(k)
+        for dt, vtag in ((np.float32, "_v32"), (np.float64, "_v64")):
+            vals, rows, cols, nnz, nxt = port.fill_sparse(r, c, vn, "L", ctr, key, dt, idt)
+            assert nnz == len(z[t + "_rows"]), t
+            assert list(nxt) == list(z[t + "_next"]), t
+            assert _laso_vectors(rows[:nnz], cols[:nnz], vals[:nnz], r, c) == \
+                _laso_vectors(z[t + "_rows"], z[t + "_cols"], z[t + vtag], r, c), t
+            if nnz == vn * min(r, c):      # no vector had a repeat: same order, element for element
+                assert np.array_equal(rows[:nnz], z[t + "_rows"]) and np.array_equal(cols[:nnz], z[t + "_cols"]), t
+                assert np.array_equal(vals[:nnz], z[t + vtag]), t
+        n += 1
+    assert n >= 80
+
+
 def test_golden_sketch_products(port, gold):
     assert len(gold.m["sketch"]) >= 30
     for c in gold.m["sketch"]:
