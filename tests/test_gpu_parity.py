@@ -663,6 +663,67 @@ def test_tensor_core_float_sketch_vs_oracle(gpu, port):
         assert np.array_equal(B1.reshape(n, d + 1)[:, d], B0.reshape(n, d + 1)[:, d])
 
 
+def test_edge_cases_beta_zero_overwrites_nan_and_empty_dimensions(gpu):
+    """BLAS semantics the reference inherits (blas::gemm; util.hh:55-62 safe_scal): beta == 0 overwrites B without
+    reading it (NaNs in B must not survive), alpha == 0 and m == 0 leave beta * B, zero-sized outputs are no-ops.
+    Run on shapes that reach each kernel: tcgen05 float, DMMA double, generic SIMT, binned SASO, atomic SASO,
+    k-group sketch_sparse."""
+    import randblas_b200 as rb
+    import torch
+    nan = float("nan")
+
+    def dense_case(dt, d, n, m, layout):
+        tdt = torch.float32 if dt == np.float32 else torch.float64
+        S = rb.DenseSkOp(rb.DenseDist(d, m, rb.ScalarDist.Uniform), rb.RNGState(3), dt)
+        A = torch.randn(m * n, dtype=tdt, device="cuda")
+        lda, ldb = (m, d) if layout == "C" else (n, n)
+        Bn = torch.full((d * n,), nan, dtype=tdt, device="cuda")
+        Bz = torch.zeros(d * n, dtype=tdt, device="cuda")
+        rb.sketch_general(layout, "N", "N", d, n, m, 1.0, S, 0, 0, A, lda, 0.0, Bn, ldb)
+        rb.sketch_general(layout, "N", "N", d, n, m, 1.0, S, 0, 0, A, lda, 0.0, Bz, ldb)
+        assert bool(torch.isfinite(Bn).all()) and torch.equal(Bn, Bz), ("beta=0 must not read B", dt, d, n, m, layout)
+        B2 = torch.full((d * n,), 2.0, dtype=tdt, device="cuda")
+        rb.sketch_general(layout, "N", "N", d, n, m, 0.0, S, 0, 0, A, lda, 0.5, B2, ldb)       # alpha == 0
+        assert bool((B2 == 1.0).all())
+        rb.sketch_general(layout, "N", "N", d, n, 0, 1.0, S, 0, 0, A, max(lda if layout == "R" else 1, 1), 3.0, B2, ldb)
+        assert bool((B2 == 3.0).all()), "m == 0 leaves beta * B"
+        rb.sketch_general(layout, "N", "N", d, 0, m, 1.0, S, 0, 0, A, lda if layout == "C" else 1, 0.0, B2, ldb if layout == "C" else 1)
+        assert bool((B2 == 3.0).all()), "n == 0 is a no-op"
+
+    dense_case(np.float32, 256, 512, 4096, "C")      # tcgen05 path
+    dense_case(np.float64, 256, 256, 4096, "C")      # DMMA path
+    dense_case(np.float32, 33, 17, 129, "R")         # generic kernel
+    dense_case(np.float64, 33, 17, 129, "R")
+
+    for (d, n, m, vn) in ((2048, 64, 40000, 8), (45, 29, 211, 4)):       # binned kernel / atomic kernel
+        S = rb.SparseSkOp(rb.SparseDist(d, m, vn), rb.RNGState(3), dtype=np.float32)
+        A = torch.randn(m * n, dtype=torch.float32, device="cuda")
+        Bn = torch.full((d * n,), nan, dtype=torch.float32, device="cuda")
+        Bz = torch.zeros(d * n, dtype=torch.float32, device="cuda")
+        rb.sketch_general("R", "N", "N", d, n, m, 1.0, S, 0, 0, A, n, 0.0, Bn, n)
+        rb.sketch_general("R", "N", "N", d, n, m, 1.0, S, 0, 0, A, n, 0.0, Bz, n)
+        assert bool(torch.isfinite(Bn).all())
+        assert float((Bn - Bz).abs().max()) <= 1e-4 * float(Bz.abs().max())     # reductions commute up to rounding
+        B2 = torch.full((d * n,), 2.0, dtype=torch.float32, device="cuda")
+        rb.sketch_general("R", "N", "N", d, n, m, 0.0, S, 0, 0, A, n, 0.5, B2, n)
+        assert bool((B2 == 1.0).all())
+        rb.sketch_general("R", "N", "N", d, n, 0, 1.0, S, 0, 0, A, n, 3.0, B2, n)
+        assert bool((B2 == 3.0).all())
+
+    # sketch_sparse: CSR with an empty matrix, and NaN-filled B with beta == 0
+    d, m, n = 64, 5000, 300
+    S = rb.DenseSkOp(rb.DenseDist(d, m), rb.RNGState(3), np.float32)
+    rowptr = torch.zeros(m + 1, dtype=torch.int64, device="cuda")
+    empty = rb.CSRMatrix(m, n, 0, torch.zeros(1, dtype=torch.float32, device="cuda"), rowptr,
+                         torch.zeros(1, dtype=torch.int64, device="cuda"))
+    Bn = torch.full((d * n,), nan, dtype=torch.float32, device="cuda")
+    rb.sketch_sparse("C", "N", "N", d, n, m, 1.0, S, 0, 0, empty, 0.0, Bn, d)
+    assert bool((Bn == 0).all()), "empty sparse matrix with beta == 0 gives zeros"
+    B2 = torch.full((d * n,), 2.0, dtype=torch.float32, device="cuda")
+    rb.sketch_sparse("C", "N", "N", d, n, m, 1.0, S, 0, 0, empty, 0.5, B2, d)
+    assert bool((B2 == 1.0).all())
+
+
 def test_argument_errors_on_gpu(gpu):
     import randblas_b200 as rb
     import torch
