@@ -26,6 +26,14 @@
 // split-K partial tiles go to a workspace and are summed in a fixed order, in round-to-nearest fp32, by a
 // second small kernel, so the result does not depend on the grid (the reference guarantees thread-count invariance, dense_skops.hh:90-94).
 //
+// Data contiguous along Q instead of K (left sketch of RowMajor data, right sketch of ColMajor data -- the
+// range-finder call A * S): the Y tile arrives un-swizzled as 32 k-rows of 256 q (one TMA box) in a raw staging
+// buffer and the generator warps transpose it into the K-major swizzled Y / Y_lo tiles (4 conflict-free 4-byte reads,
+// 2 conflict-free 16-byte writes per 4 elements) before they generate X, so the next raw tile travels while X is
+// being generated. The MMA side is unchanged. (Feeding the Q-contiguous tile to tcgen05 directly as an MN-major
+// operand -- instruction-descriptor bit 16, LBO 4096 / SBO 1024 -- faulted with "illegal memory access" on this
+// toolchain and was dropped.)
+//
 // Roofline: tensor. 2*P*Q*K algorithmic flops, 3 MMAs issued per product => peak = TF32 dense peak / 3.
 #include <cuda.h>
 #include "common.cuh"
@@ -41,8 +49,12 @@ constexpr int X_PER_THREAD = (BM * BK / 4) / (32 * GEN_WARPS);   // Philox block
 constexpr int TC_THREADS = 64 + 32 * GEN_WARPS;
 constexpr uint32_t X_BYTES = BM * BK * 4, Y_BYTES = BN * BK * 4;
 constexpr uint32_t STAGE_BYTES = 2 * X_BYTES + 2 * Y_BYTES;
-constexpr uint32_t BAR_OFFSET = STAGES * STAGE_BYTES;
+constexpr int RAW_K = 16;                                // k-rows per raw tile: the 32-deep step arrives in two halves
+constexpr uint32_t RAW_BYTES = RAW_K * BN * 4;
+constexpr uint32_t RAW_OFFSET = STAGES * STAGE_BYTES;   // raw Q-contiguous Y tile (y_mn mode): RAW_K k-rows x 256 q
+constexpr uint32_t BAR_OFFSET = RAW_OFFSET + RAW_BYTES;
 constexpr uint32_t TC_SMEM = BAR_OFFSET + 128 + 1024;   // barriers + TMEM slot + 1 KB alignment slack
+static_assert(TC_SMEM + 8752 + 64 <= 232448, "shared memory budget (dynamic + the Gaussian table)");
 constexpr uint32_t TMEM_COLS = 512;      // two 128 x 256 fp32 accumulators: hi*hi and the two cross terms
 constexpr int MAX_CHAIN_STEPS = 40;       // K steps accumulated in TMEM before the partial sum leaves the tensor core
 
@@ -56,6 +68,7 @@ struct TcArgs {
     int kshift;        // u0 & 3: when non-zero every 4-wide chunk of X straddles two Philox blocks
     int64_t P, Q;
     int steps_total;   // ceil(K / 32)
+    int y_mn;          // 1: Y is Q-contiguous; raw tiles are transposed by the generator warps
     int splits;
     float alpha, beta;
     float* C;
@@ -165,7 +178,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) skge3_tc_kernel(const __grid_co
     auto bar_ready = [&](int s) { return bar0 + 8u * (STAGES + s); };
     auto bar_empty = [&](int s) { return bar0 + 8u * (2 * STAGES + s); };
     const uint32_t bar_accum = bar0 + 8u * (3 * STAGES);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + BAR_OFFSET + 8 * (3 * STAGES + 1));
+    const uint32_t bar_raw_full = bar0 + 8u * (3 * STAGES + 1), bar_raw_empty = bar0 + 8u * (3 * STAGES + 2);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + BAR_OFFSET + 8 * (3 * STAGES + 3));
 
     if constexpr (GAUSS) load_logf_table(logtab, a.logtab);
     if (warp == 0 && lane == 0) {
@@ -175,6 +189,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) skge3_tc_kernel(const __grid_co
             mbar_init(bar_empty(s), 1);
         }
         mbar_init(bar_accum, 1);
+        mbar_init(bar_raw_full, 1);
+        mbar_init(bar_raw_empty, GEN_WARPS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmY) : "memory");
     } else if (warp == 1) {
@@ -197,14 +213,25 @@ __global__ void __launch_bounds__(TC_THREADS, 1) skge3_tc_kernel(const __grid_co
     if (warp == 0) {
         if (lane == 0) {
             constexpr int PF = 6;
-            for (int it = 0; it < min(PF, nsteps); ++it) tma_prefetch_2d(&tmY, (s_begin + it) * BK, (int) j0);
-            for (int it = 0; it < nsteps; ++it) {
-                const int st = it % STAGES;
-                const uint32_t ph = (it / STAGES) & 1;
-                if (it + PF < nsteps) tma_prefetch_2d(&tmY, (s_begin + it + PF) * BK, (int) j0);
-                mbar_wait(bar_empty(st), ph ^ 1);
-                mbar_arrive_expect_tx(bar_full(st), Y_BYTES);
-                tma_load_2d(base + st * STAGE_BYTES + 2 * X_BYTES, &tmY, bar_full(st), (s_begin + it) * BK, (int) j0);
+            if (!a.y_mn) {
+                for (int it = 0; it < min(PF, nsteps); ++it) tma_prefetch_2d(&tmY, (s_begin + it) * BK, (int) j0);
+                for (int it = 0; it < nsteps; ++it) {
+                    const int st = it % STAGES;
+                    const uint32_t ph = (it / STAGES) & 1;
+                    if (it + PF < nsteps) tma_prefetch_2d(&tmY, (s_begin + it + PF) * BK, (int) j0);
+                    mbar_wait(bar_empty(st), ph ^ 1);
+                    mbar_arrive_expect_tx(bar_full(st), Y_BYTES);
+                    tma_load_2d(base + st * STAGE_BYTES + 2 * X_BYTES, &tmY, bar_full(st), (s_begin + it) * BK, (int) j0);
+                }
+            } else {
+                // tensor map (Q, K), box 256 q x RAW_K k, no swizzle: one raw tile in flight
+                for (int j = 0; j < min(2 * PF, 2 * nsteps); ++j) tma_prefetch_2d(&tmY, (int) j0, s_begin * BK + j * RAW_K);
+                for (int j = 0; j < 2 * nsteps; ++j) {          // raw tile j = half (j & 1) of step j / 2
+                    if (j + 2 * PF < 2 * nsteps) tma_prefetch_2d(&tmY, (int) j0, s_begin * BK + (j + 2 * PF) * RAW_K);
+                    mbar_wait(bar_raw_empty, (uint32_t) ((j & 1) ^ 1));
+                    mbar_arrive_expect_tx(bar_raw_full, RAW_BYTES);
+                    tma_load_2d(base + RAW_OFFSET, &tmY, bar_raw_full, (int) j0, s_begin * BK + j * RAW_K);
+                }
             }
         }
     } else if (warp == 1) {
@@ -213,7 +240,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) skge3_tc_kernel(const __grid_co
                 const int st = it % STAGES;
                 const uint32_t ph = (it / STAGES) & 1;
                 mbar_wait(bar_ready(st), ph);
-                mbar_wait(bar_full(st), ph);
+                if (!a.y_mn) mbar_wait(bar_full(st), ph);
                 tc_fence_after();
                 const uint32_t xh = base + st * STAGE_BYTES, xl = xh + X_BYTES, yh = xl + X_BYTES, yl = yh + Y_BYTES;
 #pragma unroll
@@ -245,6 +272,33 @@ __global__ void __launch_bounds__(TC_THREADS, 1) skge3_tc_kernel(const __grid_co
             const uint32_t ph = (it / STAGES) & 1;
             uint8_t* stage = smem + st * STAGE_BYTES;
             mbar_wait(bar_empty(st), ph ^ 1);
+            if (a.y_mn) {
+                // transpose the raw Q-contiguous tile into the K-major swizzled Y (the tensor core truncates it to TF32
+                // itself) and Y_lo tiles of this stage, then hand the raw buffer back to the TMA producer
+                const uint8_t* rawt = smem + RAW_OFFSET;
+                uint8_t* yh = stage + 2 * X_BYTES;
+                uint8_t* yl = yh + Y_BYTES;
+#pragma unroll
+                for (int half = 0; half < BK / RAW_K; ++half) {
+                    mbar_wait(bar_raw_full, (uint32_t) half);          // raw tile 2 it + half: parity = half
+#pragma unroll
+                    for (int q4 = 0; q4 < (BN * RAW_K / 4) / (32 * GEN_WARPS); ++q4) {
+                        const int ch = gt + 32 * GEN_WARPS * q4;
+                        const int qq = ch & (BN - 1), kl = ch / BN;        // column of the tile, 4-deep k chunk of this half
+                        const float* src = reinterpret_cast<const float*>(rawt) + (4 * kl) * BN + qq;
+                        float4 y;
+                        y.x = src[0]; y.y = src[BN]; y.z = src[2 * BN]; y.w = src[3 * BN];
+                        float4 l;
+                        l.x = lo_trunc(y.x); l.y = lo_trunc(y.y); l.z = lo_trunc(y.z); l.w = lo_trunc(y.w);
+                        const int kc = kl + half * (RAW_K / 4);
+                        const uint32_t o = (uint32_t) qq * 128u + (uint32_t) ((kc ^ (qq & 7)) << 4);
+                        *reinterpret_cast<float4*>(yh + o) = y;
+                        *reinterpret_cast<float4*>(yl + o) = l;
+                    }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_raw_empty);
+                }
+            }
 #pragma unroll
             for (int rr = 0; rr < X_PER_THREAD; ++rr) {
                 const uint64_t lo = seed_lo + off[rr];
@@ -267,6 +321,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) skge3_tc_kernel(const __grid_co
                 *reinterpret_cast<float4*>(stage + xoff + rr * (ROWS_PER_PASS * 128)) = h;
                 *reinterpret_cast<float4*>(stage + X_BYTES + xoff + rr * (ROWS_PER_PASS * 128)) = l;
             }
+            if (!a.y_mn) {
             mbar_wait(bar_full(st), ph);
             const uint8_t* ysrc = stage + 2 * X_BYTES;
             uint8_t* ydst = stage + 2 * X_BYTES + Y_BYTES;
@@ -277,6 +332,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) skge3_tc_kernel(const __grid_co
                 float4 l;
                 l.x = lo_trunc(y.x); l.y = lo_trunc(y.y); l.z = lo_trunc(y.z); l.w = lo_trunc(y.w);
                 *reinterpret_cast<float4*>(ydst + o) = l;
+            }
             }
             fence_proxy_async();
             __syncwarp();
@@ -369,10 +425,13 @@ int launch_dense_tc_f32(const DenseProblem<float>& p, cudaStream_t st) {
     if (p.S_buff != nullptr) return -1;
     if (p.family == 'G' && !p.gen.logtab) return -1;
     if (!(p.uk == 1 && p.vi == 1)) return -1;                 // Philox blocks must run along K
-    if (p.yrs != 1) return -1;                                // Y must be K-contiguous
+    // Y K-contiguous, or Q-contiguous (left sketch of RowMajor data, right sketch of ColMajor data)
+    const bool y_mn = (p.yrs != 1);
+    if (y_mn && p.ycs != 1) return -1;
+    if (y_mn && get_option("dense_path") == 3) return -1;     // experiment switch: Q-contiguous data to the generic kernel
     if (p.K < 64 || p.P < 1 || p.Q < 1) return -1;
-    if (p.Q > 0x7fffffffLL || p.K > 0x7fffff00LL) return -1;
-    if ((reinterpret_cast<uintptr_t>(p.Y) & 15) != 0 || (p.ycs & 3) != 0) return -1;   // TMA alignment rules
+    if (p.Q > 0x7fffff00LL || p.K > 0x7fffff00LL) return -1;
+    if ((reinterpret_cast<uintptr_t>(p.Y) & 15) != 0 || ((y_mn ? p.yrs : p.ycs) & 3) != 0) return -1;   // TMA alignment rules
     if ((int64_t) p.P * p.Q < 128 * 64 && p.K < 4096) return -1;                       // tiny: launch cost dominates
     EncodeTiledFn enc = encode_tiled();
     if (!enc) return -1;
@@ -402,13 +461,13 @@ int launch_dense_tc_f32(const DenseProblem<float>& p, cudaStream_t st) {
         if (splits > steps) splits = (int) steps;
     }
     CUtensorMap tm;
-    const cuuint64_t gdim[2] = {(cuuint64_t) p.K, (cuuint64_t) p.Q};
-    const cuuint64_t gstr[1] = {(cuuint64_t) p.ycs * 4ull};
-    const cuuint32_t box[2] = {BK, BN};
+    const cuuint64_t gdim[2] = {(cuuint64_t) (y_mn ? p.Q : p.K), (cuuint64_t) (y_mn ? p.K : p.Q)};
+    const cuuint64_t gstr[1] = {(cuuint64_t) (y_mn ? p.yrs : p.ycs) * 4ull};
+    const cuuint32_t box[2] = {(cuuint32_t) (y_mn ? BN : BK), (cuuint32_t) (y_mn ? RAW_K : BN)};
     const cuuint32_t estr[2] = {1, 1};
     CUresult cr = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(p.Y), gdim, gstr, box, estr,
-                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, y_mn ? CU_TENSOR_MAP_SWIZZLE_NONE : CU_TENSOR_MAP_SWIZZLE_128B,
+                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (cr != CUDA_SUCCESS) return -1;
 
     TcArgs a;
@@ -418,6 +477,7 @@ int launch_dense_tc_f32(const DenseProblem<float>& p, cudaStream_t st) {
     a.ublk0 = p.u0 >> 2;
     a.P = p.P; a.Q = p.Q;
     a.steps_total = (int) steps;
+    a.y_mn = y_mn ? 1 : 0;
     a.splits = splits;
     a.alpha = p.alpha; a.beta = p.beta;
     a.C = p.C; a.crs = p.crs; a.ccs = p.ccs;

@@ -663,6 +663,44 @@ def test_tensor_core_float_sketch_vs_oracle(gpu, port):
         assert np.array_equal(B1.reshape(n, d + 1)[:, d], B0.reshape(n, d + 1)[:, d])
 
 
+def test_tensor_core_float_sketch_mn_major_data_vs_oracle(gpu, port):
+    """The tcgen05 kernel with the data matrix as an MN-major operand (contiguous along the non-contracted
+    dimension): left sketch of RowMajor A and right sketch of ColMajor A (A * S, the range-finder call), ragged in all
+    dimensions, windows, both families, alpha/beta. The launch counter proves the tensor-core kernel is what ran."""
+    import randblas_b200 as rb
+    rng = np.random.default_rng(6)
+    ctr, key = ol.state_from_u64(1997)
+    dt = np.float32
+    # left, RowMajor: B(d x n) = S(d x m) A(m x n), A row-major with lda = n (multiple of 4)
+    for (d, n, m, Dr, Dc, ro, co, fam, alpha, beta) in [(128, 256, 4096, 128, 4096, 0, 0, "U", 1.0, 0.0),
+                                                         (200, 300, 5003, 210, 6000, 3, 6, "G", 0.5, -1.5),
+                                                         (64, 600, 777, 64, 800, 0, 8, "U", 1.0, 0.25)]:
+        lda = n + (4 - n % 4) % 4
+        A = rng.standard_normal(m * lda).astype(dt)
+        B0 = rng.standard_normal(d * (n + 1)).astype(dt)
+        B1, B2 = B0.copy(), B0.copy()
+        before = rb.counter("tensor_core_launches")
+        gpu.lskge3("R", "N", "N", d, n, m, dt(alpha), (Dr, Dc, fam, "L"), ctr, key, ro, co, A, lda, dt(beta), B1, n + 1)
+        assert rb.counter("tensor_core_launches") == before + 1, ("left RowMajor", d, n, m)
+        port.lskge3("R", "N", "N", d, n, m, dt(alpha), (Dr, Dc, fam, "L"), ctr, key, ro, co, A, lda, dt(beta), B2, n + 1)
+        assert relerr(B1, B2) < 1e-5, (("left RowMajor", d, n, m, ro, co, fam), relerr(B1, B2))
+        assert np.array_equal(B1.reshape(d, n + 1)[:, n], B0.reshape(d, n + 1)[:, n])
+    # right, ColMajor: B(m x d) = A(m x n) S(n x d), S tall with Axis::Long (blocks run along n = K)
+    for (m, d, n, Dr, Dc, ro, co, fam, alpha, beta) in [(4096, 128, 2048, 2048, 128, 0, 0, "G", 1.0, 0.0),
+                                                         (3001, 100, 1777, 1800, 120, 5, 3, "U", -0.5, 2.0),
+                                                         (500, 300, 4100, 4100, 300, 0, 0, "U", 1.0, 0.0)]:
+        lda = m + (4 - m % 4) % 4
+        A = rng.standard_normal(n * lda).astype(dt)
+        B0 = rng.standard_normal(d * (m + 3)).astype(dt)
+        B1, B2 = B0.copy(), B0.copy()
+        before = rb.counter("tensor_core_launches")
+        gpu.rskge3("C", "N", "N", m, d, n, dt(alpha), A, lda, (Dr, Dc, fam, "L"), ctr, key, ro, co, dt(beta), B1, m + 3)
+        assert rb.counter("tensor_core_launches") == before + 1, ("right ColMajor", m, d, n)
+        port.rskge3("C", "N", "N", m, d, n, dt(alpha), A, lda, (Dr, Dc, fam, "L"), ctr, key, ro, co, dt(beta), B2, m + 3)
+        assert relerr(B1, B2) < 1e-5, (("right ColMajor", m, d, n, ro, co, fam), relerr(B1, B2))
+        assert np.array_equal(B1.reshape(d, m + 3)[:, m:], B0.reshape(d, m + 3)[:, m:])
+
+
 def test_edge_cases_beta_zero_overwrites_nan_and_empty_dimensions(gpu):
     """BLAS semantics the reference inherits (blas::gemm; util.hh:55-62 safe_scal): beta == 0 overwrites B without
     reading it (NaNs in B must not survive), alpha == 0 and m == 0 leave beta * B, zero-sized outputs are no-ops.
