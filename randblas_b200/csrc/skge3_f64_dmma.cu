@@ -38,6 +38,8 @@ constexpr int D_STAGES = 3;
 constexpr int D_WM = 2, D_WN = 4;                             // warp grid
 constexpr int D_MI = DM / (D_WM * 8), D_NI = DN / (D_WN * 8);   // DMMA tiles per warp: 8 x 4 (64 x 32 elements)
 constexpr int D_GR = DM / (D_THREADS / 4);                    // rows of the S tile generated per thread and step
+constexpr int DLQ = DN + 4;                                   // row length of a Q-contiguous Y tile [k][q] (conflict-free fragments)
+static_assert(DK * DLQ <= DN * DLD, "the Q-contiguous tile reuses the Y stage");
 
 struct DmmaArgs {
     Ctr128 ctr;
@@ -49,7 +51,7 @@ struct DmmaArgs {
     int steps_total, splits;
     double alpha, beta;
     const double* Y;
-    int64_t ycs;          // column stride of Y in elements (rows are contiguous: yrs == 1)
+    int64_t ycs;          // column stride of Y in elements when rows are contiguous (yrs == 1), else the ROW stride (YMN)
     double* C;
     int64_t crs, ccs;
     double* W;            // split-K workspace W[split][j][i] (i fastest, ld = P_pad) or null
@@ -66,7 +68,9 @@ __device__ __forceinline__ void cp_async16(void* dst, const void* src, int src_b
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(src_bytes) : "memory");
 }
 
-template <bool GAUSS>
+// YMN: Y is contiguous along Q (left sketch of RowMajor data, right sketch of ColMajor data); the tile is staged as
+// [k][q] and the B fragments are read across rows.
+template <bool GAUSS, bool YMN>
 __global__ void __launch_bounds__(D_THREADS, 1) skge3_dmma_kernel(const DmmaArgs a) {
     __shared__ __align__(16) double2 logtab[GAUSS ? LOGF_TABLE_ENTRIES : 1];
     extern __shared__ __align__(16) double dsm[];
@@ -118,15 +122,28 @@ __global__ void __launch_bounds__(D_THREADS, 1) skge3_dmma_kernel(const DmmaArgs
 #pragma unroll
         for (int q = 0; q < (DN * DK / 2) / D_THREADS; ++q) {
             const int ch = tid + D_THREADS * q;
-            const int jj = ch >> 3, kc = (ch & 7) * 2;
-            double* dst = Ys + ((size_t) buf * DN + jj) * DLD + kc;
-            const int64_t j = j0 + jj, k = k0 + kc;
-            if (j < a.Q && k + 1 < a.K) {
-                cp_async16(dst, a.Y + j * a.ycs + k, 16);
+            if constexpr (!YMN) {
+                const int jj = ch >> 3, kc = (ch & 7) * 2;
+                double* dst = Ys + ((size_t) buf * DN + jj) * DLD + kc;
+                const int64_t j = j0 + jj, k = k0 + kc;
+                if (j < a.Q && k + 1 < a.K) {
+                    cp_async16(dst, a.Y + j * a.ycs + k, 16);
+                } else {
+                    double y0 = 0.0, y1 = 0.0;
+                    if (j < a.Q && k < a.K) y0 = a.Y[j * a.ycs + k];
+                    dst[0] = y0; dst[1] = y1;
+                }
             } else {
-                double y0 = 0.0, y1 = 0.0;
-                if (j < a.Q && k < a.K) y0 = a.Y[j * a.ycs + k];
-                dst[0] = y0; dst[1] = y1;
+                const int kk = ch / (DN / 2), jc = (ch % (DN / 2)) * 2;     // k-row of the tile, pair of columns
+                double* dst = Ys + (size_t) buf * DN * DLD + kk * DLQ + jc;
+                const int64_t j = j0 + jc, k = k0 + kk;
+                if (k < a.K && j + 1 < a.Q) {
+                    cp_async16(dst, a.Y + k * a.ycs + j, 16);
+                } else {
+                    double y0 = 0.0, y1 = 0.0;
+                    if (k < a.K && j < a.Q) y0 = a.Y[k * a.ycs + j];
+                    dst[0] = y0; dst[1] = y1;
+                }
             }
         }
         // the stage's full barrier gets one more arrival when this thread's copies have landed
@@ -163,14 +180,15 @@ __global__ void __launch_bounds__(D_THREADS, 1) skge3_dmma_kernel(const DmmaArgs
         const int buf = step % D_STAGES;
         tma::mbar_wait(bar_full + 8u * (uint32_t) buf, (uint32_t) ((step / D_STAGES) & 1));
         const double* xb = Xs + ((size_t) buf * DM + wi * (D_MI * 8) + g) * DLD + t4;
-        const double* yb = Ys + ((size_t) buf * DN + wj * (D_NI * 8) + g) * DLD + t4;
+        const double* yb = YMN ? Ys + (size_t) buf * DN * DLD + t4 * DLQ + wj * (D_NI * 8) + g
+                               : Ys + ((size_t) buf * DN + wj * (D_NI * 8) + g) * DLD + t4;
 #pragma unroll
         for (int k4 = 0; k4 < DK / 4; ++k4) {
             double af[D_MI], bf[D_NI];
 #pragma unroll
             for (int mi = 0; mi < D_MI; ++mi) af[mi] = xb[mi * 8 * DLD + k4 * 4];
 #pragma unroll
-            for (int ni = 0; ni < D_NI; ++ni) bf[ni] = yb[ni * 8 * DLD + k4 * 4];
+            for (int ni = 0; ni < D_NI; ++ni) bf[ni] = YMN ? yb[k4 * 4 * DLQ + ni * 8] : yb[ni * 8 * DLD + k4 * 4];
 #pragma unroll
             for (int mi = 0; mi < D_MI; ++mi)
 #pragma unroll
@@ -240,9 +258,12 @@ int launch_dense_dmma_f64(const DenseProblem<double>& p, cudaStream_t st) {
     if (p.S_buff != nullptr) return -1;
     if (p.family == 'G' && !p.gen.logtab) return -1;
     if (!(p.uk == 1 && p.vi == 1)) return -1;                 // Philox blocks must run along K
-    if (p.yrs != 1) return -1;                                // Y must be K-contiguous
+    // Y K-contiguous, or Q-contiguous (left sketch of RowMajor data, right sketch of ColMajor data)
+    const bool y_mn = (p.yrs != 1);
+    if (y_mn && p.ycs != 1) return -1;
+    if (y_mn && get_option("dense_path") == 3) return -1;     // experiment switch: Q-contiguous data to the generic kernel
     if (p.K < 32 || p.P < 1 || p.Q < 1) return -1;
-    if ((reinterpret_cast<uintptr_t>(p.Y) & 15) != 0 || (p.ycs & 1) != 0) return -1;   // 16-byte cp.async
+    if ((reinterpret_cast<uintptr_t>(p.Y) & 15) != 0 || ((y_mn ? p.yrs : p.ycs) & 1) != 0) return -1;   // 16-byte cp.async
     if ((int64_t) p.P * p.Q < 64 * 64 && p.K < 4096) return -1;
     const int64_t tiles_p = (p.P + DM - 1) / DM, tiles_q = (p.Q + DN - 1) / DN;
     if (tiles_p > 65535 || tiles_q > 0x7fffffff) return -1;
@@ -274,7 +295,7 @@ int launch_dense_dmma_f64(const DenseProblem<double>& p, cudaStream_t st) {
     a.P = p.P; a.Q = p.Q; a.K = p.K;
     a.steps_total = (int) steps; a.splits = splits;
     a.alpha = p.alpha; a.beta = p.beta;
-    a.Y = p.Y; a.ycs = p.ycs;
+    a.Y = p.Y; a.ycs = y_mn ? p.yrs : p.ycs;
     a.C = p.C; a.crs = p.crs; a.ccs = p.ccs;
     a.P_pad = tiles_p * DM; a.Q_pad = tiles_q * DN;
     a.W = nullptr;
@@ -283,17 +304,24 @@ int launch_dense_dmma_f64(const DenseProblem<double>& p, cudaStream_t st) {
         if (!a.W) return fail_cuda(cudaErrorMemoryAllocation, "split-K workspace");
     }
     constexpr size_t smem = (size_t) D_STAGES * (DM + DN) * DLD * sizeof(double);
-    static bool attr_done[2] = {false, false};
     const bool gauss = p.family == 'G';
-    if (!attr_done[gauss]) {
-        cudaError_t e = gauss ? cudaFuncSetAttribute(skge3_dmma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)
-                              : cudaFuncSetAttribute(skge3_dmma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
-        if (e != cudaSuccess) { cudaGetLastError(); return -1; }
-        attr_done[gauss] = true;
-    }
     dim3 grid((unsigned) tiles_q, (unsigned) tiles_p, (unsigned) splits);
-    if (gauss) skge3_dmma_kernel<true><<<grid, D_THREADS, smem, st>>>(a);
-    else skge3_dmma_kernel<false><<<grid, D_THREADS, smem, st>>>(a);
+    auto launch = [&](auto kern, bool& attr_done) -> int {
+        if (!attr_done) {
+            if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem) != cudaSuccess) {
+                cudaGetLastError();
+                return -1;
+            }
+            attr_done = true;
+        }
+        kern<<<grid, D_THREADS, smem, st>>>(a);
+        return 0;
+    };
+    static bool attr_done[4] = {false, false, false, false};
+    int lrc;
+    if (gauss) lrc = y_mn ? launch(skge3_dmma_kernel<true, true>, attr_done[3]) : launch(skge3_dmma_kernel<true, false>, attr_done[2]);
+    else lrc = y_mn ? launch(skge3_dmma_kernel<false, true>, attr_done[1]) : launch(skge3_dmma_kernel<false, false>, attr_done[0]);
+    if (lrc) return -1;
     count_launch();
     count_tc_launch();
     RB_CUDA(cudaGetLastError());

@@ -701,6 +701,40 @@ def test_tensor_core_float_sketch_mn_major_data_vs_oracle(gpu, port):
         assert np.array_equal(B1.reshape(d, m + 3)[:, m:], B0.reshape(d, m + 3)[:, m:])
 
 
+def test_dmma_double_sketch_q_contiguous_data_vs_oracle(gpu, port):
+    """The DMMA kernel (skge3_f64_dmma.cu) with data contiguous along the non-contracted dimension: left sketch of
+    RowMajor A and right sketch of ColMajor A, ragged shapes, windows with Philox-block straddling, alpha/beta."""
+    import randblas_b200 as rb
+    rng = np.random.default_rng(8)
+    ctr, key = ol.state_from_u64(1997)
+    dt = np.float64
+    for (d, n, m, Dr, Dc, ro, co, fam, alpha, beta) in [(128, 256, 2048, 128, 2048, 0, 0, "U", 1.0, 0.0),
+                                                         (200, 150, 1503, 210, 3000, 3, 6, "G", 0.5, -1.5),
+                                                         (70, 130, 777, 80, 800, 1, 9, "U", 1.0, 0.25)]:
+        lda = n + (n % 2)
+        A = rng.standard_normal(m * lda)
+        B0 = rng.standard_normal(d * (n + 1))
+        B1, B2 = B0.copy(), B0.copy()
+        before = rb.counter("tensor_core_launches")
+        gpu.lskge3("R", "N", "N", d, n, m, dt(alpha), (Dr, Dc, fam, "L"), ctr, key, ro, co, A, lda, dt(beta), B1, n + 1)
+        assert rb.counter("tensor_core_launches") == before + 1, ("left RowMajor", d, n, m)
+        port.lskge3("R", "N", "N", d, n, m, dt(alpha), (Dr, Dc, fam, "L"), ctr, key, ro, co, A, lda, dt(beta), B2, n + 1)
+        assert relerr(B1, B2) < 1e-12, (("left RowMajor", d, n, m, ro, co, fam), relerr(B1, B2))
+        assert np.array_equal(B1.reshape(d, n + 1)[:, n], B0.reshape(d, n + 1)[:, n])
+    for (m, d, n, Dr, Dc, ro, co, fam, alpha, beta) in [(2048, 128, 1024, 1024, 128, 0, 0, "G", 1.0, 0.0),
+                                                         (1501, 100, 977, 1000, 120, 5, 3, "U", -0.5, 2.0)]:
+        lda = m + (m % 2)
+        A = rng.standard_normal(n * lda)
+        B0 = rng.standard_normal(d * (m + 3))
+        B1, B2 = B0.copy(), B0.copy()
+        before = rb.counter("tensor_core_launches")
+        gpu.rskge3("C", "N", "N", m, d, n, dt(alpha), A, lda, (Dr, Dc, fam, "L"), ctr, key, ro, co, dt(beta), B1, m + 3)
+        assert rb.counter("tensor_core_launches") == before + 1, ("right ColMajor", m, d, n)
+        port.rskge3("C", "N", "N", m, d, n, dt(alpha), A, lda, (Dr, Dc, fam, "L"), ctr, key, ro, co, dt(beta), B2, m + 3)
+        assert relerr(B1, B2) < 1e-12, (("right ColMajor", m, d, n, ro, co, fam), relerr(B1, B2))
+        assert np.array_equal(B1.reshape(d, m + 3)[:, m:], B0.reshape(d, m + 3)[:, m:])
+
+
 def test_edge_cases_beta_zero_overwrites_nan_and_empty_dimensions(gpu):
     """BLAS semantics the reference inherits (blas::gemm; util.hh:55-62 safe_scal): beta == 0 overwrites B without
     reading it (NaNs in B must not survive), alpha == 0 and m == 0 leave beta * B, zero-sized outputs are no-ops.
