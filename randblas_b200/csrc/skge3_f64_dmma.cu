@@ -8,13 +8,13 @@
 // to fill the SMs.
 //
 // Canonical problem (kernels.h): C(P x Q) = alpha * X(P x K) * Y(K x Q) + beta * C, X = op(S window).
-// CTA tile 128 x 128, 8 warps as 2 x 4, warp tile 64 x 32 = 8 x 4 DMMA tiles (64 accumulator doubles per
-// thread), K step 16. (16 warps with 32 x 32 warp tiles -- D_THREADS 512, D_WM 4 -- measured the same: the DMMA
-// pipe stays ~70% busy with two or four warps per scheduler.) Per step every thread
+// CTA tile 64 x 256 (Q > 128) or 128 x 128, 8 warps, warp tile 64 x 32 = 8 x 4 DMMA tiles (64 accumulator doubles
+// per thread), K step 16 (see DmmaTile below for why the wide tile). 16 warps with 32 x 32 warp tiles measured the
+// same as 8: the DMMA pipe does not get busier with four warps per scheduler than with two. Per step every thread
 //   * issues the 16-byte cp.async copies of the next Y tile (columns of A are K-contiguous: ColMajor A),
 //   * runs the 128 DMMAs of the current tile from shared memory (rows padded to 20 doubles: conflict-free
 //     8-byte fragment loads),
-//   * regenerates its share (2 Philox blocks = 8 samples) of the next 128 x 16 tile of S from
+//   * regenerates its share (1 or 2 Philox blocks) of the next DM x 16 tile of S from
 //     (key, counter, ro_s, co_s) -- Philox4x32-10, uneg11 or Box-Muller in float exactly as fill_dense, promoted
 //     to double; S never touches HBM.
 // Three shared-memory stages and mbarriers (full[]: one arrival per thread + one per thread's cp.async completions,
@@ -32,14 +32,24 @@ namespace rb {
 
 namespace {
 
-constexpr int DM = 128, DN = 128, DK = 16, DLD = DK + 4;     // DLD: padded row length in doubles
+constexpr int DK = 16, DLD = DK + 4;                         // K step; padded row length in doubles
 constexpr int D_THREADS = 256;
 constexpr int D_STAGES = 3;
-constexpr int D_WM = 2, D_WN = 4;                             // warp grid
-constexpr int D_MI = DM / (D_WM * 8), D_NI = DN / (D_WN * 8);   // DMMA tiles per warp: 8 x 4 (64 x 32 elements)
-constexpr int D_GR = DM / (D_THREADS / 4);                    // rows of the S tile generated per thread and step
-constexpr int DLQ = DN + 4;                                   // row length of a Q-contiguous Y tile [k][q] (conflict-free fragments)
-static_assert(DK * DLQ <= DN * DLD, "the Q-contiguous tile reuses the Y stage");
+// Two CTA tiles, both with 8 warps of 64 x 32 (8 x 4 DMMA tiles, 64 accumulator doubles per thread):
+//   64 x 256 (warps 1 x 8): half the operator rows per column of C, i.e. half the generation work per flop -- the
+//             Gaussian operator costs 13% of the kernel at 128 x 128 and 4% here (C3: 81.3 -> 72.9 ms);
+//   128 x 128 (warps 2 x 4): for Q <= 128, where the wide tile would be half empty.
+template <int DM_, int DN_, int WM_, int WN_>
+struct DmmaTile {
+    static constexpr int DM = DM_, DN = DN_, D_WM = WM_, D_WN = WN_;
+    static constexpr int D_MI = DM / (D_WM * 8), D_NI = DN / (D_WN * 8);
+    static constexpr int D_GR = DM / (D_THREADS / 4);        // rows of the S tile generated per thread and step
+    static constexpr int DLQ = DN + 4;                       // row length of a Q-contiguous Y tile [k][q] (conflict-free fragments)
+    static constexpr size_t smem = (size_t) D_STAGES * (DM + DN) * DLD * sizeof(double);
+    static_assert(D_WM * D_WN * 32 == D_THREADS && D_GR >= 1 && DK * DLQ <= DN * DLD, "tile configuration");
+};
+using TileWide = DmmaTile<64, 256, 1, 8>;
+using TileSquare = DmmaTile<128, 128, 2, 4>;
 
 struct DmmaArgs {
     Ctr128 ctr;
@@ -70,8 +80,10 @@ __device__ __forceinline__ void cp_async16(void* dst, const void* src, int src_b
 
 // YMN: Y is contiguous along Q (left sketch of RowMajor data, right sketch of ColMajor data); the tile is staged as
 // [k][q] and the B fragments are read across rows.
-template <bool GAUSS, bool YMN>
+template <bool GAUSS, bool YMN, class TILE>
 __global__ void __launch_bounds__(D_THREADS, 1) skge3_dmma_kernel(const DmmaArgs a) {
+    constexpr int DM = TILE::DM, DN = TILE::DN, D_WN = TILE::D_WN, D_MI = TILE::D_MI, D_NI = TILE::D_NI, D_GR = TILE::D_GR,
+                  DLQ = TILE::DLQ;
     __shared__ __align__(16) double2 logtab[GAUSS ? LOGF_TABLE_ENTRIES : 1];
     extern __shared__ __align__(16) double dsm[];
     double* Xs = dsm;                              // [D_STAGES][DM][DLD]
@@ -201,7 +213,7 @@ __global__ void __launch_bounds__(D_THREADS, 1) skge3_dmma_kernel(const DmmaArgs
     // warps of a scheduler (warp w and w + 4)
     if (nsteps > 0) produce(0);
     if (nsteps > 1) produce(1);
-    if ((wi & 1) == 0) {
+    if (((warp >> 2) & 1) == 0) {
         for (int step = 0; step < nsteps; ++step) {
             consume(step);
             if (step + 2 < nsteps) produce(step + 2);
@@ -265,6 +277,8 @@ int launch_dense_dmma_f64(const DenseProblem<double>& p, cudaStream_t st) {
     if (p.K < 32 || p.P < 1 || p.Q < 1) return -1;
     if ((reinterpret_cast<uintptr_t>(p.Y) & 15) != 0 || ((y_mn ? p.yrs : p.ycs) & 1) != 0) return -1;   // 16-byte cp.async
     if ((int64_t) p.P * p.Q < 64 * 64 && p.K < 4096) return -1;
+    const bool wide = p.Q > 128;
+    const int DM = wide ? TileWide::DM : TileSquare::DM, DN = wide ? TileWide::DN : TileSquare::DN;
     const int64_t tiles_p = (p.P + DM - 1) / DM, tiles_q = (p.Q + DN - 1) / DN;
     if (tiles_p > 65535 || tiles_q > 0x7fffffff) return -1;
     const int64_t steps = (p.K + DK - 1) / DK;
@@ -303,7 +317,7 @@ int launch_dense_dmma_f64(const DenseProblem<double>& p, cudaStream_t st) {
         a.W = (double*) workspace(6, (size_t) splits * a.P_pad * a.Q_pad * sizeof(double));
         if (!a.W) return fail_cuda(cudaErrorMemoryAllocation, "split-K workspace");
     }
-    constexpr size_t smem = (size_t) D_STAGES * (DM + DN) * DLD * sizeof(double);
+    const size_t smem = wide ? TileWide::smem : TileSquare::smem;
     const bool gauss = p.family == 'G';
     dim3 grid((unsigned) tiles_q, (unsigned) tiles_p, (unsigned) splits);
     auto launch = [&](auto kern, bool& attr_done) -> int {
@@ -317,10 +331,15 @@ int launch_dense_dmma_f64(const DenseProblem<double>& p, cudaStream_t st) {
         kern<<<grid, D_THREADS, smem, st>>>(a);
         return 0;
     };
-    static bool attr_done[4] = {false, false, false, false};
+    static bool attr_done[8] = {false, false, false, false, false, false, false, false};
     int lrc;
-    if (gauss) lrc = y_mn ? launch(skge3_dmma_kernel<true, true>, attr_done[3]) : launch(skge3_dmma_kernel<true, false>, attr_done[2]);
-    else lrc = y_mn ? launch(skge3_dmma_kernel<false, true>, attr_done[1]) : launch(skge3_dmma_kernel<false, false>, attr_done[0]);
+    if (wide) {
+        if (gauss) lrc = y_mn ? launch(skge3_dmma_kernel<true, true, TileWide>, attr_done[7]) : launch(skge3_dmma_kernel<true, false, TileWide>, attr_done[6]);
+        else lrc = y_mn ? launch(skge3_dmma_kernel<false, true, TileWide>, attr_done[5]) : launch(skge3_dmma_kernel<false, false, TileWide>, attr_done[4]);
+    } else {
+        if (gauss) lrc = y_mn ? launch(skge3_dmma_kernel<true, true, TileSquare>, attr_done[3]) : launch(skge3_dmma_kernel<true, false, TileSquare>, attr_done[2]);
+        else lrc = y_mn ? launch(skge3_dmma_kernel<false, true, TileSquare>, attr_done[1]) : launch(skge3_dmma_kernel<false, false, TileSquare>, attr_done[0]);
+    }
     if (lrc) return -1;
     count_launch();
     count_tc_launch();
