@@ -280,6 +280,26 @@ class C4SasoApply(Workload):
                 "peak_source": pk["source"],
                 "algorithmic_bytes_per_launch": self.m * self.n * 4}
 
+    def extra(self, pk):
+        """fill_sparse alone, int64 COO arrays written to HBM."""
+        torch = self.torch
+        Sf = self.rb.SparseSkOp(self.rb.SparseDist(self.d, self.m, self.k), self.rb.RNGState(1997), dtype=np.float32)
+        self.rb.fill_sparse(Sf)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(3):
+            self.rb.fill_sparse(Sf)
+        b.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b) / 3
+        nnz = self.k * self.m
+        gbs = nnz * 20 / 1e9 / (ms / 1e3)
+        del Sf
+        return {"fill_sparse": {"ms": ms, "nnz": nnz, "Mnnz_per_s": nnz / ms / 1e3, "bytes_written": nnz * 20,
+                                "achieved_GBs": gbs, "frac_hbm": gbs / pk["hbm_gbs"],
+                                "kernel": "saso_fill_warp_kernel<int64, float>"}}
+
     def e2e_setup(self):
         torch = self.torch
         self.e2e_m = 1000000
@@ -631,6 +651,8 @@ def main():
                            "sharding": "independent shards per rank" + (" + NCCL reduce-scatter" if args.workload == "c3" else ", no collective")},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu,
                 "kernel_ms": float(np.mean(kms))}
+        if hasattr(wl, "extra"):
+            line["extra"] = wl.extra(pk)
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -187,8 +187,9 @@ __global__ void __launch_bounds__(256) spdata_kgroup_kernel(const SpDataProblem<
                     int my_q = -1;
                     T my_a = (T) 0;
                     if (eb + lane < e[kk + 1]) {
-                        const int64_t q = (int64_t) qidx[eb + lane] - q_off;
-                        if (q >= 0 && q < p.Q) { my_q = (int) q; my_a = p.alpha * vals[eb + lane]; }
+                        // streamed once per slab: evict-first, so that the slab of C stays resident in L2
+                        const int64_t q = (int64_t) __ldcs(qidx + eb + lane) - q_off;
+                        if (q >= 0 && q < p.Q) { my_q = (int) q; my_a = p.alpha * __ldcs(vals + eb + lane); }
                     }
                     const int cnt = (int) min((int64_t) 32, e[kk + 1] - eb);
                     for (int t = 0; t < cnt; ++t) {
