@@ -94,6 +94,39 @@ __global__ void __launch_bounds__(256) saso_fill_warp_kernel(Ctr128 ctr, PhiloxK
     }
 }
 
+// k <= 32 and dim_major < 2^31: G = 2^ceil(log2 k) lanes per vector, 32 / G vectors per warp (the warp-per-vector
+// kernel above keeps 32 - k lanes idle: 75% of them at vec_nnz = 8). Lane (vector, j) writes entry vector * k + j
+// directly: consecutive lanes hit consecutive addresses, so the stores are coalesced without staging.
+template <typename IDX, typename VAL, int G>
+__global__ void __launch_bounds__(256) saso_fill_group_kernel(Ctr128 ctr, PhiloxKey key, int k, uint32_t dim_major,
+                                                              int64_t dim_minor, IDX* __restrict__ maj,
+                                                              IDX* __restrict__ mnr, VAL* __restrict__ vals) {
+    constexpr int VPW = 32 / G;
+    const int lane = threadIdx.x & 31, sub = lane & (G - 1);
+    const int64_t warp = ((int64_t) blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t) gridDim.x * blockDim.x) >> 5;
+    for (int64_t wv = warp * VPW; wv < dim_minor; wv += nwarps * VPW) {
+        const int64_t v = wv + lane / G;
+        const bool live = v < dim_minor && sub < k;
+        uint32_t piv = 0, w1 = 0;
+        if (live) {
+            const uint4 w = philox4x32_10(ctr_add(ctr, (uint64_t) (v * k + sub)), key);
+            piv = (uint32_t) sub + w.x % (dim_major - (uint32_t) sub);      // sparse_skops.hh:78
+            w1 = w.y;
+        }
+        // value at position piv after swaps 0..sub-1 of an identity permutation: walk the swaps backwards
+        uint32_t pos = piv;
+        for (int t = k - 2; t >= 0; --t) {
+            const uint32_t pt = __shfl_sync(0xffffffffu, piv, t, G);
+            if (t < sub) {
+                if (pos == (uint32_t) t) pos = pt;
+                else if (pos == pt) pos = (uint32_t) t;
+            }
+        }
+        if (live) put_entry<IDX, VAL>(maj, mnr, vals, v * k + sub, (int64_t) pos, v, (int) (w1 & 1u));
+    }
+}
+
 // any k: thread per vector, pivots in global scratch (k entries per thread of the grid)
 template <typename IDX, typename VAL>
 __global__ void saso_fill_thread_kernel(Ctr128 ctr, PhiloxKey key, int64_t k, int64_t dim_major, int64_t dim_minor,
@@ -114,7 +147,24 @@ __global__ void saso_fill_thread_kernel(Ctr128 ctr, PhiloxKey key, int64_t k, in
 template <typename IDX, typename VAL>
 int launch_saso_t(Ctr128 ctr, PhiloxKey key, int64_t k, int64_t dim_major, int64_t dim_minor, void* maj, void* mnr,
                   void* vals, cudaStream_t st) {
-    if (k <= 32) {
+    if (k <= 32 && dim_major < 0x7fffffffLL && get_option("saso_fill_path") == 0) {
+        const int G = k <= 1 ? 1 : k <= 2 ? 2 : k <= 4 ? 4 : k <= 8 ? 8 : k <= 16 ? 16 : 32;
+        const int64_t vpb = 8 * (32 / G);                      // vectors per 256-thread CTA and iteration
+        int64_t grid = (dim_minor + vpb - 1) / vpb;
+        const int64_t cap = (int64_t) sm_count() * 16;
+        if (grid > cap) grid = cap;
+#define RB_SASO_GROUP(GG) saso_fill_group_kernel<IDX, VAL, GG><<<(unsigned) grid, 256, 0, st>>>(                       \
+            ctr, key, (int) k, (uint32_t) dim_major, dim_minor, (IDX*) maj, (IDX*) mnr, (VAL*) vals)
+        switch (G) {
+            case 1: RB_SASO_GROUP(1); break;
+            case 2: RB_SASO_GROUP(2); break;
+            case 4: RB_SASO_GROUP(4); break;
+            case 8: RB_SASO_GROUP(8); break;
+            case 16: RB_SASO_GROUP(16); break;
+            default: RB_SASO_GROUP(32); break;
+        }
+#undef RB_SASO_GROUP
+    } else if (k <= 32) {
         int64_t grid = (dim_minor + 63) / 64;
         int64_t cap = (int64_t) sm_count() * 8;
         if (grid > cap) grid = cap;

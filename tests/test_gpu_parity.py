@@ -223,16 +223,22 @@ def test_saso_goldens(gpu, gold):
 
 def test_saso_sweep_vs_oracle(gpu, port):
     rng = np.random.default_rng(2)
+    import randblas_b200 as rb
     shapes = [(7, 20, 3), (20, 7, 7), (1, 9, 1), (64, 64, 64), (40, 1000, 33), (2048, 20000, 8), (300, 5, 5),
-              (100, 100000, 32), (33, 50, 1)]
-    for (r, c, k) in shapes:
-        ctr, key = ol.state_from_u64(int(rng.integers(0, 1 << 62)))
-        ctr = ol.ctr_add(ctr, (1 << 32) - 7)
-        for idt in (np.int32, np.int64):
-            a = gpu.fill_sparse(r, c, k, "S", ctr, key, np.float32, idt)
-            b = port.fill_sparse(r, c, k, "S", ctr, key, np.float32, idt)
-            for x, y in zip(a, b):
-                assert np.array_equal(x, y), (r, c, k)
+              (100, 100000, 32), (33, 50, 1), (50, 400, 16), (9, 300, 2), (20, 3000, 11)]
+    try:
+        for path in (0, 1):     # 0: sub-warp groups (saso_fill_group_kernel), 1: warp per vector
+            rb.set_option("saso_fill_path", path)
+            for (r, c, k) in shapes:
+                ctr, key = ol.state_from_u64(int(rng.integers(0, 1 << 62)))
+                ctr = ol.ctr_add(ctr, (1 << 32) - 7)
+                for idt in (np.int32, np.int64):
+                    a = gpu.fill_sparse(r, c, k, "S", ctr, key, np.float32, idt)
+                    b = port.fill_sparse(r, c, k, "S", ctr, key, np.float32, idt)
+                    for x, y in zip(a, b):
+                        assert np.array_equal(x, y), (path, r, c, k)
+    finally:
+        rb.set_option("saso_fill_path", 0)
     # every short-axis vector holds vec_nnz distinct indices (test_sparseskop.cc:64-117)
     vals, rows, cols, nnz, _ = gpu.fill_sparse(2048, 50000, 8, "S", *ol.state_from_u64(1), np.float32, np.int64)
     rr = rows.reshape(-1, 8)
