@@ -59,6 +59,19 @@ RB_DEF_T(float, f32)
 RB_DEF_T(double, f64)
 #undef RB_DEF_T
 
+inline int spmm_c(int left, int fmt, char l, char oA, char oB, int64_t d, int64_t n, int64_t m, float alpha, int64_t ar,
+                  int64_t ac, int64_t nnz, const float* vals, const void* i0, const void* i1, int ib, int64_t ro,
+                  int64_t co, const float* B, int64_t ldb, float beta, float* C, int64_t ldc) {
+    return rb_spmm_f32(left, fmt, l, oA, oB, d, n, m, alpha, ar, ac, nnz, vals, i0, i1, ib, ro, co, B, ldb, beta, C, ldc,
+                       nullptr);
+}
+inline int spmm_c(int left, int fmt, char l, char oA, char oB, int64_t d, int64_t n, int64_t m, double alpha, int64_t ar,
+                  int64_t ac, int64_t nnz, const double* vals, const void* i0, const void* i1, int ib, int64_t ro,
+                  int64_t co, const double* B, int64_t ldb, double beta, double* C, int64_t ldc) {
+    return rb_spmm_f64(left, fmt, l, oA, oB, d, n, m, alpha, ar, ac, nnz, vals, i0, i1, ib, ro, co, B, ldb, beta, C, ldc,
+                       nullptr);
+}
+
 // device-pointer calls are stream-ordered; keep the reference's synchronous semantics
 inline void finish(int rc, const char* func) {
     check(rc, func);
@@ -179,5 +192,33 @@ inline void sketch_sparse(blas::Layout layout, blas::Op opA, blas::Op opS, int64
                                        m, alpha, S, ro_s, co_s, A, (int64_t) 0, (int64_t) 0, beta, B, ldb),
                      __func__);
 }
+
+// ======================================================================= sparse data times dense matrix
+namespace sparse_data {
+// spmm_dispatch.hh:52-178: C(d x n) = alpha * op(A_sp[ro_a:, co_a:]) * op(B) + beta * C
+template <typename SpMat, typename T = typename SpMat::scalar_t>
+inline void left_spmm(blas::Layout layout, blas::Op opA, blas::Op opB, int64_t d, int64_t n, int64_t m, T alpha,
+                      const SpMat& A, int64_t ro_a, int64_t co_a, const T* B, int64_t ldb, T beta, T* C, int64_t ldc) {
+    randblas_require(A.index_base == IndexBase::Zero);     // :92
+    int fmt; const void* i0; const void* i1;
+    internal::sp_arrays(A, fmt, i0, i1);
+    internal::finish(internal::spmm_c(1, fmt, internal::to_char(layout), internal::to_char(opA), internal::to_char(opB), d, n,
+                                      m, alpha, A.n_rows, A.n_cols, A.nnz, A.vals, i0, i1,
+                                      (int) sizeof(typename SpMat::index_t), ro_a, co_a, B, ldb, beta, C, ldc),
+                     __func__);
+}
+// spmm_dispatch.hh:180-219: C(m x d) = alpha * op(A) * op(B_sp[i_off:, j_off:]) + beta * C
+template <typename SpMat, typename T = typename SpMat::scalar_t>
+inline void right_spmm(blas::Layout layout, blas::Op opA, blas::Op opB, int64_t m, int64_t d, int64_t n, T alpha,
+                       const T* A, int64_t lda, const SpMat& B, int64_t i_off, int64_t j_off, T beta, T* C, int64_t ldc) {
+    randblas_require(B.index_base == IndexBase::Zero);
+    int fmt; const void* i0; const void* i1;
+    internal::sp_arrays(B, fmt, i0, i1);
+    internal::finish(internal::spmm_c(0, fmt, internal::to_char(layout), internal::to_char(opB), internal::to_char(opA), d, n,
+                                      m, alpha, B.n_rows, B.n_cols, B.nnz, B.vals, i0, i1,
+                                      (int) sizeof(typename SpMat::index_t), i_off, j_off, A, lda, beta, C, ldc),
+                     __func__);
+}
+}  // namespace sparse_data
 
 }  // namespace RandBLAS

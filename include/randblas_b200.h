@@ -152,6 +152,22 @@ int rb_coo_apply_f64(int side_left, char layout, char opS, char opA, int64_t d, 
                      const void* cols, int idx_bytes, int64_t ro_s, int64_t co_s, const double* A, int64_t lda,
                      double beta, double* B, int64_t ldb, void* stream);
 
+/* ---- sparse data matrix times dense matrix ----
+ * Replaces sparse_data::left_spmm / right_spmm (RandBLAS/sparse_data/spmm_dispatch.hh:52-219; the kernels in
+ * coo_spmm_impl.hh, csr_spmm_impl.hh, csc_spmm_impl.hh), the public entry points RandLAPACK calls on sparse data.
+ *   side_left = 1: C(d x n) = alpha * op(A_sp[ro_a:, co_a:])(d x m) * op(B)(m x n) + beta * C      (left_spmm)
+ *   side_left = 0: C(m x d) = alpha * op(B)(m x n) * op(A_sp[ro_a:, co_a:])(n x d) + beta * C      (right_spmm)
+ * fmt: 0 CSR (idx0 = rowptr, idx1 = colidxs), 1 CSC (idx0 = rowidxs, idx1 = colptr), 2 COO (idx0 = rows, idx1 = cols).
+ * CSR/CSC take no submatrix (ro_a = co_a = 0, exact dimensions, spmm_dispatch.hh:99-107). index_base must be Zero. */
+int rb_spmm_f32(int side_left, int fmt, char layout, char opA, char opB, int64_t d, int64_t n, int64_t m, float alpha,
+                int64_t A_rows, int64_t A_cols, int64_t nnz, const float* vals, const void* idx0, const void* idx1,
+                int idx_bytes, int64_t ro_a, int64_t co_a, const float* B, int64_t ldb, float beta, float* C, int64_t ldc,
+                void* stream);
+int rb_spmm_f64(int side_left, int fmt, char layout, char opA, char opB, int64_t d, int64_t n, int64_t m, double alpha,
+                int64_t A_rows, int64_t A_cols, int64_t nnz, const double* vals, const void* idx0, const void* idx1,
+                int idx_bytes, int64_t ro_a, int64_t co_a, const double* B, int64_t ldb, double beta, double* C,
+                int64_t ldc, void* stream);
+
 /* ---- K4: dense operator applied to sparse data ----
  * Replaces sparse_data::lsksp3 (RandBLAS/sparse_data/sksp.hh:132-182) / rsksp3 (:277-326), i.e. sketch_sparse
  * (:418-437, :520-539) and the right_spmm/left_spmm kernels under them (spmm_dispatch.hh:52-219,

@@ -402,6 +402,28 @@ def sketch_vector(opS, *args):
     return sketch_general(Layout.RowMajor, opS, Op.NoTrans, _d, 1, _m, alpha, S, ro_s, co_s, x, incx, beta, y, incy)
 
 
+def left_spmm(layout, opA, opB, d, n, m, alpha, A, ro_a, co_a, B, ldb, beta, C, ldc):
+    """RandBLAS::sparse_data::left_spmm (RandBLAS/sparse_data/spmm_dispatch.hh:52-178):
+    C(d x n) = alpha * op(A_sp[ro_a:, co_a:])(d x m) * op(B)(m x n) + beta * C."""
+    _require(A.index_base == 0, "A.index_base == IndexBase::Zero")      # spmm_dispatch.hh:92
+    sfx, t = _sfx(_dtype_of(C))
+    ib = np.dtype(_dtype_of(A._idx0)).itemsize
+    call(f"rb_spmm_{sfx}", "iicccqqq" + t + "qqqpppi" + "qqpq" + t + "pqp", 1, A._fmt, layout, opA, opB, int(d), int(n),
+         int(m), alpha, A.n_rows, A.n_cols, A.nnz, _ptr(A.vals), _ptr(A._idx0), _ptr(A._idx1), ib, int(ro_a), int(co_a),
+         _ptr(B), int(ldb), beta, _ptr(C), int(ldc), _stream(B, C))
+
+
+def right_spmm(layout, opA, opB, m, d, n, alpha, A, lda, B, i_off, j_off, beta, C, ldc):
+    """RandBLAS::sparse_data::right_spmm (spmm_dispatch.hh:180-219):
+    C(m x d) = alpha * op(A)(m x n) * op(B_sp[i_off:, j_off:])(n x d) + beta * C, A dense, B sparse."""
+    _require(B.index_base == 0, "B.index_base == IndexBase::Zero")
+    sfx, t = _sfx(_dtype_of(C))
+    ib = np.dtype(_dtype_of(B._idx0)).itemsize
+    call(f"rb_spmm_{sfx}", "iicccqqq" + t + "qqqpppi" + "qqpq" + t + "pqp", 0, B._fmt, layout, opB, opA, int(d), int(n),
+         int(m), alpha, B.n_rows, B.n_cols, B.nnz, _ptr(B.vals), _ptr(B._idx0), _ptr(B._idx1), ib, int(i_off), int(j_off),
+         _ptr(A), int(lda), beta, _ptr(C), int(ldc), _stream(A, C))
+
+
 def sketch_sparse(layout, op1, op2, x, y, z, alpha, *rest):
     """RandBLAS/sparse_data/sksp.hh:418-437 (left) and :520-539 (right).
 

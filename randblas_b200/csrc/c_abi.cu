@@ -507,6 +507,48 @@ static int coo_apply_impl(int left, char layout, char opS, char opA, int64_t d, 
     return rc;
 }
 
+// sparse data matrix applied to a dense matrix: left_spmm / right_spmm [spmm_dispatch.hh:52-219].
+//   left : C(d x n) = alpha * op(A_sp[ro_a:, co_a:])(d x m) * op(B)(m x n) + beta * C
+//   right: C(m x d) = alpha * op(B)(m x n) * op(A_sp[ro_a:, co_a:])(n x d) + beta * C
+// COO goes to the COO kernel as is; CSR / CSC first get their pointer array expanded to an index array.
+template <typename T>
+static int spmm_impl(int left, int fmt, char layout, char opA, char opB, int64_t d, int64_t n, int64_t m, T alpha,
+                     int64_t A_rows, int64_t A_cols, int64_t nnz, const T* vals, const void* idx0, const void* idx1,
+                     int idx_bytes, int64_t ro_a, int64_t co_a, const T* B, int64_t ldb, T beta, T* C, int64_t ldc,
+                     void* stream) {
+    cudaStream_t st = (cudaStream_t) stream;
+    RB_REQUIRE(fmt >= 0 && fmt <= 2);
+    RB_REQUIRE(ok_op(opA));
+    RB_REQUIRE(nnz >= 0 && A_rows >= 0 && A_cols >= 0);
+    RB_REQUIRE(idx_bytes == 4 || idx_bytes == 8);
+    if (fmt != 2) {
+        // spmm_dispatch.hh:99-107 (after the transposition of :87-88): compressed formats take no submatrix
+        const int64_t a1 = left ? d : n, a2 = left ? m : d;              // op(A_sp window) is a1 x a2
+        RB_REQUIRE(((opA == 'N') ? A_rows : A_cols) == a1);
+        RB_REQUIRE(((opA == 'N') ? A_cols : A_rows) == a2);
+        RB_REQUIRE(ro_a == 0);
+        RB_REQUIRE(co_a == 0);
+    }
+    if (fmt == 2)
+        return coo_apply_impl<T>(left, layout, opA, opB, d, n, m, alpha, A_rows, A_cols, nnz, vals, idx0, idx1, idx_bytes,
+                                 ro_a, co_a, B, ldb, beta, C, ldc, stream);
+    // CSR: idx0 = rowptr (A_rows + 1), idx1 = colidxs; CSC: idx0 = rowidxs, idx1 = colptr (A_cols + 1)
+    const int64_t n_major = (fmt == 0) ? A_rows : A_cols;
+    const void* ptr = (fmt == 0) ? idx0 : idx1;
+    RB_REQUIRE(ptr != nullptr || n_major == 0);
+    Staged sp;
+    int rc = sp.open(ptr, (size_t) idx_bytes, 1, n_major + 1, n_major + 1, true, false, st); if (rc) return rc;
+    void* expanded = workspace(3, (size_t) (nnz > 0 ? nnz : 1) * (size_t) idx_bytes);
+    if (!expanded) return fail_cuda(cudaErrorMemoryAllocation, "spmm index workspace");
+    rc = launch_expand_ptr(n_major, sp.dev, expanded, idx_bytes, st);
+    int rc2 = sp.close(); if (!rc) rc = rc2;
+    if (rc) return rc;
+    const void* rows = (fmt == 0) ? expanded : idx0;
+    const void* cols = (fmt == 0) ? idx1 : expanded;
+    return coo_apply_impl<T>(left, layout, opA, opB, d, n, m, alpha, A_rows, A_cols, nnz, vals, rows, cols, idx_bytes, ro_a,
+                             co_a, B, ldb, beta, C, ldc, stream);
+}
+
 // dense operator applied to sparse data [sksp.hh:132-182, 277-326]
 template <typename T>
 static int sksp3_impl(bool left, int fmt, char layout, char opS, char opA, int64_t d, int64_t n, int64_t m, T alpha,
@@ -754,6 +796,13 @@ int rb_repeated_fisher_yates(int64_t k, int64_t n, int64_t r, void* samples, int
                            T beta, T* B, int64_t ldb, void* stream) {                                                  \
         return coo_apply_impl<T>(side_left, layout, opS, opA, d, n, m, alpha, S_rows, S_cols, nnz, vals, rows, cols,   \
                                  idx_bytes, ro_s, co_s, A, lda, beta, B, ldb, stream);                                 \
+    }                                                                                                                  \
+    int rb_spmm_##sfx(int side_left, int fmt, char layout, char opA, char opB, int64_t d, int64_t n, int64_t m,         \
+                      T alpha, int64_t A_rows, int64_t A_cols, int64_t nnz, const T* vals, const void* idx0,           \
+                      const void* idx1, int idx_bytes, int64_t ro_a, int64_t co_a, const T* B, int64_t ldb, T beta,    \
+                      T* C, int64_t ldc, void* stream) {                                                               \
+        return spmm_impl<T>(side_left, fmt, layout, opA, opB, d, n, m, alpha, A_rows, A_cols, nnz, vals, idx0, idx1,   \
+                            idx_bytes, ro_a, co_a, B, ldb, beta, C, ldc, stream);                                      \
     }                                                                                                                  \
     int rb_lsksp3_##sfx(int fmt, char layout, char opS, char opA, int64_t d, int64_t n, int64_t m, T alpha,            \
                         int64_t D_rows, int64_t D_cols, char family, char major_axis, const uint32_t ctr[4],           \

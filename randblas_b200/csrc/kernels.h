@@ -103,6 +103,9 @@ struct CooProblem {
 template <typename T>
 int launch_coo_apply(const CooProblem<T>& p, cudaStream_t st);
 
+// CSR rowptr / CSC colptr expanded to one index per stored entry (device pointers)
+int launch_expand_ptr(int64_t n_major, const void* ptr, void* out, int idx_bytes, cudaStream_t st);
+
 // beta pre-scale of a strided P x Q matrix (beta == 0 writes zeros without reading)
 template <typename T>
 int launch_scale(int64_t P, int64_t Q, T beta, T* C, int64_t crs, int64_t ccs, cudaStream_t st);

@@ -305,6 +305,29 @@ int launch_coo_apply(const CooProblem<T>& p, cudaStream_t st) {
     RB_CUDA(cudaGetLastError());
     return 0;
 }
+// CSR rowptr / CSC colptr -> one index per stored entry (warp per major index), so that compressed formats can use
+// the COO kernel: out[e] = r for ptr[r] <= e < ptr[r + 1]
+template <typename IDX>
+__global__ void __launch_bounds__(256) expand_ptr_kernel(int64_t n_major, const IDX* __restrict__ ptr, IDX* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t) blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t) gridDim.x * blockDim.x) >> 5;
+    for (int64_t r = warp; r < n_major; r += nwarps)
+        for (int64_t e = (int64_t) ptr[r] + lane; e < (int64_t) ptr[r + 1]; e += 32) out[e] = (IDX) r;
+}
+
+int launch_expand_ptr(int64_t n_major, const void* ptr, void* out, int idx_bytes, cudaStream_t st) {
+    if (n_major <= 0) return 0;
+    int64_t grid = (n_major + 7) / 8;
+    const int64_t cap = (int64_t) sm_count() * 8;
+    if (grid > cap) grid = cap;
+    if (idx_bytes == 4) expand_ptr_kernel<int32_t><<<(unsigned) grid, 256, 0, st>>>(n_major, (const int32_t*) ptr, (int32_t*) out);
+    else expand_ptr_kernel<int64_t><<<(unsigned) grid, 256, 0, st>>>(n_major, (const int64_t*) ptr, (int64_t*) out);
+    count_launch();
+    RB_CUDA(cudaGetLastError());
+    return 0;
+}
+
 template int launch_coo_apply<float>(const CooProblem<float>&, cudaStream_t);
 template int launch_coo_apply<double>(const CooProblem<double>&, cudaStream_t);
 

@@ -182,6 +182,21 @@ static void device_checks() {
     for (int64_t i = 0; i < d * m; ++i) num += (Bs[i] - full[i]) * (Bs[i] - full[i]);
     CHECK(std::sqrt(num / den) < tol);
 
+    // --- sparse_data::left_spmm with the sparse identity in CSR form reproduces the dense operand (spmm_dispatch.hh)
+    {
+        std::vector<int64_t> rowptr(m + 1);
+        for (int64_t i = 0; i <= m; ++i) rowptr[i] = i;
+        CSRMatrix<T> Icsr(m, m, m, ones.data(), rowptr.data(), idx.data());
+        std::vector<T> Cs(m * d, T(0));
+        // C(m x d) = I(m x m) * full^T: op(B) = full(d x m)^T, RowMajor
+        sparse_data::left_spmm(blas::Layout::RowMajor, blas::Op::NoTrans, blas::Op::Trans, m, d, m, T(1), Icsr, 0, 0,
+                               full.data(), m, T(0), Cs.data(), d);
+        ok = true;
+        for (int64_t i = 0; i < d; ++i)
+            for (int64_t j = 0; j < m; ++j) ok = ok && Cs[j * d + i] == full[i * m + j];
+        CHECK(ok);
+    }
+
     // --- argument errors surface as RandBLAS::Error before data is touched (skge.hh:183-192)
     CHECK(throws_error([&] { sketch_general(blas::Layout::RowMajor, blas::Op::NoTrans, blas::Op::NoTrans, d, m, m, T(1), S0, 1,
                                             0, I.data(), m, T(0), B.data(), m); }));

@@ -814,6 +814,84 @@ def test_edge_cases_beta_zero_overwrites_nan_and_empty_dimensions(gpu):
     assert bool((B2 == 1.0).all())
 
 
+def test_left_and_right_spmm_vs_scipy(gpu):
+    """sparse_data::left_spmm / right_spmm (spmm_dispatch.hh:52-219) for CSR, CSC and COO data, both ops of the sparse
+    and of the dense matrix, both layouts, int32/int64 indices, float/double, COO submatrix windows; against a scipy
+    product in float64. Compressed formats with offsets must raise (spmm_dispatch.hh:99-107)."""
+    import randblas_b200 as rb
+    import scipy.sparse as sp
+    import torch
+    rng = np.random.default_rng(13)
+
+    def dense(rows, cols, lay, dt):
+        M = rng.standard_normal((rows, cols)).astype(dt)
+        ld = (rows if lay == "C" else cols) + 1
+        buf = np.zeros((cols if lay == "C" else rows) * ld, dt)
+        if lay == "C":
+            buf.reshape(cols, ld)[:, :rows] = M.T
+        else:
+            buf.reshape(rows, ld)[:, :cols] = M
+        return M, buf, ld
+
+    def view(buf, rows, cols, lay, ld):
+        return buf.reshape(cols, ld)[:, :rows].T if lay == "C" else buf.reshape(rows, ld)[:, :cols]
+
+    def to_rb(M, fmt, idt, dt):
+        if fmt == "csr":
+            M = M.tocsr(); M.sort_indices()
+            return rb.CSRMatrix(M.shape[0], M.shape[1], M.nnz, torch.from_numpy(M.data.astype(dt)).cuda(),
+                                torch.from_numpy(M.indptr.astype(idt)).cuda(), torch.from_numpy(M.indices.astype(idt)).cuda())
+        if fmt == "csc":
+            M = M.tocsc(); M.sort_indices()
+            return rb.CSCMatrix(M.shape[0], M.shape[1], M.nnz, torch.from_numpy(M.data.astype(dt)).cuda(),
+                                torch.from_numpy(M.indices.astype(idt)).cuda(), torch.from_numpy(M.indptr.astype(idt)).cuda())
+        M = M.tocoo()
+        return rb.COOMatrix(M.shape[0], M.shape[1], M.nnz, torch.from_numpy(M.data.astype(dt)).cuda(),
+                            torch.from_numpy(M.row.astype(idt)).cuda(), torch.from_numpy(M.col.astype(idt)).cuda())
+
+    d, n, m = 37, 23, 211
+    for dt, tol in ((np.float64, 1e-12), (np.float32, 1e-5)):
+        for fmt, idt, lay, opA, opB in itertools.product(("csr", "csc", "coo"), (np.int32, np.int64), "CR", "NT", "NT"):
+            # left: C(d x n) = alpha op(A)(d x m) op(B)(m x n) + beta C
+            Am = sp.random(*((d, m) if opA == "N" else (m, d)), density=0.08, random_state=int(rng.integers(1 << 30)),
+                           format="coo", dtype=np.float64)
+            A = to_rb(Am, fmt, idt, dt)
+            Bm, Bbuf, ldb = dense(*((m, n) if opB == "N" else (n, m)), lay, dt)
+            Cm, Cbuf, ldc = dense(d, n, lay, dt)
+            Cd = torch.from_numpy(Cbuf.copy()).cuda()
+            rb.left_spmm(lay, opA, opB, d, n, m, 0.5, A, 0, 0, torch.from_numpy(Bbuf).cuda(), ldb, -1.5, Cd, ldc)
+            opAm = Am.toarray().astype(dt).astype(np.float64)
+            opAm = opAm if opA == "N" else opAm.T
+            opBm = Bm.astype(np.float64) if opB == "N" else Bm.astype(np.float64).T
+            want = 0.5 * opAm @ opBm - 1.5 * Cm.astype(np.float64)
+            got = view(Cd.cpu().numpy(), d, n, lay, ldc)
+            assert relerr(got, want) < tol, ("left", fmt, idt, lay, opA, opB, relerr(got, want))
+            # right: C(n x d) = alpha op(B)(n x m) op(A)(m x d) + beta C   [right_spmm(layout, opB, opA, n, d, m, ...)]
+            Am2 = sp.random(*((m, d) if opA == "N" else (d, m)), density=0.08, random_state=int(rng.integers(1 << 30)),
+                            format="coo", dtype=np.float64)
+            A2 = to_rb(Am2, fmt, idt, dt)
+            Bm2, Bbuf2, ldb2 = dense(*((n, m) if opB == "N" else (m, n)), lay, dt)
+            Cm2, Cbuf2, ldc2 = dense(n, d, lay, dt)
+            Cd2 = torch.from_numpy(Cbuf2.copy()).cuda()
+            rb.right_spmm(lay, opB, opA, n, d, m, 2.0, torch.from_numpy(Bbuf2).cuda(), ldb2, A2, 0, 0, 0.25, Cd2, ldc2)
+            opA2 = Am2.toarray().astype(dt).astype(np.float64)
+            opA2 = opA2 if opA == "N" else opA2.T
+            opB2 = Bm2.astype(np.float64) if opB == "N" else Bm2.astype(np.float64).T
+            want2 = 2.0 * opB2 @ opA2 + 0.25 * Cm2.astype(np.float64)
+            got2 = view(Cd2.cpu().numpy(), n, d, lay, ldc2)
+            assert relerr(got2, want2) < tol, ("right", fmt, idt, lay, opA, opB, relerr(got2, want2))
+    # COO submatrix window; compressed formats refuse offsets
+    big = sp.random(60, 300, density=0.05, random_state=5, format="coo", dtype=np.float64)
+    Acoo = to_rb(big, "coo", np.int64, np.float64)
+    Bm, Bbuf, ldb = dense(m, n, "R", np.float64)
+    Cd = torch.zeros(d * n, dtype=torch.float64, device="cuda")
+    rb.left_spmm("R", "N", "N", d, n, m, 1.0, Acoo, 3, 7, torch.from_numpy(Bbuf).cuda(), ldb, 0.0, Cd, n)
+    assert relerr(Cd.cpu().numpy().reshape(d, n), big.toarray()[3:3 + d, 7:7 + m] @ Bm) < 1e-12
+    Acsr = to_rb(big, "csr", np.int64, np.float64)
+    with pytest.raises(rb.RandBLASError):
+        rb.left_spmm("R", "N", "N", d, n, m, 1.0, Acsr, 3, 7, torch.from_numpy(Bbuf).cuda(), ldb, 0.0, Cd, n)
+
+
 def test_argument_errors_on_gpu(gpu):
     import randblas_b200 as rb
     import torch
