@@ -121,6 +121,23 @@ static bool on_device(const void* p) {
     return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
 }
 
+// Staging buffers come from the device's default memory pool. Its default release threshold is 0, i.e. every
+// synchronisation hands the memory back to the driver and the next host-pointer call pays for a fresh allocation of
+// hundreds of megabytes; keep freed blocks in the pool instead (once per device).
+static void keep_pool_memory() {
+    static std::atomic<uint64_t> done{0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) { cudaGetLastError(); return; }
+    if (done.load() & (1ull << dev)) return;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        uint64_t thr = UINT64_MAX;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    cudaGetLastError();
+    done.fetch_or(1ull << dev);
+}
+
 // A (outer x inner) strided matrix or a flat array that may live on the host. Staged copies keep `ld`.
 struct Staged {
     void* dev = nullptr;
@@ -138,6 +155,7 @@ struct Staged {
         host = const_cast<void*>(p);
         staged = true;
         const size_t bytes = ((outer - 1) * ld + inner) * elem;
+        keep_pool_memory();
         RB_CUDA(cudaMallocAsync(&dev, bytes, st));
         if (copy_in)
             RB_CUDA(cudaMemcpy2DAsync(dev, ld * elem, host, ld * elem, inner * elem, outer, cudaMemcpyHostToDevice, st));
@@ -624,7 +642,15 @@ extern "C" {
 
 const char* rb_last_error(void) { return g_err.c_str(); }
 int rb_version(void) { return 100; }
-int rb_release_workspace(void) { release_workspace(); return 0; }
+int rb_release_workspace(void) {
+    release_workspace();
+    int dev = 0;
+    cudaMemPool_t pool;
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess)
+        cudaMemPoolTrimTo(pool, 0);            // staging buffers kept by keep_pool_memory()
+    cudaGetLastError();
+    return 0;
+}
 
 int rb_device_info(int64_t info[3]) {
     int dev = 0;
