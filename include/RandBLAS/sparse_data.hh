@@ -2,6 +2,8 @@
 // Field names and constructor signatures follow RandBLAS/sparse_data/{base,coo_matrix,csr_matrix,csc_matrix}.hh;
 // conversions, sorting and the CPU SpMM kernels of the reference are outside the hot path.
 #pragma once
+#include <algorithm>
+#include <type_traits>
 #include "base.hh"
 
 namespace RandBLAS {
@@ -128,5 +130,59 @@ inline void sp_arrays(const CSCMatrix<T, I>& A, int& fmt, const void*& i0, const
 template <typename T, typename I>
 inline void sp_arrays(const COOMatrix<T, I>& A, int& fmt, const void*& i0, const void*& i1) { fmt = 2; i0 = A.rows; i1 = A.cols; }
 }  // namespace internal
+
+namespace sparse_data {
+// conversions.hh:101-121 / :79-99. The destination must be an empty owning matrix of the same shape (reserve() is
+// called here, as in the reference); the arrays are host memory, the sort runs on the device (rb_coo_to_compressed).
+template <typename T, typename I1, typename I2>
+void coo_to_csr(const COOMatrix<T, I1>& coo, CSRMatrix<T, I2>& csr) {
+    static_assert(std::is_same_v<I1, I2>, "index types must match in this build");
+    randblas_require(csr.n_rows == coo.n_rows);
+    randblas_require(csr.n_cols == coo.n_cols);
+    randblas_require(csr.index_base == IndexBase::Zero);
+    if (coo.nnz == 0) return;
+    csr.reserve(coo.nnz);
+    internal::check(rb_coo_to_compressed(0, coo.n_rows, coo.n_cols, coo.nnz, coo.vals, (int) sizeof(T), coo.rows, coo.cols,
+                                         (int) sizeof(I1), csr.vals, csr.colidxs, csr.rowptr, nullptr),
+                    __func__);
+}
+template <typename T, typename I1, typename I2>
+void coo_to_csc(const COOMatrix<T, I1>& coo, CSCMatrix<T, I2>& csc) {
+    static_assert(std::is_same_v<I1, I2>, "index types must match in this build");
+    randblas_require(csc.n_rows == coo.n_rows);
+    randblas_require(csc.n_cols == coo.n_cols);
+    randblas_require(csc.index_base == IndexBase::Zero);
+    if (coo.nnz == 0) return;
+    csc.reserve(coo.nnz);
+    internal::check(rb_coo_to_compressed(1, coo.n_rows, coo.n_cols, coo.nnz, coo.vals, (int) sizeof(T), coo.rows, coo.cols,
+                                         (int) sizeof(I1), csc.vals, csc.rowidxs, csc.colptr, nullptr),
+                    __func__);
+}
+// conversions.hh:63-75 / :49-61
+template <typename T, typename I1, typename I2>
+void csr_to_coo(const CSRMatrix<T, I1>& csr, COOMatrix<T, I2>& coo) {
+    static_assert(std::is_same_v<I1, I2>, "index types must match in this build");
+    randblas_require(csr.n_rows == coo.n_rows);
+    randblas_require(csr.n_cols == coo.n_cols);
+    if (csr.nnz == 0) return;
+    coo.reserve(csr.nnz);
+    internal::check(rb_expand_ptr(csr.n_rows, csr.rowptr, csr.nnz, coo.rows, (int) sizeof(I1), nullptr), __func__);
+    std::copy(csr.vals, csr.vals + csr.nnz, coo.vals);
+    std::copy(csr.colidxs, csr.colidxs + csr.nnz, coo.cols);
+    coo.sort = NonzeroSort::CSR;
+}
+template <typename T, typename I1, typename I2>
+void csc_to_coo(const CSCMatrix<T, I1>& csc, COOMatrix<T, I2>& coo) {
+    static_assert(std::is_same_v<I1, I2>, "index types must match in this build");
+    randblas_require(csc.n_rows == coo.n_rows);
+    randblas_require(csc.n_cols == coo.n_cols);
+    if (csc.nnz == 0) return;
+    coo.reserve(csc.nnz);
+    internal::check(rb_expand_ptr(csc.n_cols, csc.colptr, csc.nnz, coo.cols, (int) sizeof(I1), nullptr), __func__);
+    std::copy(csc.vals, csc.vals + csc.nnz, coo.vals);
+    std::copy(csc.rowidxs, csc.rowidxs + csc.nnz, coo.rows);
+    coo.sort = NonzeroSort::CSC;
+}
+}  // namespace sparse_data
 
 }  // namespace RandBLAS

@@ -168,6 +168,17 @@ int rb_spmm_f64(int side_left, int fmt, char layout, char opA, char opB, int64_t
                 int idx_bytes, int64_t ro_a, int64_t co_a, const double* B, int64_t ldb, double beta, double* C,
                 int64_t ldc, void* stream);
 
+/* ---- sparse format conversions on the device ----
+ * Replaces coo_to_csr / coo_to_csc (RandBLAS/sparse_data/conversions.hh:79-121 with COOMatrix::sort_arrays and
+ * sorted_idxs_to_compressed_ptr, sparse_data/base.hh:279-301): to_csc = 0 compresses the rows, 1 the columns.
+ * out_vals / out_idx hold nnz entries ordered by (major, minor) index, out_ptr n_major + 1 offsets. */
+int rb_coo_to_compressed(int to_csc, int64_t n_rows, int64_t n_cols, int64_t nnz, const void* vals, int val_bytes,
+                         const void* rows, const void* cols, int idx_bytes, void* out_vals, void* out_idx, void* out_ptr,
+                         void* stream);
+/* csr_to_coo / csc_to_coo (conversions.hh:49-75): ptr (n_major + 1 offsets) expanded to one major index per entry;
+ * the other two COO arrays are the compressed matrix's own vals and index array. */
+int rb_expand_ptr(int64_t n_major, const void* ptr, int64_t nnz, void* out_idx, int idx_bytes, void* stream);
+
 /* ---- K4: dense operator applied to sparse data ----
  * Replaces sparse_data::lsksp3 (RandBLAS/sparse_data/sksp.hh:132-182) / rsksp3 (:277-326), i.e. sketch_sparse
  * (:418-437, :520-539) and the right_spmm/left_spmm kernels under them (spmm_dispatch.hh:52-219,

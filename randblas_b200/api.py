@@ -402,6 +402,49 @@ def sketch_vector(opS, *args):
     return sketch_general(Layout.RowMajor, opS, Op.NoTrans, _d, 1, _m, alpha, S, ro_s, co_s, x, incx, beta, y, incy)
 
 
+def _like(x, n, dtype=None):
+    """A new array of n entries living where x lives (torch CUDA tensor or numpy array)."""
+    if torch is not None and isinstance(x, torch.Tensor):
+        return torch.empty(int(n), dtype=dtype if dtype is not None else x.dtype, device=x.device)
+    return np.empty(int(n), dtype=dtype if dtype is not None else x.dtype)
+
+
+def coo_to_csr(coo):
+    """RandBLAS/sparse_data/conversions.hh:101-121. Returns a new CSRMatrix (entries ordered by (row, col))."""
+    _require(coo.index_base == 0, "coo.index_base == IndexBase::Zero")
+    vals, idx, ptr = _like(coo.vals, coo.nnz), _like(coo.rows, coo.nnz), _like(coo.rows, coo.n_rows + 1)
+    call("rb_coo_to_compressed", "iqqqpippipppp", 0, coo.n_rows, coo.n_cols, coo.nnz, _ptr(coo.vals),
+         np.dtype(_dtype_of(coo.vals)).itemsize, _ptr(coo.rows), _ptr(coo.cols), np.dtype(_dtype_of(coo.rows)).itemsize,
+         _ptr(vals), _ptr(idx), _ptr(ptr), _stream(coo.vals, vals))
+    return CSRMatrix(coo.n_rows, coo.n_cols, coo.nnz, vals, ptr, idx)
+
+
+def coo_to_csc(coo):
+    """RandBLAS/sparse_data/conversions.hh:79-99. Returns a new CSCMatrix (entries ordered by (col, row))."""
+    _require(coo.index_base == 0, "coo.index_base == IndexBase::Zero")
+    vals, idx, ptr = _like(coo.vals, coo.nnz), _like(coo.rows, coo.nnz), _like(coo.rows, coo.n_cols + 1)
+    call("rb_coo_to_compressed", "iqqqpippipppp", 1, coo.n_rows, coo.n_cols, coo.nnz, _ptr(coo.vals),
+         np.dtype(_dtype_of(coo.vals)).itemsize, _ptr(coo.rows), _ptr(coo.cols), np.dtype(_dtype_of(coo.rows)).itemsize,
+         _ptr(vals), _ptr(idx), _ptr(ptr), _stream(coo.vals, vals))
+    return CSCMatrix(coo.n_rows, coo.n_cols, coo.nnz, vals, idx, ptr)
+
+
+def csr_to_coo(csr):
+    """RandBLAS/sparse_data/conversions.hh:63-75. vals and cols are shared with the CSR matrix, rows is new."""
+    rows = _like(csr.colidxs, csr.nnz)
+    call("rb_expand_ptr", "qpqpip", csr.n_rows, _ptr(csr.rowptr), csr.nnz, _ptr(rows),
+         np.dtype(_dtype_of(csr.rowptr)).itemsize, _stream(csr.rowptr, rows))
+    return COOMatrix(csr.n_rows, csr.n_cols, csr.nnz, csr.vals, rows, csr.colidxs)
+
+
+def csc_to_coo(csc):
+    """RandBLAS/sparse_data/conversions.hh:49-61. vals and rows are shared with the CSC matrix, cols is new."""
+    cols = _like(csc.rowidxs, csc.nnz)
+    call("rb_expand_ptr", "qpqpip", csc.n_cols, _ptr(csc.colptr), csc.nnz, _ptr(cols),
+         np.dtype(_dtype_of(csc.colptr)).itemsize, _stream(csc.colptr, cols))
+    return COOMatrix(csc.n_rows, csc.n_cols, csc.nnz, csc.vals, csc.rowidxs, cols)
+
+
 def left_spmm(layout, opA, opB, d, n, m, alpha, A, ro_a, co_a, B, ldb, beta, C, ldc):
     """RandBLAS::sparse_data::left_spmm (RandBLAS/sparse_data/spmm_dispatch.hh:52-178):
     C(d x n) = alpha * op(A_sp[ro_a:, co_a:])(d x m) * op(B)(m x n) + beta * C."""

@@ -712,6 +712,51 @@ int rb_sparse_next_state(int64_t n_rows, int64_t n_cols, int64_t vec_nnz, char m
     return 0;
 }
 
+// coo_to_csr / coo_to_csc [sparse_data/conversions.hh:79-121]; to_csc = 0: rows are compressed, 1: columns
+int rb_coo_to_compressed(int to_csc, int64_t n_rows, int64_t n_cols, int64_t nnz, const void* vals, int val_bytes,
+                         const void* rows, const void* cols, int idx_bytes, void* out_vals, void* out_idx, void* out_ptr,
+                         void* stream) {
+    cudaStream_t st = (cudaStream_t) stream;
+    RB_REQUIRE(n_rows >= 0 && n_cols >= 0 && nnz >= 0);
+    RB_REQUIRE(idx_bytes == 4 || idx_bytes == 8);
+    RB_REQUIRE(val_bytes == 4 || val_bytes == 8);
+    RB_REQUIRE(out_ptr != nullptr);
+    RB_REQUIRE(nnz == 0 || (vals && rows && cols && out_vals && out_idx));
+    const int64_t n_major = to_csc ? n_cols : n_rows, n_minor = to_csc ? n_rows : n_cols;
+    Staged sv, sr, sc, ov, oi, op;
+    int rc = sv.open(vals, (size_t) val_bytes, 1, nnz, nnz, true, false, st); if (rc) return rc;
+    rc = sr.open(rows, (size_t) idx_bytes, 1, nnz, nnz, true, false, st); if (rc) return rc;
+    rc = sc.open(cols, (size_t) idx_bytes, 1, nnz, nnz, true, false, st); if (rc) return rc;
+    rc = ov.open(out_vals, (size_t) val_bytes, 1, nnz, nnz, false, true, st); if (rc) return rc;
+    rc = oi.open(out_idx, (size_t) idx_bytes, 1, nnz, nnz, false, true, st); if (rc) return rc;
+    rc = op.open(out_ptr, (size_t) idx_bytes, 1, n_major + 1, n_major + 1, false, true, st); if (rc) return rc;
+    rc = launch_coo_to_compressed(n_major, n_minor, nnz, sv.dev, val_bytes, to_csc ? sc.dev : sr.dev, to_csc ? sr.dev : sc.dev,
+                                  idx_bytes, ov.dev, oi.dev, op.dev, nullptr, st);
+    int rc2 = sv.close(); if (!rc) rc = rc2;
+    rc2 = sr.close(); if (!rc) rc = rc2;
+    rc2 = sc.close(); if (!rc) rc = rc2;
+    rc2 = ov.close(); if (!rc) rc = rc2;
+    rc2 = oi.close(); if (!rc) rc = rc2;
+    rc2 = op.close(); if (!rc) rc = rc2;
+    return rc;
+}
+
+// csr_to_coo / csc_to_coo [sparse_data/conversions.hh:49-75]: the pointer array expanded to one index per entry
+int rb_expand_ptr(int64_t n_major, const void* ptr, int64_t nnz, void* out_idx, int idx_bytes, void* stream) {
+    cudaStream_t st = (cudaStream_t) stream;
+    RB_REQUIRE(n_major >= 0 && nnz >= 0);
+    RB_REQUIRE(idx_bytes == 4 || idx_bytes == 8);
+    RB_REQUIRE(ptr != nullptr);
+    RB_REQUIRE(nnz == 0 || out_idx != nullptr);
+    Staged sp, so;
+    int rc = sp.open(ptr, (size_t) idx_bytes, 1, n_major + 1, n_major + 1, true, false, st); if (rc) return rc;
+    rc = so.open(out_idx, (size_t) idx_bytes, 1, nnz, nnz, false, true, st); if (rc) return rc;
+    rc = launch_expand_ptr(n_major, sp.dev, so.dev, idx_bytes, st);
+    int rc2 = sp.close(); if (!rc) rc = rc2;
+    rc2 = so.close(); if (!rc) rc = rc2;
+    return rc;
+}
+
 int rb_philox_words(const uint32_t ctr[4], const uint32_t key[2], int64_t n_blocks, uint32_t* out, void* stream) {
     RB_REQUIRE(ctr != nullptr && key != nullptr && n_blocks >= 0);
     if (n_blocks == 0) return 0;

@@ -106,6 +106,11 @@ int launch_coo_apply(const CooProblem<T>& p, cudaStream_t st);
 // CSR rowptr / CSC colptr expanded to one index per stored entry (device pointers)
 int launch_expand_ptr(int64_t n_major, const void* ptr, void* out, int idx_bytes, cudaStream_t st);
 
+// COO -> CSR / CSC on the device (conversions.cu); device pointers
+int launch_coo_to_compressed(int64_t n_major, int64_t n_minor, int64_t nnz, const void* vals, int val_bytes, const void* major,
+                             const void* minor, int idx_bytes, void* ovals, void* ominor, void* optr, void* omajor,
+                             cudaStream_t st);
+
 // beta pre-scale of a strided P x Q matrix (beta == 0 writes zeros without reading)
 template <typename T>
 int launch_scale(int64_t P, int64_t Q, T beta, T* C, int64_t crs, int64_t ccs, cudaStream_t st);

@@ -197,6 +197,27 @@ static void device_checks() {
         CHECK(ok);
     }
 
+    // --- format conversions (sparse_data/conversions.hh): COO -> CSR -> COO round trip of a small unsorted matrix
+    {
+        int64_t r[5] = {2, 0, 1, 2, 0}, c[5] = {1, 3, 0, 0, 1};
+        T v[5] = {T(5), T(2), T(3), T(4), T(1)};
+        COOMatrix<T> Acoo(3, 4, 5, v, r, c);
+        CSRMatrix<T> Acsr(3, 4);
+        sparse_data::coo_to_csr(Acoo, Acsr);
+        const int64_t want_ptr[4] = {0, 2, 3, 5}, want_col[5] = {1, 3, 0, 0, 1};
+        const T want_val[5] = {T(1), T(2), T(3), T(4), T(5)};
+        ok = Acsr.nnz == 5;
+        for (int i = 0; i < 4; ++i) ok = ok && Acsr.rowptr[i] == want_ptr[i];
+        for (int i = 0; i < 5; ++i) ok = ok && Acsr.colidxs[i] == want_col[i] && Acsr.vals[i] == want_val[i];
+        CHECK(ok);
+        COOMatrix<T> Aback(3, 4);
+        sparse_data::csr_to_coo(Acsr, Aback);
+        const int64_t want_row[5] = {0, 0, 1, 2, 2};
+        ok = Aback.nnz == 5;
+        for (int i = 0; i < 5; ++i) ok = ok && Aback.rows[i] == want_row[i] && Aback.cols[i] == want_col[i];
+        CHECK(ok);
+    }
+
     // --- argument errors surface as RandBLAS::Error before data is touched (skge.hh:183-192)
     CHECK(throws_error([&] { sketch_general(blas::Layout::RowMajor, blas::Op::NoTrans, blas::Op::NoTrans, d, m, m, T(1), S0, 1,
                                             0, I.data(), m, T(0), B.data(), m); }));

@@ -892,6 +892,33 @@ def test_left_and_right_spmm_vs_scipy(gpu):
         rb.left_spmm("R", "N", "N", d, n, m, 1.0, Acsr, 3, 7, torch.from_numpy(Bbuf).cuda(), ldb, 0.0, Cd, n)
 
 
+def test_sparse_format_conversions_vs_scipy(gpu):
+    """coo_to_csr / coo_to_csc / csr_to_coo / csc_to_coo on the device (sparse_data/conversions.hh:49-121): the compressed
+    matrices must equal scipy's canonical ones (sorted indices), for int32/int64 indices and float/double values, with
+    device and with host arrays, including an empty matrix and duplicate-free random patterns at two sizes."""
+    import randblas_b200 as rb
+    import scipy.sparse as sp
+    import torch
+    rng = np.random.default_rng(17)
+    for (nr, nc, dens) in ((37, 53, 0.2), (2000, 3000, 0.01), (5, 7, 0.0)):
+        M = sp.random(nr, nc, density=dens, random_state=int(rng.integers(1 << 30)), format="coo", dtype=np.float64)
+        perm = rng.permutation(M.nnz)          # unsorted input
+        for idt, dt, on_dev in itertools.product((np.int32, np.int64), (np.float32, np.float64), (True, False)):
+            mk = (lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()) if on_dev else np.ascontiguousarray
+            back = (lambda t: t.cpu().numpy()) if on_dev else (lambda t: t)
+            coo = rb.COOMatrix(nr, nc, M.nnz, mk(M.data[perm].astype(dt)), mk(M.row[perm].astype(idt)), mk(M.col[perm].astype(idt)))
+            csr, csc = rb.coo_to_csr(coo), rb.coo_to_csc(coo)
+            R = M.astype(dt).tocsr(); R.sort_indices()
+            C = M.astype(dt).tocsc(); C.sort_indices()
+            assert np.array_equal(back(csr.rowptr), R.indptr) and np.array_equal(back(csr.colidxs), R.indices)
+            assert np.array_equal(back(csr.vals), R.data)
+            assert np.array_equal(back(csc.colptr), C.indptr) and np.array_equal(back(csc.rowidxs), C.indices)
+            assert np.array_equal(back(csc.vals), C.data)
+            c2, c3 = rb.csr_to_coo(csr), rb.csc_to_coo(csc)
+            assert np.array_equal(back(c2.rows), R.tocoo().row) and np.array_equal(back(c2.cols), R.indices)
+            assert np.array_equal(back(c3.cols), C.tocoo().col) and np.array_equal(back(c3.rows), C.indices)
+
+
 def test_argument_errors_on_gpu(gpu):
     import randblas_b200 as rb
     import torch
