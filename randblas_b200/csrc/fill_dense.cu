@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(256) fill_dense_kernel(const FillArgs a, T* __
 // Fast path for long vectors: a tile is FILL_UNROLL x 256 consecutive blocks of ONE vector, so the counter of
 // a block is (tile-uniform 128-bit base) + (small offset) and the destination pointer is base + 4 * offset.
 // Tiles whose blocks are all interior and 4-element aligned take a predicate-free store path.
-constexpr int FILL_UNROLL = 4;
+constexpr int FILL_UNROLL = 4;   // Uniform family; the kernel is templated on the unroll and on the CTAs per SM
 
 struct FillTileArgs {
     Ctr128 ctr;
@@ -105,8 +105,8 @@ struct FillTileArgs {
     const double2* logtab;
 };
 
-template <typename T, bool GAUSS>
-__global__ void __launch_bounds__(256, 4) fill_dense_tiled_kernel(const FillTileArgs a, T* __restrict__ dst) {
+template <typename T, bool GAUSS, int FILL_UNROLL = 4, int MINB = 4>
+__global__ void __launch_bounds__(256, MINB) fill_dense_tiled_kernel(const FillTileArgs a, T* __restrict__ dst) {
     __shared__ __align__(16) double2 logtab[GAUSS ? LOGF_TABLE_ENTRIES : 1];
     if constexpr (GAUSS) {
         load_logf_table(logtab, a.logtab);
@@ -222,19 +222,23 @@ int launch_fill_dense(const DenseGen& g, char family, int64_t v0, int64_t nv, in
     // lanes walk whichever direction is contiguous in memory
     const bool walk_v = (su != 1) && (sv == 1 || sv < su);
     const bool gauss_ = family == 'G';
-    if (!walk_v && su == 1 && a.nblk >= 2 * 256 * FILL_UNROLL) {
+    // Tiled fast path. Gaussian: 8 blocks per thread and tile, 5 CTAs (10 warps per scheduler, 48 registers) -- the
+    // Box-Muller chains want both the instruction-level and the thread-level parallelism (measured on C2: 561 vs 518
+    // Gsamples/s for 4 blocks / 4 CTAs; tools/exp_fill_variants.py). Uniform: 4 blocks, 4 CTAs (already at the HBM roofline).
+    const int unroll = gauss_ ? 8 : FILL_UNROLL;
+    if (!walk_v && su == 1 && a.nblk >= 2 * 256 * unroll) {
         FillTileArgs t;
         t.ctr = g.ctr; t.key = g.key; t.R = g.R; t.logtab = g.logtab; t.v0 = v0; t.nv = nv; t.u0 = u0; t.nu = nu;
         t.blk_first = a.blk_first; t.nblk = a.nblk; t.sv = sv;
-        t.tiles_per_vec = (a.nblk + 256 * FILL_UNROLL - 1) / (256 * FILL_UNROLL);
+        t.tiles_per_vec = (a.nblk + 256 * unroll - 1) / (256 * unroll);
         t.total_tiles = nv * t.tiles_per_vec;
         int64_t tgrid = t.total_tiles;
-        const int64_t tcap = (int64_t) sm_count() * 8;
+        const int64_t tcap = (int64_t) sm_count() * (gauss_ ? 10 : 8);
         if (tgrid > tcap) tgrid = tcap;
         t.q_step = tgrid / t.tiles_per_vec;
         t.r_step = tgrid % t.tiles_per_vec;
-        if (gauss_) fill_dense_tiled_kernel<T, true><<<(unsigned) tgrid, 256, 0, st>>>(t, dst);
-        else fill_dense_tiled_kernel<T, false><<<(unsigned) tgrid, 256, 0, st>>>(t, dst);
+        if (gauss_) fill_dense_tiled_kernel<T, true, 8, 5><<<(unsigned) tgrid, 256, 0, st>>>(t, dst);
+        else fill_dense_tiled_kernel<T, false, FILL_UNROLL, 4><<<(unsigned) tgrid, 256, 0, st>>>(t, dst);
         count_launch();
         RB_CUDA(cudaGetLastError());
         return 0;
