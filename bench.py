@@ -148,10 +148,10 @@ class C2FillDense(Workload):
     def roofline(self, kernel_ms, pk):
         gbs = self.rows * self.cols * 8 / 1e9 / (kernel_ms / 1e3)
         return {"bound": "hbm", "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gbs / pk["hbm_gbs"],
-                "traffic": self.rows * self.cols * 8 * (1.988955 + 0.000193) / 2.048,
+                "traffic": self.rows * self.cols * 8 * (1.989540 + 0.000055) / 2.048,
                 "traffic_source": "ncu --set full on a 256 x 1e6 slice of this launch (profiles/r01_ncu_prof_fill_gauss_f64"
-                                  ".txt): dram write 1.989 GB + read 0.0002 GB for 2.048 GB algorithmic, scaled by rows",
-                "kernel": "fill_dense_tiled_kernel<double, GAUSS>", "peak_source": pk["source"],
+                                  ".txt): dram write 1.990 GB + read 0.0001 GB for 2.048 GB algorithmic, scaled by rows",
+                "kernel": "fill_dense_tiled_kernel<double, GAUSS, 8, 5>", "peak_source": pk["source"],
                 "algorithmic_bytes_per_launch": self.rows * self.cols * 8}
 
     # end to end: host (pinned) destination through the C ABI, D2H inside the timed region
