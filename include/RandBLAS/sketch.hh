@@ -193,6 +193,31 @@ inline void sketch_sparse(blas::Layout layout, blas::Op opA, blas::Op opS, int64
                      __func__);
 }
 
+// ============================================================================================ sketch_symmetric
+namespace util {
+// util.hh:128-148
+inline void require_symmetric(blas::Layout layout, const float* A, int64_t n, int64_t lda, float tol) {
+    internal::check(rb_require_symmetric_f32(internal::to_char(layout), A, n, lda, tol, nullptr), __func__);
+}
+inline void require_symmetric(blas::Layout layout, const double* A, int64_t n, int64_t lda, double tol) {
+    internal::check(rb_require_symmetric_f64(internal::to_char(layout), A, n, lda, tol, nullptr), __func__);
+}
+}  // namespace util
+// sksy.hh:159-176: B(n x d) = alpha * A * S[ro_s:, co_s:] + beta * B, A symmetric, stored as a general matrix
+template <typename SKOP, typename T = typename SKOP::scalar_t>
+inline void sketch_symmetric(blas::Layout layout, int64_t n, int64_t d, T alpha, const T* A, int64_t lda, const SKOP& S,
+                             int64_t ro_s, int64_t co_s, T beta, T* B, int64_t ldb, T sym_check_tol = 0) {
+    util::require_symmetric(layout, A, n, lda, sym_check_tol);
+    sketch_general(layout, blas::Op::NoTrans, blas::Op::NoTrans, n, d, n, alpha, A, lda, S, ro_s, co_s, beta, B, ldb);
+}
+// sksy.hh:294-312: B(d x n) = alpha * S[ro_s:, co_s:] * A + beta * B
+template <typename SKOP, typename T = typename SKOP::scalar_t>
+inline void sketch_symmetric(blas::Layout layout, int64_t d, int64_t n, T alpha, const SKOP& S, int64_t ro_s, int64_t co_s,
+                             const T* A, int64_t lda, T beta, T* B, int64_t ldb, T sym_check_tol = 0) {
+    util::require_symmetric(layout, A, n, lda, sym_check_tol);
+    sketch_general(layout, blas::Op::NoTrans, blas::Op::NoTrans, d, n, n, alpha, S, ro_s, co_s, A, lda, beta, B, ldb);
+}
+
 // ======================================================================= sparse data times dense matrix
 namespace sparse_data {
 // spmm_dispatch.hh:52-178: C(d x n) = alpha * op(A_sp[ro_a:, co_a:]) * op(B) + beta * C

@@ -152,6 +152,13 @@ int rb_coo_apply_f64(int side_left, char layout, char opS, char opA, int64_t d, 
                      const void* cols, int idx_bytes, int64_t ro_s, int64_t co_s, const double* A, int64_t lda,
                      double beta, double* B, int64_t ldb, void* stream);
 
+/* ---- symmetry check in front of sketch_symmetric ----
+ * Replaces util::require_symmetric (RandBLAS/util.hh:128-148), called by sketch_symmetric (RandBLAS/sksy.hh:159-176,
+ * 294-312) before it forwards to sketch_general: fails (RB_ERR_ARG, message naming the first offending pair) if
+ * |A(i,j) - A(j,i)| > (|A(i,j)| + |A(j,i)| + 1) * tol for some i < j; tol < 0 skips the check. Synchronises. */
+int rb_require_symmetric_f32(char layout, const float* A, int64_t n, int64_t lda, float tol, void* stream);
+int rb_require_symmetric_f64(char layout, const double* A, int64_t n, int64_t lda, double tol, void* stream);
+
 /* ---- sparse data matrix times dense matrix ----
  * Replaces sparse_data::left_spmm / right_spmm (RandBLAS/sparse_data/spmm_dispatch.hh:52-219; the kernels in
  * coo_spmm_impl.hh, csr_spmm_impl.hh, csc_spmm_impl.hh), the public entry points RandLAPACK calls on sparse data.

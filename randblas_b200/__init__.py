@@ -7,5 +7,6 @@ C++ drop-in layer under include/RandBLAS/. This Python package is a thin host-si
 from .api import (Axis, COOMatrix, CSCMatrix, CSRMatrix, DenseDist, DenseSkOp, Layout, Op, RNGState, ScalarDist,  # noqa
                   SparseDist, SparseSkOp, fill_dense, fill_dense_unpacked, fill_sparse, fill_sparse_unpacked_nosub,
                   philox_words, boxmuller_words, repeated_fisher_yates, sketch_general, sketch_sparse, sketch_vector,
-                  left_spmm, right_spmm, coo_to_csr, coo_to_csc, csr_to_coo, csc_to_coo)
+                  left_spmm, right_spmm, coo_to_csr, coo_to_csc, csr_to_coo, csc_to_coo,
+                  sketch_symmetric)
 from ._lib import RandBLASError, counter, set_option  # noqa

@@ -387,6 +387,26 @@ def _skge(left, layout, opS, opA, d, n, m, alpha, S, ro_s, co_s, A, lda, beta, B
              _ptr(B), ldb, st)
 
 
+def sketch_symmetric(layout, x, y, alpha, *rest, sym_check_tol=0):
+    """RandBLAS/sksy.hh:159-176 (A on the left: B(n x d) = alpha A S + beta B) and :294-312 (S on the left:
+    B(d x n) = alpha S A + beta B); A is an n x n symmetric matrix stored as a general one.
+
+    right: sketch_symmetric(layout, n, d, alpha, A, lda, S, ro_s, co_s, beta, B, ldb)
+    left : sketch_symmetric(layout, d, n, alpha, S, ro_s, co_s, A, lda, beta, B, ldb)
+    """
+    if _is_op(rest[0]):
+        S, ro_s, co_s, A, lda, beta, B, ldb = rest
+        d, n = int(x), int(y)
+    else:
+        A, lda, S, ro_s, co_s, beta, B, ldb = rest
+        n, d = int(x), int(y)
+    sfx, t = _sfx(_dtype_of(B))
+    call(f"rb_require_symmetric_{sfx}", "cpqq" + t + "p", layout, _ptr(A), n, int(lda), sym_check_tol, _stream(A, B))
+    if _is_op(rest[0]):
+        return sketch_general(layout, Op.NoTrans, Op.NoTrans, d, n, n, alpha, S, ro_s, co_s, A, lda, beta, B, ldb)
+    return sketch_general(layout, Op.NoTrans, Op.NoTrans, n, d, n, alpha, A, lda, S, ro_s, co_s, beta, B, ldb)
+
+
 def sketch_vector(opS, *args):
     """RandBLAS/skve.hh:141-164 (submatrix) and :233-246 (full operator).
 

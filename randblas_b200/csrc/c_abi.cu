@@ -525,6 +525,38 @@ static int coo_apply_impl(int left, char layout, char opS, char opA, int64_t d, 
     return rc;
 }
 
+// util::require_symmetric [util.hh:128-148], the check in front of sketch_symmetric [sksy.hh:159-176, 294-312]
+template <typename T>
+static int require_symmetric_impl(char layout, const T* A, int64_t n, int64_t lda, T tol, void* stream) {
+    cudaStream_t st = (cudaStream_t) stream;
+    if (tol < (T) 0) return 0;
+    RB_REQUIRE(ok_layout(layout));
+    RB_REQUIRE(n >= 0 && lda >= n);
+    if (n <= 1) return 0;
+    RB_REQUIRE(A != nullptr);
+    Staged sA;
+    int rc = sA.open(A, sizeof(T), n, n, lda, true, false, st); if (rc) return rc;
+    unsigned long long* first = (unsigned long long*) workspace(2, 8);
+    if (!first) return fail_cuda(cudaErrorMemoryAllocation, "symmetry check workspace");
+    const int64_t rs = (layout == 'C') ? 1 : lda, cs = (layout == 'C') ? lda : 1;
+    rc = launch_symmetry_check<T>((const T*) sA.dev, n, rs, cs, tol, first, st);
+    unsigned long long h = ~0ull;
+    if (!rc) {
+        if (cudaMemcpyAsync(&h, first, 8, cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess)
+            rc = fail_cuda(cudaGetLastError(), "symmetry check");
+    }
+    int rc2 = sA.close(); if (!rc) rc = rc2;
+    if (rc) return rc;
+    if (h != ~0ull) {
+        const long long i = (long long) (h / (unsigned long long) n), j = (long long) (h % (unsigned long long) n);
+        char msg[200];
+        std::snprintf(msg, sizeof msg, "Symmetry check failed. |A(%lld,%lld) - A(%lld,%lld)| exceeds the tolerance of %e.", i, j,
+                      j, i, (double) tol);
+        return fail(msg);
+    }
+    return 0;
+}
+
 // sparse data matrix applied to a dense matrix: left_spmm / right_spmm [spmm_dispatch.hh:52-219].
 //   left : C(d x n) = alpha * op(A_sp[ro_a:, co_a:])(d x m) * op(B)(m x n) + beta * C
 //   right: C(m x d) = alpha * op(B)(m x n) * op(A_sp[ro_a:, co_a:])(n x d) + beta * C
@@ -867,6 +899,9 @@ int rb_repeated_fisher_yates(int64_t k, int64_t n, int64_t r, void* samples, int
                            T beta, T* B, int64_t ldb, void* stream) {                                                  \
         return coo_apply_impl<T>(side_left, layout, opS, opA, d, n, m, alpha, S_rows, S_cols, nnz, vals, rows, cols,   \
                                  idx_bytes, ro_s, co_s, A, lda, beta, B, ldb, stream);                                 \
+    }                                                                                                                  \
+    int rb_require_symmetric_##sfx(char layout, const T* A, int64_t n, int64_t lda, T tol, void* stream) {             \
+        return require_symmetric_impl<T>(layout, A, n, lda, tol, stream);                                              \
     }                                                                                                                  \
     int rb_spmm_##sfx(int side_left, int fmt, char layout, char opA, char opB, int64_t d, int64_t n, int64_t m,         \
                       T alpha, int64_t A_rows, int64_t A_cols, int64_t nnz, const T* vals, const void* idx0,           \

@@ -111,6 +111,10 @@ int launch_coo_to_compressed(int64_t n_major, int64_t n_minor, int64_t nnz, cons
                              const void* minor, int idx_bytes, void* ovals, void* ominor, void* optr, void* omajor,
                              cudaStream_t st);
 
+// symmetry check of an n x n strided matrix (util.hh:128-148); *first_dev = i * n + j of the first violation or ~0
+template <typename T>
+int launch_symmetry_check(const T* A, int64_t n, int64_t rs, int64_t cs, T tol, unsigned long long* first_dev, cudaStream_t st);
+
 // beta pre-scale of a strided P x Q matrix (beta == 0 writes zeros without reading)
 template <typename T>
 int launch_scale(int64_t P, int64_t Q, T beta, T* C, int64_t crs, int64_t ccs, cudaStream_t st);

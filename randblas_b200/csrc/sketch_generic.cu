@@ -140,6 +140,38 @@ int launch_scale(int64_t P, int64_t Q, T beta, T* C, int64_t crs, int64_t ccs, c
     RB_CUDA(cudaGetLastError());
     return 0;
 }
+// util::require_symmetric (RandBLAS/util.hh:128-148): the lexicographically first (i, j), i < j, with
+// |A(i,j) - A(j,i)| > (|A(i,j)| + |A(j,i)| + 1) * tol, encoded as i * n + j (atomicMin); ~0 if the matrix is symmetric.
+template <typename T>
+__global__ void __launch_bounds__(256) symmetry_check_kernel(const T* __restrict__ A, int64_t n, int64_t rs, int64_t cs, T tol,
+                                                             unsigned long long* __restrict__ first) {
+    const int64_t total = n * n;
+    for (int64_t e = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t) gridDim.x * blockDim.x) {
+        const int64_t i = e / n, j = e - i * n;
+        if (j <= i) continue;
+        const T aij = A[i * rs + j * cs], aji = A[j * rs + i * cs];
+        const T viol = aij > aji ? aij - aji : aji - aij;
+        const T rel = ((aij < 0 ? -aij : aij) + (aji < 0 ? -aji : aji) + (T) 1) * tol;
+        if (viol > rel) atomicMin(first, (unsigned long long) e);
+    }
+}
+
+template <typename T>
+int launch_symmetry_check(const T* A, int64_t n, int64_t rs, int64_t cs, T tol, unsigned long long* first_dev, cudaStream_t st) {
+    RB_CUDA(cudaMemsetAsync(first_dev, 0xff, 8, st));
+    if (n > 1) {
+        int64_t grid = (n * n + 255) / 256;
+        const int64_t cap = (int64_t) sm_count() * 8;
+        if (grid > cap) grid = cap;
+        symmetry_check_kernel<T><<<(unsigned) grid, 256, 0, st>>>(A, n, rs, cs, tol, first_dev);
+        count_launch();
+        RB_CUDA(cudaGetLastError());
+    }
+    return 0;
+}
+template int launch_symmetry_check<float>(const float*, int64_t, int64_t, int64_t, float, unsigned long long*, cudaStream_t);
+template int launch_symmetry_check<double>(const double*, int64_t, int64_t, int64_t, double, unsigned long long*, cudaStream_t);
+
 template int launch_scale<float>(int64_t, int64_t, float, float*, int64_t, int64_t, cudaStream_t);
 template int launch_scale<double>(int64_t, int64_t, double, double*, int64_t, int64_t, cudaStream_t);
 

@@ -218,6 +218,18 @@ static void device_checks() {
         CHECK(ok);
     }
 
+    // --- sketch_symmetric (sksy.hh:159-176): symmetric input sketches, asymmetric input throws
+    {
+        std::vector<T> Asym(m * m), Bsym(m * d, T(0));
+        for (int64_t i = 0; i < m; ++i)
+            for (int64_t j = 0; j < m; ++j) Asym[i * m + j] = T(1) / T(1 + i + j);
+        DenseSkOp<T> Sr(DenseDist(m, d), seed);
+        sketch_symmetric(blas::Layout::RowMajor, m, d, T(1), Asym.data(), m, Sr, 0, 0, T(0), Bsym.data(), d);
+        Asym[3] += T(0.5);
+        CHECK(throws_error([&] { sketch_symmetric(blas::Layout::RowMajor, m, d, T(1), Asym.data(), m, Sr, 0, 0, T(0),
+                                                  Bsym.data(), d); }));
+    }
+
     // --- argument errors surface as RandBLAS::Error before data is touched (skge.hh:183-192)
     CHECK(throws_error([&] { sketch_general(blas::Layout::RowMajor, blas::Op::NoTrans, blas::Op::NoTrans, d, m, m, T(1), S0, 1,
                                             0, I.data(), m, T(0), B.data(), m); }));

@@ -919,6 +919,46 @@ def test_sparse_format_conversions_vs_scipy(gpu):
             assert np.array_equal(back(c3.cols), C.tocoo().col) and np.array_equal(back(c3.rows), C.indices)
 
 
+def test_sketch_symmetric(gpu):
+    """sketch_symmetric (RandBLAS/sksy.hh:159-176, 294-312): symmetry check (util.hh:128-148) then sketch_general.
+    Symmetric input: equals sketch_general; one perturbed pair: RandBLASError naming it, unless the tolerance allows it
+    or is negative (check skipped)."""
+    import randblas_b200 as rb
+    import torch
+    rng = np.random.default_rng(3)
+    n, d = 300, 40
+    M = rng.standard_normal((n, n))
+    A = torch.from_numpy((M + M.T) / 2).cuda().contiguous()
+    S = rb.DenseSkOp(rb.DenseDist(n, d), rb.RNGState(5), np.float64)
+    St = rb.DenseSkOp(rb.DenseDist(d, n), rb.RNGState(5), np.float64)
+    for lay in "CR":
+        B1 = torch.zeros(n * d, dtype=torch.float64, device="cuda")
+        B2 = torch.zeros(n * d, dtype=torch.float64, device="cuda")
+        ldb = n if lay == "C" else d
+        rb.sketch_symmetric(lay, n, d, 1.0, A.view(-1), n, S, 0, 0, 0.0, B1, ldb)
+        rb.sketch_general(lay, "N", "N", n, d, n, 1.0, A.view(-1), n, S, 0, 0, 0.0, B2, ldb)
+        assert torch.equal(B1, B2)
+        ldb = d if lay == "C" else n
+        rb.sketch_symmetric(lay, d, n, 1.0, St, 0, 0, A.view(-1), n, 0.0, B1, ldb)
+        rb.sketch_general(lay, "N", "N", d, n, n, 1.0, St, 0, 0, A.view(-1), n, 0.0, B2, ldb)
+        assert torch.equal(B1, B2)
+    Abad = A.clone()
+    Abad[7, 200] += 1e-3
+    B1 = torch.zeros(n * d, dtype=torch.float64, device="cuda")
+    with pytest.raises(rb.RandBLASError, match=r"A\(7,200\)"):
+        rb.sketch_symmetric("R", n, d, 1.0, Abad.view(-1), n, S, 0, 0, 0.0, B1, d)
+    rb.sketch_symmetric("R", n, d, 1.0, Abad.view(-1), n, S, 0, 0, 0.0, B1, d, sym_check_tol=1e-2)
+    rb.sketch_symmetric("R", n, d, 1.0, Abad.view(-1), n, S, 0, 0, 0.0, B1, d, sym_check_tol=-1.0)
+    # host matrix, float
+    Ah = ((M + M.T) / 2).astype(np.float32)
+    Bh = np.zeros(n * d, np.float32)
+    Sf = rb.DenseSkOp(rb.DenseDist(n, d), rb.RNGState(5), np.float32)
+    rb.sketch_symmetric("R", n, d, 1.0, Ah.reshape(-1), n, Sf, 0, 0, 0.0, Bh, d)
+    Ah[1, 0] += 1.0
+    with pytest.raises(rb.RandBLASError, match=r"A\(0,1\)"):
+        rb.sketch_symmetric("R", n, d, 1.0, Ah.reshape(-1), n, Sf, 0, 0, 0.0, Bh, d)
+
+
 def test_argument_errors_on_gpu(gpu):
     import randblas_b200 as rb
     import torch
