@@ -361,7 +361,7 @@ class C3DenseSketchF64(Workload):
         tf = 2.0 * self.d * self.m_local * self.n / 1e12 / (kernel_ms / 1e3)
         peak = measured_gemm_tflops(self.torch, self.torch.float64, n=6144, reps=3)
         return {"bound": "tensor", "achieved": tf, "peak": peak, "unit": "TFLOP/s", "frac": tf / peak, "traffic": None,
-                "kernel": "skge3_dmma_kernel (mma.sync m8n8k4 f64) + splitk_reduce_f64_kernel",
+                "kernel": "skge3_dmma_ws_kernel (mma.sync m8n8k4 f64, warp-specialised) + splitk_reduce_f64_kernel",
                 "peak_source": "measured in this run: cuBLAS DGEMM 6144^3 (nominal B200 FP64: 40 TFLOP/s)",
                 "algorithmic_flops_per_launch": 2.0 * self.d * self.m_local * self.n}
 

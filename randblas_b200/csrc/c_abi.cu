@@ -16,6 +16,7 @@ namespace rb {
 static thread_local std::string g_err;
 static std::atomic<int64_t> g_launches{0};
 static std::atomic<int64_t> g_dense_path{0};
+static std::atomic<int64_t> g_dmma_uniform{0};       // 1: DMMA kernel in which every warp generates and multiplies (first design)
 static std::atomic<int64_t> g_saso_fill_path{0};   // 1: warp-per-vector SASO fill kernel (the 64-bit-index path)
 static std::atomic<int64_t> g_tc_launches{0};
 static std::atomic<int64_t> g_tc_splits{0};
@@ -73,6 +74,7 @@ const double2* logf_table_device() {
 
 int64_t get_option(const char* name) {
     if (!std::strcmp(name, "dense_path")) return g_dense_path.load();
+    if (!std::strcmp(name, "dmma_uniform_warps")) return g_dmma_uniform.load();
     if (!std::strcmp(name, "saso_fill_path")) return g_saso_fill_path.load();
     if (!std::strcmp(name, "tc_splits")) return g_tc_splits.load();
     if (!std::strcmp(name, "saso_path")) return g_saso_path.load();
@@ -935,6 +937,7 @@ RB_DEF_T(double, f64)
 int rb_set_option(const char* name, int64_t value) {
     RB_REQUIRE(name != nullptr);
     if (!std::strcmp(name, "dense_path")) { g_dense_path = value; return 0; }
+    if (!std::strcmp(name, "dmma_uniform_warps")) { g_dmma_uniform = value; return 0; }
     if (!std::strcmp(name, "saso_fill_path")) { g_saso_fill_path = value; return 0; }
     if (!std::strcmp(name, "tc_splits")) { g_tc_splits = value; return 0; }
     if (!std::strcmp(name, "saso_path")) { g_saso_path = value; return 0; }
