@@ -727,8 +727,11 @@ def test_dmma_double_sketch_q_contiguous_data_vs_oracle(gpu, port):
         port.lskge3("R", "N", "N", d, n, m, dt(alpha), (Dr, Dc, fam, "L"), ctr, key, ro, co, A, lda, dt(beta), B2, n + 1)
         assert relerr(B1, B2) < 1e-12, (("left RowMajor", d, n, m, ro, co, fam), relerr(B1, B2))
         assert np.array_equal(B1.reshape(d, n + 1)[:, n], B0.reshape(d, n + 1)[:, n])
-    # both CTA tiles (64 x 256 for n > 128, 128 x 128 otherwise) in both data orientations
-    for lay, (d, n, m, fam) in [(l, c) for l in "CR" for c in ((300, 100, 1200, "G"), (300, 260, 1200, "U"))]:
+    # both CTA tiles (64 x 256 for n > 128, 128 x 128 otherwise) in both data orientations, for the warp-specialised
+    # kernel (default) and the first design (every warp generates and multiplies)
+    for uniform_warps, lay, (d, n, m, fam) in [(u, l, c) for u in (0, 1) for l in "CR"
+                                               for c in ((300, 100, 1200, "G"), (300, 260, 1200, "U"))]:
+        rb.set_option("dmma_uniform_warps", uniform_warps)
         lda = (m if lay == "C" else n) + 2
         A = rng.standard_normal((n if lay == "C" else m) * lda)
         ldb = (d if lay == "C" else n) + 1
@@ -738,7 +741,8 @@ def test_dmma_double_sketch_q_contiguous_data_vs_oracle(gpu, port):
         gpu.lskge3(lay, "N", "N", d, n, m, dt(0.75), (d, m, fam, "L"), ctr, key, 0, 0, A, lda, dt(0.5), B1, ldb)
         assert rb.counter("tensor_core_launches") == before + 1, (lay, d, n, m)
         port.lskge3(lay, "N", "N", d, n, m, dt(0.75), (d, m, fam, "L"), ctr, key, 0, 0, A, lda, dt(0.5), B2, ldb)
-        assert relerr(B1, B2) < 1e-12, ((lay, d, n, m, fam), relerr(B1, B2))
+        assert relerr(B1, B2) < 1e-12, ((uniform_warps, lay, d, n, m, fam), relerr(B1, B2))
+    rb.set_option("dmma_uniform_warps", 0)
     for (m, d, n, Dr, Dc, ro, co, fam, alpha, beta) in [(2048, 128, 1024, 1024, 128, 0, 0, "G", 1.0, 0.0),
                                                          (1501, 100, 977, 1000, 120, 5, 3, "U", -0.5, 2.0)]:
         lda = m + (m % 2)
