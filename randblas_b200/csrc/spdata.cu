@@ -126,6 +126,17 @@ __global__ void __launch_bounds__(256) spdata_colowner_kernel(const SpDataProble
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
+// the same with an L2 eviction-priority hint (evict_last: the slab of C that is being reduced into should stay in L2)
+__device__ __forceinline__ unsigned long long l2_evict_last_policy() {
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void red_add_v4_hint(float* addr, float a, float b, float c, float d, unsigned long long pol) {
+    asm volatile("red.global.add.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d),
+                 "l"(pol)
+                 : "memory");
+}
 
 // Input-stationary kernel: see the file header. Lane l of a warp owns rows i0..i0+3 of C, i0 = 128*ib + 4*l - ri.
 // u_along_k = 1: X[i, k] = lane (u0+k)%4 of block (v0+i, (u0+k)/4); k-groups start at k = 4g - (u0 & 3).
@@ -142,6 +153,7 @@ __global__ void __launch_bounds__(256) spdata_kgroup_kernel(const SpDataProblem<
     const int64_t nwarps = ((int64_t) gridDim.x * blockDim.x) >> 5;
     const int rk = u_along_k ? (int) (p.u0 & 3) : 0;
     const int ri = u_along_k ? 0 : (int) (p.u0 & 3);
+    const unsigned long long pol = l2_evict_last_policy();
     for (int ib = 0; ib < n_iblocks; ++ib) {
         const int64_t i0 = (int64_t) ib * 128 + 4 * lane - ri;
         const bool i_live = (i0 + 3 >= 0) && (i0 < p.P);
@@ -198,7 +210,7 @@ __global__ void __launch_bounds__(256) spdata_kgroup_kernel(const SpDataProblem<
                         if (q < 0 || !i_live) continue;      // outside the window of A_sp
                         T* c = p.C + (int64_t) q * p.ccs + i0 * p.crs;
                         if constexpr (VEC4) {
-                            red_add_v4((float*) c, a * s[0][kk], a * s[1][kk], a * s[2][kk], a * s[3][kk]);
+                            red_add_v4_hint((float*) c, a * s[0][kk], a * s[1][kk], a * s[2][kk], a * s[3][kk], pol);
                         } else {
 #pragma unroll
                             for (int ii = 0; ii < 4; ++ii)
