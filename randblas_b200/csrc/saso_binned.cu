@@ -106,6 +106,7 @@ __global__ void __launch_bounds__(BIN_THREADS) saso_bin_kernel(const BinArgs a) 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, sub = lane & (G - 1);
     constexpr int VPP = BIN_THREADS / G;               // columns per pass
     const int per_thr = a.Prows / BIN_THREADS;         // counters scanned per thread (Prows is a multiple of 1024)
+    const uint32_t dv = sub < a.k ? a.dim_major - (uint32_t) sub : 1u, dm = fastmod_magic(dv);
 
     for (int64_t c = blockIdx.x; c < a.nchunks; c += gridDim.x) {
         const int64_t v0 = c * a.Kc;
@@ -119,12 +120,13 @@ __global__ void __launch_bounds__(BIN_THREADS) saso_bin_kernel(const BinArgs a) 
             uint32_t piv = 0, w1 = 0;
             if (live) {
                 const uint4 w = philox4x32_10(ctr_add(a.ctr, (uint64_t) ((a.vec_lo + v0 + vl) * a.k + sub)), a.key);
-                piv = (uint32_t) sub + w.x % (a.dim_major - (uint32_t) sub);      // sparse_skops.hh:78
+                piv = (uint32_t) sub + fastmod(w.x, dv, dm);                      // sparse_skops.hh:78
                 w1 = w.y;
             }
             // value at position piv after swaps 0..sub-1 of an identity permutation: walk the swaps backwards
             uint32_t pos = piv;
-            for (int t = a.k - 2; t >= 0; --t) {
+#pragma unroll
+            for (int t = G - 2; t >= 0; --t) {
                 const uint32_t pt = __shfl_sync(0xffffffffu, piv, t, G);
                 if (t < sub) {
                     if (pos == (uint32_t) t) pos = pt;

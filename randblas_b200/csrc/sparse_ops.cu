@@ -105,18 +105,22 @@ __global__ void __launch_bounds__(256) saso_fill_group_kernel(Ctr128 ctr, Philox
     const int lane = threadIdx.x & 31, sub = lane & (G - 1);
     const int64_t warp = ((int64_t) blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t) gridDim.x * blockDim.x) >> 5;
+    // the divisor of step `sub` is the same for every vector this lane works on
+    const uint32_t dv = sub < k ? dim_major - (uint32_t) sub : 1u, dm = fastmod_magic(dv);
     for (int64_t wv = warp * VPW; wv < dim_minor; wv += nwarps * VPW) {
         const int64_t v = wv + lane / G;
         const bool live = v < dim_minor && sub < k;
         uint32_t piv = 0, w1 = 0;
         if (live) {
             const uint4 w = philox4x32_10(ctr_add(ctr, (uint64_t) (v * k + sub)), key);
-            piv = (uint32_t) sub + w.x % (dim_major - (uint32_t) sub);      // sparse_skops.hh:78
+            piv = (uint32_t) sub + fastmod(w.x, dv, dm);                    // sparse_skops.hh:78
             w1 = w.y;
         }
         // value at position piv after swaps 0..sub-1 of an identity permutation: walk the swaps backwards
+        // (steps t >= sub do not apply to this lane, so the walk may start at G - 2 >= k - 2 and unroll)
         uint32_t pos = piv;
-        for (int t = k - 2; t >= 0; --t) {
+#pragma unroll
+        for (int t = G - 2; t >= 0; --t) {
             const uint32_t pt = __shfl_sync(0xffffffffu, piv, t, G);
             if (t < sub) {
                 if (pos == (uint32_t) t) pos = pt;
