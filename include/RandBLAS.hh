@@ -6,3 +6,4 @@
 #include "RandBLAS/sparse_skops.hh"
 #include "RandBLAS/sparse_data.hh"
 #include "RandBLAS/sketch.hh"
+#include "RandBLAS/util.hh"

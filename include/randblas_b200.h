@@ -99,6 +99,24 @@ int rb_fill_sparse_laso(int64_t D_rows, int64_t D_cols, int64_t vec_nnz, const u
 int rb_repeated_fisher_yates(int64_t k, int64_t n, int64_t r, void* samples, int idx_bytes, const uint32_t ctr[4],
                              const uint32_t key[2], uint32_t next_ctr[4], void* stream);
 
+/* ---- index-sampling utilities ----
+ * rb_sample_indices_iid_uniform replaces RandBLAS::sample_indices_iid_uniform<T, sint_t, WriteRademachers>
+ * (RandBLAS/util.hh:515-560): k samples from the uniform distribution over {0..n-1} into samples[k] (idx_bytes in
+ * {4, 8}); rademachers[k] (val_bytes in {4, 8}) receives the signs, or is NULL for the overload without them
+ * (:556-559; it then uses one Philox word per sample instead of two). next_ctr = ctr + ceil(k / (2 or 4)).
+ * rb_sample_indices_iid replaces RandBLAS::sample_indices_iid<T, sint_t> (:490-513): k samples from the CDF cdf[n]
+ * (val_bytes in {4, 8}) by std::lower_bound semantics; next_ctr = ctr + ceil(k / 4).
+ * rb_weights_to_cdf_* replaces RandBLAS::weights_to_cdf<T> (:459-473): w[n] overwritten in place by the normalised
+ * running sum of max(w, 0) (summed serially in T, like the reference); RB_ERR_ARG if a weight is below
+ * error_if_below or the total is below sqrt(n) * eps (the entries before the failing one have been overwritten, as in
+ * the reference). Synchronises. */
+int rb_sample_indices_iid_uniform(int64_t n, int64_t k, void* samples, int idx_bytes, void* rademachers, int val_bytes,
+                                  const uint32_t ctr[4], const uint32_t key[2], uint32_t next_ctr[4], void* stream);
+int rb_sample_indices_iid(int64_t n, const void* cdf, int val_bytes, int64_t k, void* samples, int idx_bytes,
+                          const uint32_t ctr[4], const uint32_t key[2], uint32_t next_ctr[4], void* stream);
+int rb_weights_to_cdf_f32(int64_t n, float* w, float error_if_below, void* stream);
+int rb_weights_to_cdf_f64(int64_t n, double* w, double error_if_below, void* stream);
+
 /* ---- K2: dense operator applied to dense data ----
  * Replaces dense::lskge3 (RandBLAS/skge.hh:154-202) / dense::rskge3 (:307-355), i.e. the DenseSkOp
  * overloads of sketch_general (:799-821, :947-968, :1073-1097, :1175-1199) and sketch_vector (skve.hh:141-164).

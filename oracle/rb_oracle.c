@@ -12,6 +12,7 @@
  */
 #define _GNU_SOURCE
 #include "rb_oracle.h"
+#include <float.h>
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
@@ -242,6 +243,100 @@ static int fisher_yates(const uint32_t ctr[4], const uint32_t key[2], int64_t ve
 int rbo_repeated_fisher_yates(int64_t k, int64_t n, int64_t r, void* samples, int idx_bytes, const uint32_t ctr[4],
                               const uint32_t key[2], uint32_t next_ctr[4]) {
     return fisher_yates(ctr, key, k, n, r, samples, NULL, idx_bytes, NULL, 0, next_ctr);
+}
+
+/* ---- index-sampling utilities, RandBLAS/util.hh:459-560 (serial restatement of the reference's loops) ---- */
+
+/* sample_indices_iid_uniform<T, sint_t, WriteRademachers>, util.hh:515-547: one stream of Philox blocks from `ctr`;
+ * len_c = 4 words per block, rounded down to a multiple of two when Rademachers are written (:521-525). */
+int rbo_sample_indices_iid_uniform(int64_t n, int64_t k, void* samples, int idx_bytes, void* rademachers, int val_bytes,
+                                   const uint32_t ctr[4], const uint32_t key[2], uint32_t next_ctr[4]) {
+    uint32_t c[4], w[4];
+    memcpy(c, ctr, 16);
+    rbo_philox4x32_10(c, key, w);
+    const int len_c = 4;                       /* 2 * (4 / 2) with Rademachers: also 4 */
+    int rv_index = 0;
+    const double dN = (double) n;
+    for (int64_t i = 0; i < k; ++i) {
+        const double u01 = ((double) rbo_uneg11_f32(w[rv_index]) + 1.0) / 2.0;      /* uneg11_to_u01<double>, :475-478 */
+        if (idx_bytes == 4) ((int32_t*) samples)[i] = (int32_t) ((double) (int32_t) dN * u01);   /* :532-533 */
+        else ((int64_t*) samples)[i] = (int64_t) ((double) (int64_t) dN * u01);
+        rv_index += 1;
+        if (rademachers) {
+            const double r = (rbo_uneg11_f32(w[rv_index]) >= 0) ? 1.0 : -1.0;       /* :536 */
+            store_val(rademachers, val_bytes, i, r);
+            rv_index += 1;
+        }
+        if (rv_index == len_c) {
+            rbo_ctr_incr(c, 1);
+            rbo_philox4x32_10(c, key, w);
+            rv_index = 0;
+        }
+    }
+    if (0 < rv_index) rbo_ctr_incr(c, 1);
+    if (next_ctr) memcpy(next_ctr, c, 16);
+    return 0;
+}
+
+/* sample_indices_iid<T, sint_t>, util.hh:490-513: u = ((T) x + 1) / 2 in T, std::lower_bound on the CDF */
+int rbo_sample_indices_iid(int64_t n, const void* cdf, int val_bytes, int64_t k, void* samples, int idx_bytes,
+                           const uint32_t ctr[4], const uint32_t key[2], uint32_t next_ctr[4]) {
+    uint32_t c[4], w[4];
+    memcpy(c, ctr, 16);
+    rbo_philox4x32_10(c, key, w);
+    int rv_index = 0;
+    for (int64_t i = 0; i < k; ++i) {
+        int64_t lo = 0, len = n;
+        if (val_bytes == 4) {
+            const float u = (rbo_uneg11_f32(w[rv_index]) + 1.0f) / 2.0f;
+            const float* f = (const float*) cdf;
+            while (len > 0) { int64_t h = len / 2; if (f[lo + h] < u) { lo += h + 1; len -= h + 1; } else len = h; }
+        } else {
+            const double u = ((double) rbo_uneg11_f32(w[rv_index]) + 1.0) / 2.0;
+            const double* f = (const double*) cdf;
+            while (len > 0) { int64_t h = len / 2; if (f[lo + h] < u) { lo += h + 1; len -= h + 1; } else len = h; }
+        }
+        store_idx(samples, idx_bytes, i, lo);
+        rv_index += 1;
+        if (rv_index == 4) {
+            rbo_ctr_incr(c, 1);
+            rbo_philox4x32_10(c, key, w);
+            rv_index = 0;
+        }
+    }
+    if (0 < rv_index) rbo_ctr_incr(c, 1);
+    if (next_ctr) memcpy(next_ctr, c, 16);
+    return 0;
+}
+
+/* weights_to_cdf<T>, util.hh:459-473. Returns 1 where the reference throws (w keeps what had been written). */
+int rbo_weights_to_cdf_f32(int64_t n, float* w, float error_if_below) {
+    float sum = 0.0f;
+    for (int64_t i = 0; i < n; ++i) {
+        float val = w[i];
+        if (!(val >= error_if_below)) return 1;
+        val = (val < 0.0f) ? 0.0f : val;
+        sum += val;
+        w[i] = sum;
+    }
+    if (!(sum >= ((float) sqrt((double) n)) * FLT_EPSILON)) return 1;
+    const float a = 1.0f / sum;
+    for (int64_t i = 0; i < n; ++i) w[i] = w[i] * a;        /* blas::scal */
+    return 0;
+}
+int rbo_weights_to_cdf_f64(int64_t n, double* w, double error_if_below) {
+    double sum = 0.0;
+    for (int64_t i = 0; i < n; ++i) {
+        double val = w[i];
+        if (!(val >= error_if_below)) return 1;
+        val = (val < 0.0) ? 0.0 : val;
+        sum += val;
+        w[i] = sum;
+    }
+    if (!(sum >= ((double) sqrt((double) n)) * DBL_EPSILON)) return 1;
+    const double a = 1.0 / sum;
+    for (int64_t i = 0; i < n; ++i) w[i] = w[i] * a;
+    return 0;
 }
 
 /* fill_sparse_unpacked_nosub, SASO branch, RandBLAS/sparse_skops.hh:515-533: the short-axis index

@@ -172,6 +172,32 @@ static int rfy_t(int64_t k, int64_t n, int64_t r, sint_t* samples, const uint32_
     RBREF_CATCH
 }
 
+// index-sampling utilities, RandBLAS/util.hh:459-560
+template <typename T, typename sint_t>
+static int iid_uniform_t(int64_t n, int64_t k, sint_t* samples, T* rad, const uint32_t* ctr, const uint32_t* key,
+                         uint32_t* next_ctr) {
+    RBREF_TRY
+    auto st = mk_state(ctr, key);
+    auto next = rad ? RandBLAS::sample_indices_iid_uniform<T, sint_t, true>(n, k, samples, rad, st)
+                    : RandBLAS::sample_indices_iid_uniform(n, k, samples, st);
+    put_ctr(next, next_ctr);
+    RBREF_CATCH
+}
+template <typename T, typename sint_t>
+static int iid_t(int64_t n, const T* cdf, int64_t k, sint_t* samples, const uint32_t* ctr, const uint32_t* key,
+                 uint32_t* next_ctr) {
+    RBREF_TRY
+    auto next = RandBLAS::sample_indices_iid(n, cdf, k, samples, mk_state(ctr, key));
+    put_ctr(next, next_ctr);
+    RBREF_CATCH
+}
+template <typename T>
+static int w2cdf_t(int64_t n, T* w, T error_if_below) {
+    RBREF_TRY
+    RandBLAS::weights_to_cdf(n, w, error_if_below);
+    RBREF_CATCH
+}
+
 // dense operator, left/right sketch. prefill != 0 => fill_dense(S) first (exercises the buff != nullptr path)
 template <typename T>
 static int skge_dense_t(int side_left, char layout, char op1, char op2, int64_t d, int64_t n, int64_t m, T alpha,
@@ -305,6 +331,17 @@ extern "C" {
 
 DEF_FOR_T(float, f32)
 DEF_FOR_T(double, f64)
+
+int rbref_sample_indices_iid_uniform_f32_i32(int64_t n, int64_t k, int32_t* s, float* rad, const uint32_t* ctr, const uint32_t* key, uint32_t* nx) { return iid_uniform_t<float, int32_t>(n, k, s, rad, ctr, key, nx); }
+int rbref_sample_indices_iid_uniform_f32_i64(int64_t n, int64_t k, int64_t* s, float* rad, const uint32_t* ctr, const uint32_t* key, uint32_t* nx) { return iid_uniform_t<float, int64_t>(n, k, s, rad, ctr, key, nx); }
+int rbref_sample_indices_iid_uniform_f64_i32(int64_t n, int64_t k, int32_t* s, double* rad, const uint32_t* ctr, const uint32_t* key, uint32_t* nx) { return iid_uniform_t<double, int32_t>(n, k, s, rad, ctr, key, nx); }
+int rbref_sample_indices_iid_uniform_f64_i64(int64_t n, int64_t k, int64_t* s, double* rad, const uint32_t* ctr, const uint32_t* key, uint32_t* nx) { return iid_uniform_t<double, int64_t>(n, k, s, rad, ctr, key, nx); }
+int rbref_sample_indices_iid_f32_i32(int64_t n, const float* cdf, int64_t k, int32_t* s, const uint32_t* ctr, const uint32_t* key, uint32_t* nx) { return iid_t<float, int32_t>(n, cdf, k, s, ctr, key, nx); }
+int rbref_sample_indices_iid_f32_i64(int64_t n, const float* cdf, int64_t k, int64_t* s, const uint32_t* ctr, const uint32_t* key, uint32_t* nx) { return iid_t<float, int64_t>(n, cdf, k, s, ctr, key, nx); }
+int rbref_sample_indices_iid_f64_i32(int64_t n, const double* cdf, int64_t k, int32_t* s, const uint32_t* ctr, const uint32_t* key, uint32_t* nx) { return iid_t<double, int32_t>(n, cdf, k, s, ctr, key, nx); }
+int rbref_sample_indices_iid_f64_i64(int64_t n, const double* cdf, int64_t k, int64_t* s, const uint32_t* ctr, const uint32_t* key, uint32_t* nx) { return iid_t<double, int64_t>(n, cdf, k, s, ctr, key, nx); }
+int rbref_weights_to_cdf_f32(int64_t n, float* w, float eib) { return w2cdf_t<float>(n, w, eib); }
+int rbref_weights_to_cdf_f64(int64_t n, double* w, double eib) { return w2cdf_t<double>(n, w, eib); }
 
 int rbref_repeated_fisher_yates_i32(int64_t k, int64_t n, int64_t r, int32_t* samples, const uint32_t* ctr,
                                     const uint32_t* key, uint32_t* next_ctr) {

@@ -313,6 +313,35 @@ def repeated_fisher_yates(k, n, r, samples, state):
     return RNGState(counter=list(nxt), key=state.key)
 
 
+def sample_indices_iid_uniform(n, k, samples, state, rademachers=None):
+    """RandBLAS/util.hh:515-560: `sample_indices_iid_uniform(n, k, samples, state)` and, with `rademachers`, the
+    `<T, sint_t, WriteRademachers = true>` form. Returns the advanced RNGState."""
+    nxt = (ctypes.c_uint32 * 4)()
+    vb = np.dtype(_dtype_of(rademachers)).itemsize if rademachers is not None else 4
+    call("rb_sample_indices_iid_uniform", "qqpipipppp", int(n), int(k), _ptr(samples),
+         np.dtype(_dtype_of(samples)).itemsize, _ptr(rademachers), vb, _addr(state._c()), _addr(state._k()), _addr(nxt),
+         _stream(samples, rademachers))
+    return RNGState(counter=list(nxt), key=state.key)
+
+
+def sample_indices_iid(n, cdf, k, samples, state):
+    """RandBLAS/util.hh:490-513. Returns the advanced RNGState."""
+    nxt = (ctypes.c_uint32 * 4)()
+    call("rb_sample_indices_iid", "qpiqpipppp", int(n), _ptr(cdf), np.dtype(_dtype_of(cdf)).itemsize, int(k),
+         _ptr(samples), np.dtype(_dtype_of(samples)).itemsize, _addr(state._c()), _addr(state._k()), _addr(nxt),
+         _stream(samples, cdf))
+    return RNGState(counter=list(nxt), key=state.key)
+
+
+def weights_to_cdf(n, w, error_if_below=None):
+    """RandBLAS/util.hh:459-473 (default error_if_below = -sqrt(epsilon<T>), :440-443). In place."""
+    dt = np.dtype(_dtype_of(w))
+    if error_if_below is None:
+        error_if_below = -float(np.sqrt(np.finfo(dt).eps).astype(dt))
+    sfx, t = _sfx(dt)
+    call(f"rb_weights_to_cdf_{sfx}", "qp" + t + "p", int(n), _ptr(w), float(error_if_below), _stream(w))
+
+
 def _is_op(x):
     return isinstance(x, (DenseSkOp, SparseSkOp))
 

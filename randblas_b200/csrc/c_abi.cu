@@ -672,6 +672,20 @@ static int sksp3_impl(bool left, int fmt, char layout, char opS, char opA, int64
 
 using namespace rb;
 
+// weights_to_cdf<T> (util.hh:459-473). The prefix written before a failing weight stays in w, as in the reference.
+template <typename T>
+static int weights_to_cdf_impl(int64_t n, T* w, T error_if_below, void* stream) {
+    cudaStream_t st = (cudaStream_t) stream;
+    RB_REQUIRE(n >= 0);
+    if (n == 0) return 0;
+    RB_REQUIRE(w != nullptr);
+    Staged sw;
+    int rc = sw.open(w, sizeof(T), 1, n, n, true, true, st); if (rc) return rc;
+    rc = launch_weights_to_cdf<T>(n, (T*) sw.dev, error_if_below, st);
+    int rc2 = sw.close(); if (!rc) rc = rc2;
+    return rc;
+}
+
 extern "C" {
 
 const char* rb_last_error(void) { return g_err.c_str(); }
@@ -866,6 +880,59 @@ int rb_repeated_fisher_yates(int64_t k, int64_t n, int64_t r, void* samples, int
     rc = launch_saso(c, PhiloxKey{key[0], key[1]}, k, n, r, ss.dev, nullptr, idx_bytes, nullptr, 4, st);
     int rc2 = ss.close();
     return rc ? rc : rc2;
+}
+
+// sample_indices_iid_uniform<T, sint_t, WriteRademachers> (util.hh:515-560)
+int rb_sample_indices_iid_uniform(int64_t n, int64_t k, void* samples, int idx_bytes, void* rademachers, int val_bytes,
+                                  const uint32_t ctr[4], const uint32_t key[2], uint32_t next_ctr[4], void* stream) {
+    cudaStream_t st = (cudaStream_t) stream;
+    RB_REQUIRE(n >= 0 && k >= 0);
+    RB_REQUIRE(idx_bytes == 4 || idx_bytes == 8);
+    RB_REQUIRE(rademachers == nullptr || val_bytes == 4 || val_bytes == 8);
+    RB_REQUIRE(ctr != nullptr && key != nullptr);
+    if (idx_bytes == 4) RB_REQUIRE(n <= 2147483647LL);
+    const Ctr128 c = load_ctr(ctr);
+    const int64_t spb = rademachers ? 2 : 4;                       // util.hh:521-525
+    store_ctr(ctr_add(c, (uint64_t) ((k + spb - 1) / spb)), next_ctr);   // one incr per block used, util.hh:538-544
+    if (k == 0) return 0;
+    RB_REQUIRE(samples != nullptr);
+    Staged ss, sr;
+    int rc = ss.open(samples, (size_t) idx_bytes, 1, k, k, false, true, st); if (rc) return rc;
+    rc = sr.open(rademachers, (size_t) (rademachers ? val_bytes : 4), 1, k, k, false, true, st); if (rc) return rc;
+    rc = launch_sample_indices_iid_uniform(c, PhiloxKey{key[0], key[1]}, n, k, ss.dev, idx_bytes, sr.dev, val_bytes, st);
+    int rc2 = ss.close(); if (!rc) rc = rc2;
+    rc2 = sr.close(); if (!rc) rc = rc2;
+    return rc;
+}
+
+// sample_indices_iid<T, sint_t> (util.hh:490-513)
+int rb_sample_indices_iid(int64_t n, const void* cdf, int val_bytes, int64_t k, void* samples, int idx_bytes,
+                          const uint32_t ctr[4], const uint32_t key[2], uint32_t next_ctr[4], void* stream) {
+    cudaStream_t st = (cudaStream_t) stream;
+    RB_REQUIRE(n >= 0 && k >= 0);
+    RB_REQUIRE(idx_bytes == 4 || idx_bytes == 8);
+    RB_REQUIRE(val_bytes == 4 || val_bytes == 8);
+    RB_REQUIRE(ctr != nullptr && key != nullptr);
+    if (idx_bytes == 4) RB_REQUIRE(n <= 2147483647LL);
+    const Ctr128 c = load_ctr(ctr);
+    store_ctr(ctr_add(c, (uint64_t) ((k + 3) / 4)), next_ctr);     // util.hh:505-511
+    if (k == 0) return 0;
+    RB_REQUIRE(samples != nullptr);
+    RB_REQUIRE(n == 0 || cdf != nullptr);
+    Staged sc, ss;
+    int rc = sc.open(cdf, (size_t) val_bytes, 1, n, n, true, false, st); if (rc) return rc;
+    rc = ss.open(samples, (size_t) idx_bytes, 1, k, k, false, true, st); if (rc) return rc;
+    rc = launch_sample_indices_iid(c, PhiloxKey{key[0], key[1]}, n, sc.dev, val_bytes, k, ss.dev, idx_bytes, st);
+    int rc2 = ss.close(); if (!rc) rc = rc2;
+    rc2 = sc.close(); if (!rc) rc = rc2;
+    return rc;
+}
+
+int rb_weights_to_cdf_f32(int64_t n, float* w, float error_if_below, void* stream) {
+    return weights_to_cdf_impl<float>(n, w, error_if_below, stream);
+}
+int rb_weights_to_cdf_f64(int64_t n, double* w, double error_if_below, void* stream) {
+    return weights_to_cdf_impl<double>(n, w, error_if_below, stream);
 }
 
 #define RB_DEF_T(T, sfx)                                                                                               \

@@ -27,6 +27,14 @@ int launch_saso(Ctr128 ctr, PhiloxKey key, int64_t vec_nnz, int64_t dim_major, i
 int launch_laso(Ctr128 ctr, PhiloxKey key, int64_t vec_nnz, int64_t dim_major, int64_t dim_minor, void* idxs_long,
                 void* idxs_short, int idx_bytes, void* vals, int val_bytes, int64_t* nnz_host, cudaStream_t st);
 
+// Index-sampling utilities (sampling.cu): RandBLAS/util.hh:459-560. rademachers may be null.
+int launch_sample_indices_iid_uniform(Ctr128 ctr, PhiloxKey key, int64_t n, int64_t k, void* samples, int idx_bytes,
+                                      void* rademachers, int val_bytes, cudaStream_t st);
+int launch_sample_indices_iid(Ctr128 ctr, PhiloxKey key, int64_t n, const void* cdf, int val_bytes, int64_t k,
+                              void* samples, int idx_bytes, cudaStream_t st);
+template <typename T>
+int launch_weights_to_cdf(int64_t n, T* w, T error_if_below, cudaStream_t st);   // synchronises
+
 // Canonical dense problem: C(P x Q) = alpha * X(P x K) * Y(K x Q) + beta * C where X = op(S window) and
 // Y, C are strided views (element (k,j) of Y at Y + k*yrs + j*ycs; element (i,j) of C at C + i*crs + j*ccs).
 // Right sketches are mapped to this form by transposition in the C-ABI layer.

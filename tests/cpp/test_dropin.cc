@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <limits>
 #include <set>
 #include <vector>
 #include "RandBLAS.hh"
@@ -228,6 +229,59 @@ static void device_checks() {
         Asym[3] += T(0.5);
         CHECK(throws_error([&] { sketch_symmetric(blas::Layout::RowMajor, m, d, T(1), Asym.data(), m, Sr, 0, 0, T(0),
                                                   Bsym.data(), d); }));
+    }
+
+    // --- index sampling (util.hh:459-560), written like test/test_basic_rng/test_discrete.cc:72-212
+    {
+        const int64_t N = 100, ns = N * N;
+        std::vector<int64_t> samples(ns, -1);
+        RNGState<> st(0);
+        sample_indices_iid_uniform(N, ns, samples.data(), st);
+        ok = true;
+        for (auto v : samples) ok = ok && v >= 0 && v < N;
+        CHECK(ok);                                                  // test_iid_uniform_smoke
+        // degenerate distributions (test_discrete.cc:136-167)
+        std::vector<float> cdf(N, 0.0f);
+        for (int i = 0; i < N; i += 2) cdf[i] = 1.0f / ((float) i + 1.0f);
+        cdf[10] = 0.0f;
+        weights_to_cdf(N, cdf.data());
+        CHECK(cdf[N - 1] == 1.0f || cdf[N - 2] == 1.0f);
+        sample_indices_iid(N, cdf.data(), ns, samples.data(), st);
+        ok = true;
+        for (auto v : samples) ok = ok && !(v == 10 || v % 2 == 1);
+        CHECK(ok);
+        std::fill(cdf.begin(), cdf.end(), 0.0f);
+        cdf[17] = 99.0f;
+        cdf[3] = -std::numeric_limits<float>::epsilon() / 10;       // clipped without error
+        weights_to_cdf(N, cdf.data());
+        sample_indices_iid(N, cdf.data(), ns, samples.data(), st);
+        ok = true;
+        for (auto v : samples) ok = ok && v == 17;
+        CHECK(ok);
+        cdf[5] = -1.0f;
+        CHECK(throws_error([&] { weights_to_cdf(N, cdf.data()); }));   // a weight below error_if_below (util.hh:465)
+        // state updates (test_discrete.cc:169-212)
+        RNGState<> sd;
+        sd.counter.incr(3456);
+        std::vector<int> un(34);
+        auto s1 = sample_indices_iid_uniform(40, 17, un.data(), sd);
+        auto s2 = sample_indices_iid_uniform(40, 17, un.data(), s1);
+        auto t1 = sample_indices_iid_uniform(40, 34, un.data(), sd);
+        CHECK(s2.counter.v[0] - 3456 == 2 * (s1.counter.v[0] - 3456));
+        CHECK(t1.counter.v[0] <= s2.counter.v[0] && s2.counter.v[0] <= t1.counter.v[0] + 1);
+        std::vector<float> ucdf(29, 1.0f);
+        weights_to_cdf(29, ucdf.data());
+        auto c1 = sample_indices_iid(29, ucdf.data(), 13, un.data(), sd);
+        auto c2 = sample_indices_iid(29, ucdf.data(), 13, un.data(), c1);
+        auto ct = sample_indices_iid(29, ucdf.data(), 26, un.data(), sd);
+        CHECK(c2.counter.v[0] - 3456 == 2 * (c1.counter.v[0] - 3456));
+        CHECK(ct.counter.v[0] <= c2.counter.v[0] && c2.counter.v[0] <= ct.counter.v[0] + 1);
+        // Rademacher form: signs are +-1, two words per sample
+        std::vector<T> rad(34);
+        auto r1 = sample_indices_iid_uniform<T, int, true>(40, 34, un.data(), rad.data(), sd);
+        ok = r1.counter.v[0] == 3456u + 17u;
+        for (auto v : rad) ok = ok && (v == T(1) || v == T(-1));
+        CHECK(ok);
     }
 
     // --- argument errors surface as RandBLAS::Error before data is touched (skge.hh:183-192)

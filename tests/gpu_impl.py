@@ -66,6 +66,35 @@ class Gpu:
         self._out(t, s)
         return s, np.array(nxt.counter, np.uint32)
 
+    # --- index-sampling utilities (RandBLAS/util.hh:459-560) ---
+    def sample_indices_iid_uniform(self, n, k, ctr, key, idx_dtype=np.int64, rad_dtype=None):
+        s = np.full(max(k, 1), -1, idx_dtype)
+        r = None if rad_dtype is None else np.zeros(max(k, 1), rad_dtype)
+        ts, tr = self._in(s), (None if r is None else self._in(r))
+        nxt = rb.sample_indices_iid_uniform(n, k, ts, state(ctr, key), tr)
+        self._out(ts, s)
+        if r is not None:
+            self._out(tr, r)
+        return s[:k], (None if r is None else r[:k]), np.array(nxt.counter, np.uint32)
+
+    def sample_indices_iid(self, n, cdf, k, ctr, key, idx_dtype=np.int64):
+        s = np.full(max(k, 1), -1, idx_dtype)
+        ts, tc = self._in(s), self._in(np.ascontiguousarray(cdf))
+        nxt = rb.sample_indices_iid(n, tc, k, ts, state(ctr, key))
+        self._out(ts, s)
+        return s[:k], np.array(nxt.counter, np.uint32)
+
+    def weights_to_cdf(self, w, error_if_below=None):
+        w = np.ascontiguousarray(w).copy()
+        t = self._in(w)
+        ok = True
+        try:
+            rb.weights_to_cdf(len(w), t, error_if_below)
+        except rb.RandBLASError:
+            ok = False
+        self._out(t, w)
+        return w, ok
+
     def _dense_op(self, dist, ctr, key, dtype, prefill):
         S = rb.DenseSkOp(rb.DenseDist(*dist), state(ctr, key), dtype)
         if prefill:

@@ -197,6 +197,34 @@ class Port(_Base):
         self._check(rc, "fill_sparse")
         return vals, rows, cols, int(nnz[0]), nxt
 
+    # --- index-sampling utilities (RandBLAS/util.hh:459-560) ---
+    def sample_indices_iid_uniform(self, n, k, ctr, key, idx_dtype=np.int64, rad_dtype=None):
+        samples = np.full(max(k, 1), -1, idx_dtype)[:k]
+        rad = None if rad_dtype is None else np.zeros(max(k, 1), rad_dtype)[:k]
+        nxt = np.zeros(4, np.uint32)
+        self._check(_call(self.lib.rbo_sample_indices_iid_uniform, "qqpipippp",
+                          (n, k, samples, samples.itemsize, rad, 4 if rad is None else rad.itemsize, u32(ctr), u32(key),
+                           nxt)), "sample_indices_iid_uniform")
+        return samples, rad, nxt
+
+    def sample_indices_iid(self, n, cdf, k, ctr, key, idx_dtype=np.int64):
+        samples = np.full(max(k, 1), -1, idx_dtype)[:k]
+        nxt = np.zeros(4, np.uint32)
+        cdf = np.ascontiguousarray(cdf)
+        self._check(_call(self.lib.rbo_sample_indices_iid, "qpiqpippp",
+                          (n, cdf, cdf.itemsize, k, samples, samples.itemsize, u32(ctr), u32(key), nxt)),
+                    "sample_indices_iid")
+        return samples, nxt
+
+    def weights_to_cdf(self, w, error_if_below=None):
+        """Returns (cdf array, ok). ok False where the reference throws (array holds what had been written)."""
+        w = np.ascontiguousarray(w).copy()
+        sfx, t = self._t(w.dtype)
+        if error_if_below is None:
+            error_if_below = -float(np.sqrt(np.finfo(w.dtype).eps))
+        rc = _call(getattr(self.lib, f"rbo_weights_to_cdf_{sfx}"), "qp" + t, (len(w), w, float(error_if_below)))
+        return w, rc == 0
+
     def repeated_fisher_yates(self, k, n, r, ctr, key, idx_dtype=np.int64):
         samples = np.zeros(k * r, idx_dtype)
         nxt = np.zeros(4, np.uint32)
@@ -354,6 +382,35 @@ class Ref(_Base):
         self._check(_call(fn, "qqqcppppppp", (D_rows, D_cols, vec_nnz, axis, u32(ctr), u32(key), vals, rows, cols, nnz,
                                               nxt)), "fill_sparse")
         return vals, rows, cols, int(nnz[0]), nxt
+
+    # --- index-sampling utilities (RandBLAS/util.hh:459-560), the reference's own loops ---
+    def sample_indices_iid_uniform(self, n, k, ctr, key, idx_dtype=np.int64, rad_dtype=None):
+        isfx = "i32" if np.dtype(idx_dtype) == np.int32 else "i64"
+        sfx = "f64" if (rad_dtype is not None and np.dtype(rad_dtype) == np.float64) else "f32"
+        samples = np.full(max(k, 1), -1, idx_dtype)[:k]
+        rad = None if rad_dtype is None else np.zeros(max(k, 1), rad_dtype)[:k]
+        nxt = np.zeros(4, np.uint32)
+        fn = getattr(self.lib, f"rbref_sample_indices_iid_uniform_{sfx}_{isfx}")
+        self._check(_call(fn, "qqppppp", (n, k, samples, rad, u32(ctr), u32(key), nxt)), "sample_indices_iid_uniform")
+        return samples, rad, nxt
+
+    def sample_indices_iid(self, n, cdf, k, ctr, key, idx_dtype=np.int64):
+        isfx = "i32" if np.dtype(idx_dtype) == np.int32 else "i64"
+        cdf = np.ascontiguousarray(cdf)
+        sfx, _ = self._t(cdf.dtype)
+        samples = np.full(max(k, 1), -1, idx_dtype)[:k]
+        nxt = np.zeros(4, np.uint32)
+        fn = getattr(self.lib, f"rbref_sample_indices_iid_{sfx}_{isfx}")
+        self._check(_call(fn, "qpqpppp", (n, cdf, k, samples, u32(ctr), u32(key), nxt)), "sample_indices_iid")
+        return samples, nxt
+
+    def weights_to_cdf(self, w, error_if_below=None):
+        w = np.ascontiguousarray(w).copy()
+        sfx, t = self._t(w.dtype)
+        if error_if_below is None:
+            error_if_below = -float(np.sqrt(np.finfo(w.dtype).eps))
+        rc = _call(getattr(self.lib, f"rbref_weights_to_cdf_{sfx}"), "qp" + t, (len(w), w, float(error_if_below)))
+        return w, rc == 0
 
     def repeated_fisher_yates(self, k, n, r, ctr, key, idx_dtype=np.int64):
         isfx = "i32" if np.dtype(idx_dtype) == np.int32 else "i64"

@@ -13,7 +13,8 @@ import pytest
 
 import oracle_lib as ol
 from golden_util import dense_data
-from test_oracle_pins import _laso_vectors, laso_golden_cases, run_sketch_case, sketch_case_inputs
+from test_oracle_pins import (_laso_vectors, check_sampling_goldens, laso_golden_cases, run_sketch_case,
+                              sketch_case_inputs)
 
 pytestmark = pytest.mark.gpu
 
@@ -273,6 +274,33 @@ def test_laso_fill_vs_oracle_and_goldens(gpu, port):
         pv, pr, pc, pn, px = port.fill_sparse(r, c, vn, "L", ctr, key, np.float32, np.int64)
         assert gn == pn and list(gx) == list(px)
         assert np.array_equal(gr[:gn], pr[:pn]) and np.array_equal(gc[:gn], pc[:pn]) and np.array_equal(gv[:gn], pv[:pn])
+
+
+def test_sampling_utilities_goldens_and_oracle(gpu, gpu_host, port):
+    """sample_indices_iid_uniform / sample_indices_iid / weights_to_cdf (RandBLAS/util.hh:459-560, sampling.cu): the
+    fixtures generated from the compiled reference, with device and with host buffers; then larger random cases
+    against the oracle (samples and CDFs bit-exact, including a CDF of 1e6 weights summed serially in T)."""
+    check_sampling_goldens(gpu)
+    check_sampling_goldens(gpu_host)
+    rng = np.random.default_rng(11)
+    for t, (n, k) in enumerate([(1000, 200001), (1 << 33, 100003), (3, 65537), (999983, 300000)]):
+        ctr, kk = ol.state_from_u64(1997 + t)
+        ctr = ol.ctr_add(ctr, (1 << 32) - 5)
+        idt = np.int64 if n > 2147483647 else (np.int32, np.int64)[t % 2]
+        rdt = (None, np.float32, np.float64, None)[t]
+        a, b = gpu.sample_indices_iid_uniform(n, k, ctr, kk, idt, rdt), port.sample_indices_iid_uniform(n, k, ctr, kk, idt, rdt)
+        assert np.array_equal(a[0], b[0]) and list(a[2]) == list(b[2])
+        assert (a[1] is None and b[1] is None) or np.array_equal(a[1], b[1])
+    for dt in (np.float32, np.float64):
+        w = (rng.random(1000000) ** 4).astype(dt)
+        w[rng.integers(0, len(w), 1000)] = 0
+        ca, oka = gpu.weights_to_cdf(w)
+        cb, okb = port.weights_to_cdf(w)
+        assert oka and okb and np.array_equal(ca, cb)
+        ctr, kk = ol.state_from_u64(7)
+        a, b = gpu.sample_indices_iid(len(w), ca, 250001, ctr, kk, np.int64), port.sample_indices_iid(len(w), cb, 250001, ctr, kk, np.int64)
+        assert np.array_equal(a[0], b[0]) and list(a[1]) == list(b[1])
+        assert a[0].min() >= 0 and a[0].max() < len(w)
 
 
 def test_laso_operator_sketch(gpu):

@@ -212,6 +212,79 @@ def test_golden_laso(port):
     assert n >= 80
 
 
+def check_sampling_goldens(impl):
+    """Index-sampling utilities (RandBLAS/util.hh:459-560) of `impl` against tests/golden/ref_sampling.npz, generated
+    from the compiled reference by oracle/make_goldens_sampling.py: samples, Rademacher signs and next states
+    element for element; CDFs bit for bit (the sum is serial in T on every side); where the reference throws,
+    the implementation must fail too and leave the same partial result."""
+    import os
+    import sampling_cases as sc
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_sampling.npz"))
+    n_checked = 0
+    for (n, k, key, off) in sc.uniform_cases():
+        ctr, kk = ol.state_from_u64(key)
+        ctr = ol.ctr_add(ctr, off)
+        tag = f"unif_n{n}_k{k}_key{key}_off{off}"
+        for idt in ((np.int64,) if n > 2147483647 else (np.int32, np.int64)):
+            s, _, nxt = impl.sample_indices_iid_uniform(n, k, ctr, kk, idt, None)
+            assert np.array_equal(s.astype(np.int64), z[tag + "_plain"]), tag
+            assert list(nxt) == list(z[tag + "_plain_next"]), tag
+            for rdt in (np.float32, np.float64):
+                s, r, nxt = impl.sample_indices_iid_uniform(n, k, ctr, kk, idt, rdt)
+                assert np.array_equal(s.astype(np.int64), z[tag + "_rad"]), tag
+                assert np.array_equal(r, z[tag + "_rad_signs"].astype(rdt)), tag
+                assert list(nxt) == list(z[tag + "_rad_next"]), tag
+        n_checked += 1
+    cdfs = {}
+    for name, (w, eib) in sc.weight_vectors().items():
+        for dt, dtag in ((np.float32, "f32"), (np.float64, "f64")):
+            cdf, ok = impl.weights_to_cdf(w.astype(dt), eib)
+            assert ok == bool(z[f"w2c_{name}_{dtag}_ok"][0]), (name, dtag)
+            assert np.array_equal(cdf, z[f"w2c_{name}_{dtag}"]), (name, dtag)        # bit for bit, partial results too
+            cdfs[name, dtag] = cdf
+            n_checked += 1
+    for name, k in sc.CDF_CASES:
+        for dtag in ("f32", "f64"):
+            cdf = cdfs[name, dtag]
+            for key in sc.KEYS:
+                ctr, kk = ol.state_from_u64(key)
+                ctr = ol.ctr_add(ctr, sc.CDF_COUNTER_OFFSET)
+                tag = f"iid_{name}_k{k}_key{key}_{dtag}"
+                for idt in (np.int32, np.int64):
+                    s, nxt = impl.sample_indices_iid(len(cdf), cdf, k, ctr, kk, idt)
+                    assert np.array_equal(s.astype(np.int32), z[tag]), tag
+                    assert list(nxt) == list(z[tag + "_next"]), tag
+                n_checked += 1
+    assert n_checked >= 100
+
+
+def test_golden_sampling_utilities(port):
+    check_sampling_goldens(port)
+
+
+def test_sampling_utilities_port_equals_reference_live(port, ref):
+    """Random shapes beyond the fixtures: the C restatement against the compiled reference."""
+    rng = np.random.default_rng(5)
+    for t in range(40):
+        n = int(rng.integers(1, 5000))
+        k = int(rng.integers(0, 3000))
+        ctr, kk = ol.state_from_u64(int(rng.integers(0, 1 << 40)))
+        ctr = ol.ctr_add(ctr, int(rng.integers(0, 1 << 34)))
+        idt = (np.int32, np.int64)[t % 2]
+        rdt = (None, np.float32, np.float64)[t % 3]
+        a, b = port.sample_indices_iid_uniform(n, k, ctr, kk, idt, rdt), ref.sample_indices_iid_uniform(n, k, ctr, kk, idt, rdt)
+        assert np.array_equal(a[0], b[0]) and list(a[2]) == list(b[2])
+        assert (a[1] is None and b[1] is None) or np.array_equal(a[1], b[1])
+        dt = (np.float32, np.float64)[(t // 2) % 2]
+        w = rng.random(n).astype(dt) ** 3
+        ca, oka = port.weights_to_cdf(w)
+        cb, okb = ref.weights_to_cdf(w)
+        assert oka == okb and np.array_equal(ca, cb)
+        if oka:
+            a, b = port.sample_indices_iid(n, ca, k, ctr, kk, idt), ref.sample_indices_iid(n, cb, k, ctr, kk, idt)
+            assert np.array_equal(a[0], b[0]) and list(a[1]) == list(b[1])
+
+
 def test_golden_sketch_products(port, gold):
     assert len(gold.m["sketch"]) >= 30
     for c in gold.m["sketch"]:
