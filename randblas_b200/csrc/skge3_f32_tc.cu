@@ -73,6 +73,8 @@ struct TcArgs {
     float alpha, beta;
     float* C;
     int64_t crs, ccs;
+    int64_t xr0;       // XMAT: first row of X in the materialised operator (tensor-map coordinates)
+    int64_t xk0;       // XMAT: first column of X
     float* W;          // split-K workspace: W[split][j][i], i fastest, ld = P_pad; null when splits == 1
     int64_t P_pad, Q_pad;
 };
@@ -164,8 +166,12 @@ __device__ __forceinline__ void split_rn(float x, float& hi, float& lo) {
 // remainder after the truncation the tensor core applies to a raw fp32 operand
 __device__ __forceinline__ float lo_trunc(float y) { return __fsub_rn(y, __uint_as_float(__float_as_uint(y) & 0xffffe000u)); }
 
-template <bool GAUSS>
-__global__ void __launch_bounds__(TC_THREADS, 1) skge3_tc_kernel(const __grid_constant__ CUtensorMap tmY, const TcArgs a) {
+// XMAT: the operator is materialised (S.buff, skge.hh:174-181 "buff != nullptr"): its 128 x 32 tiles come in by TMA
+// (tmX, same K-major 128B-swizzled layout the generators write) on the stage's full barrier, and the generator warps
+// only split them into the two TF32 terms.
+template <bool GAUSS, bool XMAT>
+__global__ void __launch_bounds__(TC_THREADS, 1) skge3_tc_kernel(const __grid_constant__ CUtensorMap tmY,
+                                                                 const __grid_constant__ CUtensorMap tmX, const TcArgs a) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(16) double2 logtab[GAUSS ? LOGF_TABLE_ENTRIES : 1];
     const uint32_t raw = smem_u32(smem_raw);
@@ -193,6 +199,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) skge3_tc_kernel(const __grid_co
         mbar_init(bar_raw_empty, GEN_WARPS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmY) : "memory");
+        if constexpr (XMAT) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmX) : "memory");
     } else if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
                      "r"(TMEM_COLS)
@@ -220,14 +227,26 @@ __global__ void __launch_bounds__(TC_THREADS, 1) skge3_tc_kernel(const __grid_co
                     const uint32_t ph = (it / STAGES) & 1;
                     if (it + PF < nsteps) tma_prefetch_2d(&tmY, (s_begin + it + PF) * BK, (int) j0);
                     mbar_wait(bar_empty(st), ph ^ 1);
-                    mbar_arrive_expect_tx(bar_full(st), Y_BYTES);
+                    mbar_arrive_expect_tx(bar_full(st), XMAT ? Y_BYTES + X_BYTES : Y_BYTES);
                     tma_load_2d(base + st * STAGE_BYTES + 2 * X_BYTES, &tmY, bar_full(st), (s_begin + it) * BK, (int) j0);
+                    if constexpr (XMAT)
+                        tma_load_2d(base + st * STAGE_BYTES, &tmX, bar_full(st), (int) a.xk0 + (s_begin + it) * BK,
+                                    (int) (a.xr0 + i0));
                 }
             } else {
                 // tensor map (Q, K), box 256 q x RAW_K k, no swizzle: one raw tile in flight
                 for (int j = 0; j < min(2 * PF, 2 * nsteps); ++j) tma_prefetch_2d(&tmY, (int) j0, s_begin * BK + j * RAW_K);
                 for (int j = 0; j < 2 * nsteps; ++j) {          // raw tile j = half (j & 1) of step j / 2
                     if (j + 2 * PF < 2 * nsteps) tma_prefetch_2d(&tmY, (int) j0, s_begin * BK + (j + 2 * PF) * RAW_K);
+                    if constexpr (XMAT) {
+                        if ((j & 1) == 0) {                      // the X tile of step j / 2 rides that stage's full barrier
+                            const int it = j >> 1, st = it % STAGES;
+                            mbar_wait(bar_empty(st), (uint32_t) (((it / STAGES) & 1) ^ 1));
+                            mbar_arrive_expect_tx(bar_full(st), X_BYTES);
+                            tma_load_2d(base + st * STAGE_BYTES, &tmX, bar_full(st), (int) a.xk0 + (s_begin + it) * BK,
+                                        (int) (a.xr0 + i0));
+                        }
+                    }
                     mbar_wait(bar_raw_empty, (uint32_t) ((j & 1) ^ 1));
                     mbar_arrive_expect_tx(bar_raw_full, RAW_BYTES);
                     tma_load_2d(base + RAW_OFFSET, &tmY, bar_raw_full, (int) j0, s_begin * BK + j * RAW_K);
@@ -240,7 +259,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) skge3_tc_kernel(const __grid_co
                 const int st = it % STAGES;
                 const uint32_t ph = (it / STAGES) & 1;
                 mbar_wait(bar_ready(st), ph);
-                if (!a.y_mn) mbar_wait(bar_full(st), ph);
+                if (XMAT || !a.y_mn) mbar_wait(bar_full(st), ph);
                 tc_fence_after();
                 const uint32_t xh = base + st * STAGE_BYTES, xl = xh + X_BYTES, yh = xl + X_BYTES, yl = yh + Y_BYTES;
 #pragma unroll
@@ -299,6 +318,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) skge3_tc_kernel(const __grid_co
                     if (lane == 0) mbar_arrive(bar_raw_empty);
                 }
             }
+            if constexpr (XMAT) {
+                // materialised operator: split the raw tile TMA delivered into hi (nearest TF32, rewritten in place) and lo
+                mbar_wait(bar_full(st), ph);
+#pragma unroll
+                for (int q = 0; q < (int) (X_BYTES / 16) / (32 * GEN_WARPS); ++q) {
+                    const uint32_t o = (uint32_t) (gt + 32 * GEN_WARPS * q) * 16u;
+                    const float4 x = *reinterpret_cast<const float4*>(stage + o);
+                    float4 h, l;
+                    split_rn(x.x, h.x, l.x); split_rn(x.y, h.y, l.y); split_rn(x.z, h.z, l.z); split_rn(x.w, h.w, l.w);
+                    *reinterpret_cast<float4*>(stage + o) = h;
+                    *reinterpret_cast<float4*>(stage + X_BYTES + o) = l;
+                }
+            } else {
 #pragma unroll
             for (int rr = 0; rr < X_PER_THREAD; ++rr) {
                 const uint64_t lo = seed_lo + off[rr];
@@ -320,6 +352,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) skge3_tc_kernel(const __grid_co
                 split_rn(finish_sample<float, GAUSS>(f.w), h.w, l.w);
                 *reinterpret_cast<float4*>(stage + xoff + rr * (ROWS_PER_PASS * 128)) = h;
                 *reinterpret_cast<float4*>(stage + X_BYTES + xoff + rr * (ROWS_PER_PASS * 128)) = l;
+            }
             }
             if (!a.y_mn) {
             mbar_wait(bar_full(st), ph);
@@ -422,8 +455,9 @@ EncodeTiledFn encode_tiled() {
 
 int launch_dense_tc_f32(const DenseProblem<float>& p, cudaStream_t st) {
     // shapes / layouts this kernel takes; everything else goes to the generic kernel
-    if (p.S_buff != nullptr) return -1;
-    if (p.family == 'G' && !p.gen.logtab) return -1;
+    const bool xmat = p.S_buff != nullptr;
+    if (xmat && get_option("dense_path") == 4) return -1;     // experiment switch: materialised operators to the generic kernel
+    if (!xmat && p.family == 'G' && !p.gen.logtab) return -1;
     if (!(p.uk == 1 && p.vi == 1)) return -1;                 // Philox blocks must run along K
     // Y K-contiguous, or Q-contiguous (left sketch of RowMajor data, right sketch of ColMajor data)
     const bool y_mn = (p.yrs != 1);
@@ -433,6 +467,13 @@ int launch_dense_tc_f32(const DenseProblem<float>& p, cudaStream_t st) {
     if (p.Q > 0x7fffff00LL || p.K > 0x7fffff00LL) return -1;
     if ((reinterpret_cast<uintptr_t>(p.Y) & 15) != 0 || ((y_mn ? p.yrs : p.ycs) & 3) != 0) return -1;   // TMA alignment rules
     if ((int64_t) p.P * p.Q < 128 * 64 && p.K < 4096) return -1;                       // tiny: launch cost dominates
+    if (xmat) {
+        // vector v of the operator is the contiguous run S_buff[v * S_ld ...]: X(i, k) = S_buff[(v0 + i) * S_ld + u0 + k]
+        // TMA: base, row pitch and the box's first element must all sit on 16-byte boundaries (a window whose first
+        // column is not a multiple of 4 trapped the pipeline on the device), so such windows go to the generic kernel
+        if ((reinterpret_cast<uintptr_t>(p.S_buff) & 15) != 0 || (p.S_ld & 3) != 0 || (p.u0 & 3) != 0) return -1;
+        if (p.v0 + p.P > 0x7fffff00LL || p.u0 + p.K > 0x7fffff00LL) return -1;
+    }
     EncodeTiledFn enc = encode_tiled();
     if (!enc) return -1;
 
@@ -470,7 +511,20 @@ int launch_dense_tc_f32(const DenseProblem<float>& p, cudaStream_t st) {
                       CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (cr != CUDA_SUCCESS) return -1;
 
+    CUtensorMap tmx = tm;
+    if (xmat) {
+        // extents end at the window's last column / row so that the K tail and the rows past P read as zeros
+        const cuuint64_t xdim[2] = {(cuuint64_t) (p.u0 + p.K), (cuuint64_t) (p.v0 + p.P)};
+        const cuuint64_t xstr[1] = {(cuuint64_t) p.S_ld * 4ull};
+        const cuuint32_t xbox[2] = {(cuuint32_t) BK, (cuuint32_t) BM};
+        cr = enc(&tmx, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(p.S_buff), xdim, xstr, xbox, estr,
+                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (cr != CUDA_SUCCESS) return -1;
+    }
+
     TcArgs a;
+    a.xr0 = p.v0; a.xk0 = p.u0;
     a.ctr = p.gen.ctr; a.key = p.gen.key; a.R = p.gen.R; a.logtab = p.gen.logtab;
     a.v0 = p.v0;
     a.kshift = kshift;
@@ -487,17 +541,21 @@ int launch_dense_tc_f32(const DenseProblem<float>& p, cudaStream_t st) {
         a.W = (float*) workspace(6, (size_t) splits * a.P_pad * a.Q_pad * sizeof(float));
         if (!a.W) return fail_cuda(cudaErrorMemoryAllocation, "split-K workspace");
     }
-    static bool attr_done[2] = {false, false};
+    static bool attr_done[3] = {false, false, false};
     const bool gauss = p.family == 'G';
-    if (!attr_done[gauss]) {
-        cudaError_t e = gauss ? cudaFuncSetAttribute(skge3_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM)
-                              : cudaFuncSetAttribute(skge3_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM);
+    const int variant = xmat ? 2 : (gauss ? 1 : 0);
+    if (!attr_done[variant]) {
+        cudaError_t e =
+            xmat ? cudaFuncSetAttribute(skge3_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM)
+                 : gauss ? cudaFuncSetAttribute(skge3_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM)
+                         : cudaFuncSetAttribute(skge3_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM);
         if (e != cudaSuccess) { cudaGetLastError(); return -1; }
-        attr_done[gauss] = true;
+        attr_done[variant] = true;
     }
     dim3 grid((unsigned) tiles_q, (unsigned) tiles_p, (unsigned) splits);
-    if (gauss) skge3_tc_kernel<true><<<grid, TC_THREADS, TC_SMEM, st>>>(tm, a);
-    else skge3_tc_kernel<false><<<grid, TC_THREADS, TC_SMEM, st>>>(tm, a);
+    if (xmat) skge3_tc_kernel<false, true><<<grid, TC_THREADS, TC_SMEM, st>>>(tm, tmx, a);
+    else if (gauss) skge3_tc_kernel<true, false><<<grid, TC_THREADS, TC_SMEM, st>>>(tm, tmx, a);
+    else skge3_tc_kernel<false, false><<<grid, TC_THREADS, TC_SMEM, st>>>(tm, tmx, a);
     count_launch();
     count_tc_launch();
     RB_CUDA(cudaGetLastError());

@@ -71,6 +71,9 @@ struct DmmaArgs {
     int64_t ycs;          // column stride of Y in elements when rows are contiguous (yrs == 1), else the ROW stride (YMN)
     double* C;
     int64_t crs, ccs;
+    const double* X;      // materialised operator (XMAT kernels): X(i, k) = X[(xr0 + i) * xld + xk0 + k]
+    int64_t xld, xr0, xk0;
+    int x_al;             // rows of X can be read with 16-byte loads
     double* W;            // split-K workspace W[split][j][i] (i fastest, ld = P_pad) or null
     int64_t P_pad, Q_pad;
 };
@@ -262,7 +265,9 @@ __global__ void __launch_bounds__(D_THREADS, 1) skge3_dmma_kernel(const DmmaArgs
 // scheduler fills the issue slots between DMMAs. Register split with setmaxnreg: producers 72, DMMA warps 216.
 constexpr int WS_THREADS = 384, WS_PROD = 128;
 
-template <bool GAUSS, bool YMN, class TILE>
+// XMAT: the operator is materialised (S.buff != nullptr, skge.hh:174-181): the producer warps copy its DM x 16 tiles
+// from global memory instead of generating them (plain loads, three stages ahead of the DMMA warps).
+template <bool GAUSS, bool YMN, class TILE, bool XMAT = false>
 __global__ void __launch_bounds__(WS_THREADS, 1) skge3_dmma_ws_kernel(const DmmaArgs a) {
     constexpr int DM = TILE::DM, DN = TILE::DN, D_WN = TILE::D_WN, D_MI = TILE::D_MI, D_NI = TILE::D_NI, DLQ = TILE::DLQ;
     constexpr int P_GR = DM / (WS_PROD / D_CPR);             // rows of the S tile generated per producer thread and step
@@ -339,6 +344,26 @@ __global__ void __launch_bounds__(WS_THREADS, 1) skge3_dmma_ws_kernel(const Dmma
 #pragma unroll 2
             for (int rr = 0; rr < P_GR; ++rr) {
                 const int row = xr + (WS_PROD / D_CPR) * rr;
+                if constexpr (XMAT) {
+                    const int64_t i = i0 + row, k = (int64_t) (s_begin + step) * DK + 4 * xc;
+                    const double* src = a.X + (a.xr0 + i) * a.xld + a.xk0 + k;
+                    double2 x01 = make_double2(0.0, 0.0), x23 = make_double2(0.0, 0.0);
+                    if (i < a.P) {
+                        if (a.x_al && k + 3 < a.K) {
+                            x01 = __ldg(reinterpret_cast<const double2*>(src));
+                            x23 = __ldg(reinterpret_cast<const double2*>(src) + 1);
+                        } else {
+                            if (k < a.K) x01.x = __ldg(src);
+                            if (k + 1 < a.K) x01.y = __ldg(src + 1);
+                            if (k + 2 < a.K) x23.x = __ldg(src + 2);
+                            if (k + 3 < a.K) x23.y = __ldg(src + 3);
+                        }
+                    }
+                    double* dst = Xs + ((size_t) buf * DM + row) * DLD + 4 * xc;
+                    *reinterpret_cast<double2*>(dst) = x01;
+                    *reinterpret_cast<double2*>(dst + 2) = x23;
+                    continue;
+                }
                 const uint64_t o = (uint64_t) ((a.v0 + i0 + row) * a.R + a.ublk0 + xc) + (uint64_t) D_CPR * (uint64_t) (s_begin + step);
                 const uint64_t lo = seed_lo + o;
                 const uint64_t hi = seed_hi + (lo < seed_lo ? 1ull : 0ull);
@@ -439,9 +464,10 @@ __global__ void __launch_bounds__(256) splitk_reduce_f64_kernel(const double* __
 }  // namespace
 
 int launch_dense_dmma_f64(const DenseProblem<double>& p, cudaStream_t st) {
-    if (p.S_buff != nullptr) return -1;
-    if (p.family == 'G' && !p.gen.logtab) return -1;
-    if (!(p.uk == 1 && p.vi == 1)) return -1;                 // Philox blocks must run along K
+    const bool xmat = p.S_buff != nullptr;
+    if (xmat && (get_option("dense_path") == 4 || get_option("dmma_uniform_warps") != 0)) return -1;
+    if (!xmat && p.family == 'G' && !p.gen.logtab) return -1;
+    if (!(p.uk == 1 && p.vi == 1)) return -1;                 // Philox blocks (rows of a materialised operator) must run along K
     // Y K-contiguous, or Q-contiguous (left sketch of RowMajor data, right sketch of ColMajor data)
     const bool y_mn = (p.yrs != 1);
     if (y_mn && p.ycs != 1) return -1;
@@ -484,6 +510,8 @@ int launch_dense_dmma_f64(const DenseProblem<double>& p, cudaStream_t st) {
     a.Y = p.Y; a.ycs = y_mn ? p.yrs : p.ycs;
     a.C = p.C; a.crs = p.crs; a.ccs = p.ccs;
     a.P_pad = tiles_p * DM; a.Q_pad = tiles_q * DN;
+    a.X = p.S_buff; a.xld = p.S_ld; a.xr0 = p.v0; a.xk0 = p.u0;
+    a.x_al = (xmat && (reinterpret_cast<uintptr_t>(p.S_buff) & 15) == 0 && (p.S_ld & 1) == 0 && (p.u0 & 1) == 0) ? 1 : 0;
     a.W = nullptr;
     if (splits > 1) {
         a.W = (double*) workspace(6, (size_t) splits * a.P_pad * a.Q_pad * sizeof(double));
@@ -503,7 +531,7 @@ int launch_dense_dmma_f64(const DenseProblem<double>& p, cudaStream_t st) {
         kern<<<grid, D_THREADS, smem, st>>>(a);
         return 0;
     };
-    static bool attr_done[16] = {};
+    static bool attr_done[20] = {};
     const bool ws = get_option("dmma_uniform_warps") == 0;    // default: warp-specialised kernel
     auto launch_ws = [&](auto kern, bool& done) -> int {
         if (!done) {
@@ -517,7 +545,10 @@ int launch_dense_dmma_f64(const DenseProblem<double>& p, cudaStream_t st) {
         return 0;
     };
     int lrc;
-    if (ws) {
+    if (xmat) {
+        if (wide) lrc = y_mn ? launch_ws(skge3_dmma_ws_kernel<false, true, TileWide, true>, attr_done[19]) : launch_ws(skge3_dmma_ws_kernel<false, false, TileWide, true>, attr_done[18]);
+        else lrc = y_mn ? launch_ws(skge3_dmma_ws_kernel<false, true, TileSquare, true>, attr_done[17]) : launch_ws(skge3_dmma_ws_kernel<false, false, TileSquare, true>, attr_done[16]);
+    } else if (ws) {
         if (wide) {
             if (gauss) lrc = y_mn ? launch_ws(skge3_dmma_ws_kernel<true, true, TileWide>, attr_done[15]) : launch_ws(skge3_dmma_ws_kernel<true, false, TileWide>, attr_done[14]);
             else lrc = y_mn ? launch_ws(skge3_dmma_ws_kernel<false, true, TileWide>, attr_done[13]) : launch_ws(skge3_dmma_ws_kernel<false, false, TileWide>, attr_done[12]);

@@ -395,6 +395,54 @@ def test_prefilled_operator_equals_fused(gpu, dt):
         assert relerr(B1, B2) < TOL[np.dtype(dt)]
 
 
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+def test_materialised_operator_on_tensor_cores(gpu, dt):
+    """S.buff != nullptr (the reference's blas::gemm branch, skge.hh:194-200) at sizes the tensor-core kernels take:
+    the operator tile is read from S.buff (TMA for float, producer-warp loads for double) instead of regenerated.
+    Same splits and the same values as the fused path, so the result is bit-identical to it; a modified buff must
+    change the result (it is read, not regenerated); the SIMT generic kernel agrees within the tolerance."""
+    import randblas_b200 as rb
+    import torch
+    tdt = torch.float32 if dt == np.float32 else torch.float64
+    d, n, m = 200, 300, 5000
+    for (Dr, Dc, ro, co) in ((d + 8, m + 12, 3, 5), (d, m, 0, 0), (d + 8, m + 12, 2, 8), (d + 1, m + 3, 1, 2)):
+        D = rb.DenseDist(Dr, Dc, "U" if ro else "G", "L")
+        S0 = rb.DenseSkOp(D, rb.RNGState(1997), dt)
+        S1 = rb.DenseSkOp(D, rb.RNGState(1997), dt)
+        rb.fill_dense(S1)
+        eligible = (Dc % 4 == 0 and co % 4 == 0) if dt == np.float32 else True   # TMA alignment of the operator tile
+        g = torch.Generator(device="cuda").manual_seed(5)
+        for side, lay in (("L", "C"), ("L", "R"), ("R", "R"), ("R", "C")):
+            A = torch.randn(m * n, dtype=tdt, device="cuda", generator=g)
+            outs = []
+            for S, path in ((S0, 0), (S1, 0), (S1, 1)):
+                rb.set_option("dense_path", path)
+                B = torch.full((d * n,), float("nan"), dtype=tdt, device="cuda")
+                before = rb.counter("tensor_core_launches")
+                if side == "L":      # B(d x n) = S[ro:, co:](d x m) A(m x n)
+                    rb.sketch_general(lay, "N", "N", d, n, m, 1.0, S, ro, co, A, m if lay == "C" else n, 0.0, B,
+                                      d if lay == "C" else n)
+                else:                # B(n x d) = A(n x m) S^T: the operator window transposed on the right
+                    rb.sketch_general(lay, "N", "T", n, d, m, 1.0, A, n if lay == "C" else m, S, ro, co, 0.0, B,
+                                      n if lay == "C" else d)
+                ran_tc = rb.counter("tensor_core_launches") > before
+                rb.set_option("dense_path", 0)
+                if path == 0 and (S is S0 or eligible):
+                    assert ran_tc, (side, lay, Dr, Dc, "tensor-core kernel did not run")
+                outs.append(B)
+            if eligible:
+                assert torch.equal(outs[0], outs[1]), (side, lay, Dr, Dc)
+            assert relerr(outs[1].cpu().numpy(), outs[2].cpu().numpy()) < TOL[np.dtype(dt)], (side, lay, Dr, Dc)
+        # the buffer is what is multiplied: doubling it doubles the result exactly
+        S1.buff.mul_(2)
+        A = torch.randn(m * n, dtype=tdt, device="cuda", generator=g)
+        B1 = torch.zeros(d * n, dtype=tdt, device="cuda")
+        B0 = torch.zeros(d * n, dtype=tdt, device="cuda")
+        rb.sketch_general("C", "N", "N", d, n, m, 1.0, S1, ro, co, A, m, 0.0, B1, d)
+        rb.sketch_general("C", "N", "N", d, n, m, 2.0, S0, ro, co, A, m, 0.0, B0, d)
+        assert relerr(B1.cpu().numpy(), B0.cpu().numpy()) < TOL[np.dtype(dt)]
+
+
 def test_sketch_identity_reproduces_operator(gpu, port):
     """linop_common.hh:309-389: applying the operator to the identity must reproduce S (here: exactly for the
     float path up to the 3xTF32 split, so compared with tolerance 1e-6)."""
