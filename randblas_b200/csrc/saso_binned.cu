@@ -128,10 +128,7 @@ __global__ void __launch_bounds__(BIN_THREADS) saso_bin_kernel(const BinArgs a) 
 #pragma unroll
             for (int t = G - 2; t >= 0; --t) {
                 const uint32_t pt = __shfl_sync(0xffffffffu, piv, t, G);
-                if (t < sub) {
-                    if (pos == (uint32_t) t) pos = pt;
-                    else if (pos == pt) pos = (uint32_t) t;
-                }
+                if (t < sub && pos == pt) pos = (uint32_t) t;
             }
             if (live) {
                 const int64_t r = (int64_t) pos - a.m0;

@@ -30,7 +30,10 @@ __device__ __forceinline__ int64_t fy_pivot(uint32_t w0, int64_t j, int64_t dim_
 }
 
 // One warp computes one vector of k <= 32 entries: lane j holds step j's (major index, sign).
-// The value at position `ell` after swaps 0..j-1 of an identity permutation: walk the swaps backwards.
+// The value at position `ell` after swaps 0..j-1 of an identity permutation: walk the swaps backwards. Swap t
+// exchanges positions t and piv_t >= t. The traced position starts at piv_j >= j > t and, once it has been moved, sits
+// at an earlier step's index t' > t, so it can never equal t itself: the only case left per step is
+// "pos == piv_t -> pos = t" (one compare and one select instead of three and two).
 __device__ __forceinline__ void saso_vector_warp(const Ctr128& base, const PhiloxKey& key, int64_t vec, int k,
                                                  int64_t dim_major, int lane, int64_t& major, int& negative) {
     int64_t piv = 0;
@@ -43,10 +46,7 @@ __device__ __forceinline__ void saso_vector_warp(const Ctr128& base, const Philo
     int64_t pos = piv;
     for (int t = k - 2; t >= 0; --t) {
         const int64_t pt = __shfl_sync(0xffffffffu, piv, t);
-        if (t < lane) {
-            if (pos == t) pos = pt;
-            else if (pos == pt) pos = t;
-        }
+        if (t < lane && pos == pt) pos = t;
     }
     major = pos;
     negative = (int) (w1 & 1u);
@@ -55,9 +55,7 @@ __device__ __forceinline__ void saso_vector_warp(const Ctr128& base, const Philo
 // General k (any size): one thread per vector, pivots kept in a global scratch row of length k.
 __device__ __forceinline__ int64_t fy_trace(const int64_t* piv, int j, int64_t pos) {
     for (int t = j - 1; t >= 0; --t) {
-        const int64_t pt = piv[t];
-        if (pos == t) pos = pt;
-        else if (pos == pt) pos = t;
+        if (pos == piv[t]) pos = t;
     }
     return pos;
 }
@@ -122,10 +120,7 @@ __global__ void __launch_bounds__(256) saso_fill_group_kernel(Ctr128 ctr, Philox
 #pragma unroll
         for (int t = G - 2; t >= 0; --t) {
             const uint32_t pt = __shfl_sync(0xffffffffu, piv, t, G);
-            if (t < sub) {
-                if (pos == (uint32_t) t) pos = pt;
-                else if (pos == pt) pos = (uint32_t) t;
-            }
+            if (t < sub && pos == pt) pos = (uint32_t) t;
         }
         if (live) put_entry<IDX, VAL>(maj, mnr, vals, v * k + sub, (int64_t) pos, v, (int) (w1 & 1u));
     }

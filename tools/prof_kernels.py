@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """Small single-launch drivers for ncu captures (never a bench: numbers printed under a profiler are not results).
 
-    python tools/prof_kernels.py fill_gauss_f64 | fill_unif_f32 | saso_apply | dense_f32 | dense_f64 | sksp
+    python tools/prof_kernels.py fill_gauss_f64 | fill_unif_f32 | saso_apply | saso_fill | dense_f32 | dense_f64 |
+                                 dense_f32_mat | dense_f64_mat | sksp
 
 Each runs the kernel 3 times on a reduced-but-still-larger-than-L2 shape of the matching BASELINE config."""
 import os
@@ -53,6 +54,19 @@ def main():
         A = torch.randn(m * n, dtype=torch.float64, device="cuda")
         B = torch.zeros(d * n, dtype=torch.float64, device="cuda")
         f = lambda: rb.sketch_general("C", "N", "N", d, n, m, 1.0, S, 0, 0, A, m, 0.0, B, d)
+    elif what in ("dense_f32_mat", "dense_f64_mat"):
+        # materialised operator (S.buff filled): the XMAT instantiations of the tensor-core kernels
+        dt, tdt = (np.float32, torch.float32) if what == "dense_f32_mat" else (np.float64, torch.float64)
+        d, m, n = (1024, 100000, 1024) if dt == np.float32 else (4096, 32768, 512)
+        S = rb.DenseSkOp(rb.DenseDist(d, m, rb.ScalarDist.Gaussian), rb.RNGState(1997), dt)
+        rb.fill_dense(S)
+        A = torch.randn(m * n, dtype=tdt, device="cuda")
+        B = torch.zeros(d * n, dtype=tdt, device="cuda")
+        f = lambda: rb.sketch_general("C", "N", "N", d, n, m, 1.0, S, 0, 0, A, m, 0.0, B, d)
+    elif what == "saso_fill":
+        d, m, k = 2048, 8000000, 8
+        S = rb.SparseSkOp(rb.SparseDist(d, m, k), rb.RNGState(1997), dtype=np.float32)
+        f = lambda: rb.fill_sparse(S)
     elif what == "sksp":
         d, m, n, per_row = 512, 1000000, 125000, 12.5
         lens = torch.poisson(torch.full((m,), per_row, device="cuda")).to(torch.int64)
