@@ -7,6 +7,7 @@ float ulp (measured: 0 on glibc 2.39 FMA hosts). Sketch products: relative Frobe
 <= 1e-12 (double).
 """
 import itertools
+import os
 
 import numpy as np
 import pytest
@@ -441,6 +442,33 @@ def test_materialised_operator_on_tensor_cores(gpu, dt):
         rb.sketch_general("C", "N", "N", d, n, m, 1.0, S1, ro, co, A, m, 0.0, B1, d)
         rb.sketch_general("C", "N", "N", d, n, m, 2.0, S0, ro, co, A, m, 0.0, B0, d)
         assert relerr(B1.cpu().numpy(), B0.cpu().numpy()) < TOL[np.dtype(dt)]
+
+
+def test_example_total_least_squares_matches_reference_pipeline(gpu, port):
+    """examples/tls_dense_skop.py (the caller the reference ships as examples/total-least-squares/tls_dense_skop.cc) at
+    a reduced size: the sketched data S*[A|b] equals the oracle's for the same seeds, and the sketched TLS solution is
+    close to the classical one."""
+    import importlib.util
+    import torch
+    spec = importlib.util.spec_from_file_location("tls_example", os.path.join(os.path.dirname(os.path.dirname(
+        os.path.abspath(__file__))), "examples", "tls_dense_skop.py"))
+    ex = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ex)
+    m, n = 3000, 60
+    rel, sketch_x, true_x = ex.main(m, n, verbose=False)
+    assert rel < 0.2 and torch.isfinite(sketch_x).all() and torch.isfinite(true_x).all()
+    # the data the example builds is the reference's: A = fill_dense(DenseDist(m, n), RNGState(0))
+    AB = ex.init_noisy_data(m, n).cpu().numpy()
+    ctr, key = ol.state_from_u64(0)
+    A_ref, _ = port.fill_dense_unpacked("C", m, n, "G", "L", m, n, 0, 0, ctr, key, np.float64)
+    assert np.array_equal(AB[: m * n], A_ref)
+    sk = 2 * (n + 1)
+    B = np.zeros(sk * (n + 1))
+    ctr, key = ol.state_from_u64(1997)
+    port.lskge3("C", "N", "N", sk, n + 1, m, 1.0, (sk, m, "G", "L"), ctr, key, 0, 0, AB, m, 0.0, B, sk)
+    Bg = np.zeros_like(B)
+    gpu.lskge3("C", "N", "N", sk, n + 1, m, 1.0, (sk, m, "G", "L"), ctr, key, 0, 0, AB, m, 0.0, Bg, sk)
+    assert relerr(Bg, B) < 1e-12
 
 
 def test_sketch_identity_reproduces_operator(gpu, port):
