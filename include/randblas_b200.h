@@ -237,6 +237,8 @@ int rb_rsksp3_f64(int fmt, char layout, char opA, char opS, int64_t m, int64_t d
  * rb_set_option("dense_path", v): 0 = auto (tensor-core kernels where the shape allows), 1 = force the
  * generic SIMT kernel. rb_get_counter("kernel_launches") counts kernels this library launched. */
 int rb_set_option(const char* name, int64_t value);
+/* current value of an option (0 for an unknown name) */
+int64_t rb_get_option(const char* name);
 int64_t rb_get_counter(const char* name);
 
 #ifdef __cplusplus

@@ -9,4 +9,4 @@ from .api import (Axis, COOMatrix, CSCMatrix, CSRMatrix, DenseDist, DenseSkOp, L
                   philox_words, boxmuller_words, repeated_fisher_yates, sketch_general, sketch_sparse, sketch_vector,
                   left_spmm, right_spmm, coo_to_csr, coo_to_csc, csr_to_coo, csc_to_coo,
                   sketch_symmetric, sample_indices_iid, sample_indices_iid_uniform, weights_to_cdf)
-from ._lib import RandBLASError, counter, set_option  # noqa
+from ._lib import RandBLASError, counter, get_option, set_option  # noqa

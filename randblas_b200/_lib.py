@@ -58,6 +58,12 @@ def counter(name):
     return int(lib().rb_get_counter(name.encode()))
 
 
+def get_option(name):
+    fn = lib().rb_get_option
+    fn.restype = ctypes.c_int64
+    return int(fn(ctypes.c_char_p(name.encode())))
+
+
 def set_option(name, value):
     fn = lib().rb_set_option
     fn.restype = ctypes.c_int

@@ -55,6 +55,7 @@ constexpr uint32_t RAW_OFFSET = STAGES * STAGE_BYTES;   // raw Q-contiguous Y ti
 constexpr uint32_t BAR_OFFSET = RAW_OFFSET + RAW_BYTES;
 constexpr uint32_t TC_SMEM = BAR_OFFSET + 128 + 1024;   // barriers + TMEM slot + 1 KB alignment slack
 static_assert(TC_SMEM + 8752 + 64 <= 232448, "shared memory budget (dynamic + the Gaussian table)");
+static_assert(STAGES == 2, "the 2-CTA cluster mode maps stage s to generating CTA s");
 constexpr uint32_t TMEM_COLS = 512;      // two 128 x 256 fp32 accumulators: hi*hi and the two cross terms
 constexpr int MAX_CHAIN_STEPS = 40;       // K steps accumulated in TMEM before the partial sum leaves the tensor core
 
@@ -109,7 +110,43 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         }
     }
 }
+// Same bounded wait with acquire semantics at cluster scope: the data behind the barrier was written by the peer CTA.
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+    uint32_t ok = 0;
+    long long t0 = 0;
+    for (uint32_t spins = 0;; ++spins) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (ok) return;
+        if ((spins & 0xfff) == 0xfff) {
+            const long long now = clock64();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 4000000000LL) __trap();
+        }
+    }
+}
+// address of the same shared-memory location in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void st_cluster_v4(uint32_t raddr, const float4& v) {
+    asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(raddr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t raddr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(raddr) : "memory");
+}
+__device__ __forceinline__ void cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// all state spaces: the generic-proxy writes to order include stores into the peer CTA's shared memory
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -144,6 +181,13 @@ __device__ __forceinline__ void mma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 
+// the same commit, arriving on the barrier at this offset in both CTAs of a 2-CTA cluster
+__device__ __forceinline__ void mma_commit_pair(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+                 "h"((uint16_t) 3)
+                 : "memory");
+}
+
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -169,7 +213,12 @@ __device__ __forceinline__ float lo_trunc(float y) { return __fsub_rn(y, __uint_
 // XMAT: the operator is materialised (S.buff, skge.hh:174-181 "buff != nullptr"): its 128 x 32 tiles come in by TMA
 // (tmX, same K-major 128B-swizzled layout the generators write) on the stage's full barrier, and the generator warps
 // only split them into the two TF32 terms.
-template <bool GAUSS, bool XMAT>
+// CL = 2: two CTAs that own neighbouring column tiles of C (same rows, same K range) form a cluster and share the
+// generated operator tile: they take turns generating it (stage s is always produced by CTA s) and write it into BOTH
+// shared memories (st.shared::cluster), arriving on both `ready` barriers; every MMA commit that frees a stage arrives on
+// both `empty` barriers (multicast), so a stage is rewritten only when both tensor cores are done with it. Halves the
+// generator work per flop (the binding resource for Gaussian operators).
+template <bool GAUSS, bool XMAT, int CL = 1>
 __global__ void __launch_bounds__(TC_THREADS, 1) skge3_tc_kernel(const __grid_constant__ CUtensorMap tmY,
                                                                  const __grid_constant__ CUtensorMap tmX, const TcArgs a) {
     extern __shared__ uint8_t smem_raw[];
@@ -191,8 +240,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) skge3_tc_kernel(const __grid_co
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(bar_full(s), 1);
-            mbar_init(bar_ready(s), GEN_WARPS);
-            mbar_init(bar_empty(s), 1);
+            // in a cluster the stage this CTA generates itself gets local arrivals only; the other one also the peer's
+            uint32_t ready_count = GEN_WARPS;
+            if constexpr (CL > 1) {
+                uint32_t rk;
+                asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rk));
+                if ((uint32_t) s != rk) ready_count = 2 * GEN_WARPS;
+            }
+            mbar_init(bar_ready(s), ready_count);
+            mbar_init(bar_empty(s), CL);
         }
         mbar_init(bar_accum, 1);
         mbar_init(bar_raw_full, 1);
@@ -210,6 +266,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) skge3_tc_kernel(const __grid_co
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    uint32_t crank = 0;
+    if constexpr (CL > 1) {
+        asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
+        cluster_sync();                 // the peer's barriers exist before anything arrives on them
+    }
 
     const int64_t i0 = (int64_t) blockIdx.y * BM, j0 = (int64_t) blockIdx.x * BN;
     const int split = blockIdx.z;
@@ -258,8 +319,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) skge3_tc_kernel(const __grid_co
             for (int it = 0; it < nsteps; ++it) {
                 const int st = it % STAGES;
                 const uint32_t ph = (it / STAGES) & 1;
-                mbar_wait(bar_ready(st), ph);
+                if constexpr (CL > 1) mbar_wait_cluster(bar_ready(st), ph);
+                else mbar_wait(bar_ready(st), ph);
                 if (XMAT || !a.y_mn) mbar_wait(bar_full(st), ph);
+                if constexpr (CL > 1) fence_proxy_async();     // the peer's generic-proxy stores into this CTA's tiles
                 tc_fence_after();
                 const uint32_t xh = base + st * STAGE_BYTES, xl = xh + X_BYTES, yh = xl + X_BYTES, yl = yh + Y_BYTES;
 #pragma unroll
@@ -271,7 +334,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) skge3_tc_kernel(const __grid_co
                     mma_tf32(tmem_base + BN, dxh, dyl, 1u);
                     mma_tf32(tmem_base, dxh, dyh, acc);
                 }
-                mma_commit(bar_empty(st));
+                if constexpr (CL > 1) mma_commit_pair(bar_empty(st));
+                else mma_commit(bar_empty(st));
             }
             mma_commit(bar_accum);
         }
@@ -281,11 +345,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) skge3_tc_kernel(const __grid_co
         const int c = gt & 7, r0 = gt >> 3;
         const uint64_t seed_lo = ((uint64_t) a.ctr.c1 << 32) | a.ctr.c0, seed_hi = ((uint64_t) a.ctr.c3 << 32) | a.ctr.c2;
         constexpr int ROWS_PER_PASS = 4 * GEN_WARPS;      // rows of X covered by one pass of all generator threads
-        uint64_t off[X_PER_THREAD];
+        // In a cluster the two CTAs take turns: CTA r generates the whole tile of every K step whose stage is r and writes
+        // it into both shared memories. (Splitting the ROWS of each tile between the CTAs was measured first and did not
+        // help: the generators are latency-bound -- 4 warps per scheduler, two dependent Box-Muller chains per thread --
+        // so one block per thread takes as long as two. Alternating keeps two blocks per thread and gives each CTA two
+        // step times to produce a tile.)
+        constexpr int XPT = X_PER_THREAD;
+        const int rbase = r0;
+        uint64_t off[XPT];
 #pragma unroll
-        for (int rr = 0; rr < X_PER_THREAD; ++rr)
-            off[rr] = (uint64_t) ((a.v0 + i0 + r0 + ROWS_PER_PASS * rr) * a.R + a.ublk0 + c) + 8ull * (uint64_t) s_begin;
-        const uint32_t xoff = (uint32_t) r0 * 128u + (uint32_t) ((c ^ (r0 & 7)) << 4);
+        for (int rr = 0; rr < XPT; ++rr)
+            off[rr] = (uint64_t) ((a.v0 + i0 + rbase + ROWS_PER_PASS * rr) * a.R + a.ublk0 + c) + 8ull * (uint64_t) s_begin;
+        const uint32_t xoff = (uint32_t) rbase * 128u + (uint32_t) ((c ^ (r0 & 7)) << 4);
         for (int it = 0; it < nsteps; ++it) {
             const int st = it % STAGES;
             const uint32_t ph = (it / STAGES) & 1;
@@ -331,11 +402,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) skge3_tc_kernel(const __grid_co
                     *reinterpret_cast<float4*>(stage + X_BYTES + o) = l;
                 }
             } else {
+            const bool my_turn = (CL == 1) || ((uint32_t) st == crank);
 #pragma unroll
-            for (int rr = 0; rr < X_PER_THREAD; ++rr) {
+            for (int rr = 0; rr < XPT; ++rr) {
                 const uint64_t lo = seed_lo + off[rr];
                 const uint64_t hi = seed_hi + (lo < seed_lo ? 1ull : 0ull);
                 off[rr] += 8;
+                if (!my_turn) continue;
                 const Ctr128 cc{(uint32_t) lo, (uint32_t) (lo >> 32), (uint32_t) hi, (uint32_t) (hi >> 32)};
                 float4 f = transform4<GAUSS>(philox4x32_10(cc, a.key), logtab);
                 if (a.kshift) {
@@ -352,6 +425,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) skge3_tc_kernel(const __grid_co
                 split_rn(finish_sample<float, GAUSS>(f.w), h.w, l.w);
                 *reinterpret_cast<float4*>(stage + xoff + rr * (ROWS_PER_PASS * 128)) = h;
                 *reinterpret_cast<float4*>(stage + X_BYTES + xoff + rr * (ROWS_PER_PASS * 128)) = l;
+                if constexpr (CL > 1) {
+                    const uint32_t ra = map_to_cta(base + (uint32_t) st * STAGE_BYTES + xoff + rr * (ROWS_PER_PASS * 128), crank ^ 1u);
+                    st_cluster_v4(ra, h);
+                    st_cluster_v4(ra + X_BYTES, l);
+                }
             }
             }
             if (!a.y_mn) {
@@ -367,9 +445,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) skge3_tc_kernel(const __grid_co
                 *reinterpret_cast<float4*>(ydst + o) = l;
             }
             }
-            fence_proxy_async();
+            if constexpr (CL > 1) fence_proxy_async_all();
+            else fence_proxy_async();
             __syncwarp();
-            if (lane == 0) mbar_arrive(bar_ready(st));
+            if (lane == 0) {
+                mbar_arrive(bar_ready(st));
+                if constexpr (CL > 1) {
+                    if ((uint32_t) st == crank) mbar_arrive_remote(map_to_cta(bar_ready(st), crank ^ 1u));
+                }
+            }
         }
         // ---------------- epilogue ----------------
         mbar_wait(bar_accum, 0);
@@ -407,6 +491,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) skge3_tc_kernel(const __grid_co
     }
     tc_fence_before();
     __syncthreads();
+    if constexpr (CL > 1) cluster_sync();   // no CTA leaves while its peer can still arrive on its barriers
     if (warp == 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
@@ -481,6 +566,12 @@ int launch_dense_tc_f32(const DenseProblem<float>& p, cudaStream_t st) {
     if (tiles_p > 65535 || tiles_q > 0x7fffffff) return -1;
     const int kshift = (int) (p.u0 & 3);
     const int64_t steps = (p.K + BK - 1) / BK;
+    // Pairs of column tiles share the generated operator tile through a 2-CTA cluster. tc_cluster: 0 never; 1 (default)
+    // where it was measured to pay -- Gaussian operators with K-contiguous data (1.83 -> 1.70 ms at d = n = 1024,
+    // m = 1e5); 2 whenever the tile count is even. It does not pay elsewhere: distributed shared memory moves ~21 B/clk,
+    // so shipping the 32 KB (hi, lo) tile costs as much as the MMAs of the step (Uniform: 1.06 -> 1.44 ms).
+    const int64_t cl_opt = get_option("tc_cluster");
+    const bool cluster = !xmat && (tiles_q % 2 == 0) && (cl_opt == 2 || (cl_opt == 1 && p.family == 'G' && !y_mn));
     // Split K. Two constraints: (1) the tensor core adds into its fp32 accumulator with truncation, a bias that
     // grows linearly with the number of accumulated MMAs (measured: 4.6e-4 relative after 2048 K steps, 1.9e-6
     // after 8), so no partial sum stays in TMEM for more than MAX_CHAIN_STEPS steps; partial sums are added in
@@ -541,21 +632,37 @@ int launch_dense_tc_f32(const DenseProblem<float>& p, cudaStream_t st) {
         a.W = (float*) workspace(6, (size_t) splits * a.P_pad * a.Q_pad * sizeof(float));
         if (!a.W) return fail_cuda(cudaErrorMemoryAllocation, "split-K workspace");
     }
-    static bool attr_done[3] = {false, false, false};
+    static bool attr_done[5] = {false, false, false, false, false};
     const bool gauss = p.family == 'G';
-    const int variant = xmat ? 2 : (gauss ? 1 : 0);
+    const int variant = xmat ? 2 : (cluster ? 3 : 0) + (gauss ? 1 : 0);
     if (!attr_done[variant]) {
-        cudaError_t e =
-            xmat ? cudaFuncSetAttribute(skge3_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM)
-                 : gauss ? cudaFuncSetAttribute(skge3_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM)
-                         : cudaFuncSetAttribute(skge3_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM);
+        cudaError_t e;
+        switch (variant) {
+            case 0: e = cudaFuncSetAttribute(skge3_tc_kernel<false, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM); break;
+            case 1: e = cudaFuncSetAttribute(skge3_tc_kernel<true, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM); break;
+            case 2: e = cudaFuncSetAttribute(skge3_tc_kernel<false, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM); break;
+            case 3: e = cudaFuncSetAttribute(skge3_tc_kernel<false, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM); break;
+            default: e = cudaFuncSetAttribute(skge3_tc_kernel<true, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM); break;
+        }
         if (e != cudaSuccess) { cudaGetLastError(); return -1; }
         attr_done[variant] = true;
     }
     dim3 grid((unsigned) tiles_q, (unsigned) tiles_p, (unsigned) splits);
-    if (xmat) skge3_tc_kernel<false, true><<<grid, TC_THREADS, TC_SMEM, st>>>(tm, tmx, a);
-    else if (gauss) skge3_tc_kernel<true, false><<<grid, TC_THREADS, TC_SMEM, st>>>(tm, tmx, a);
-    else skge3_tc_kernel<false, false><<<grid, TC_THREADS, TC_SMEM, st>>>(tm, tmx, a);
+    if (xmat) skge3_tc_kernel<false, true, 1><<<grid, TC_THREADS, TC_SMEM, st>>>(tm, tmx, a);
+    else if (!cluster) {
+        if (gauss) skge3_tc_kernel<true, false, 1><<<grid, TC_THREADS, TC_SMEM, st>>>(tm, tmx, a);
+        else skge3_tc_kernel<false, false, 1><<<grid, TC_THREADS, TC_SMEM, st>>>(tm, tmx, a);
+    } else {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = grid; cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = TC_SMEM; cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        cudaError_t e = gauss ? cudaLaunchKernelEx(&cfg, skge3_tc_kernel<true, false, 2>, tm, tmx, a)
+                              : cudaLaunchKernelEx(&cfg, skge3_tc_kernel<false, false, 2>, tm, tmx, a);
+        if (e != cudaSuccess) return fail_cuda(e, "cluster launch of the tensor-core sketch kernel");
+    }
     count_launch();
     count_tc_launch();
     RB_CUDA(cudaGetLastError());
