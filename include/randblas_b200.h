@@ -235,7 +235,11 @@ int rb_rsksp3_f64(int fmt, char layout, char opA, char opS, int64_t m, int64_t d
 
 /* ---- tuning / introspection (not part of the reference's surface) ----
  * rb_set_option("dense_path", v): 0 = auto (tensor-core kernels where the shape allows), 1 = force the
- * generic SIMT kernel. rb_get_counter("kernel_launches") counts kernels this library launched. */
+ * generic SIMT kernel. Other switches select among kernels that compute the same result (kept for measurement):
+ * "tc_cluster" (0 / 1 / 2: 2-CTA cluster mode of the float tensor-core kernel: never / where it pays / whenever
+ * possible), "tc_splits", "dmma_uniform_warps", "saso_path", "saso_fill_path", "spdata_path" (DESIGN.md section 4).
+ * rb_get_counter("kernel_launches" | "tensor_core_launches" | "saso_owner_launches") counts kernels this library
+ * launched. */
 int rb_set_option(const char* name, int64_t value);
 /* current value of an option (0 for an unknown name) */
 int64_t rb_get_option(const char* name);
