@@ -20,6 +20,7 @@ static std::atomic<int64_t> g_dmma_uniform{0};       // 1: DMMA kernel in which 
 static std::atomic<int64_t> g_saso_fill_path{0};   // 1: warp-per-vector SASO fill kernel (the 64-bit-index path)
 static std::atomic<int64_t> g_tc_launches{0};
 static std::atomic<int64_t> g_tc_splits{0};
+static std::atomic<int64_t> g_tc_halves{0};      // generator warps split into two halves, one per stage (skge3_f32_tc.cu)
 static std::atomic<int64_t> g_tc_cluster{1};     // 2-CTA clusters sharing the generated operator tile (skge3_f32_tc.cu)
 static std::atomic<int64_t> g_spdata_path{0};   // 0 auto (k-group kernel), 1 force the column-owner kernel (no atomics)
 static std::atomic<int64_t> g_saso_path{0};     // 0 auto, 1 force the atomic kernel, 2 force the owner kernel
@@ -79,6 +80,7 @@ int64_t get_option(const char* name) {
     if (!std::strcmp(name, "saso_fill_path")) return g_saso_fill_path.load();
     if (!std::strcmp(name, "tc_splits")) return g_tc_splits.load();
     if (!std::strcmp(name, "tc_cluster")) return g_tc_cluster.load();
+    if (!std::strcmp(name, "tc_halves")) return g_tc_halves.load();
     if (!std::strcmp(name, "saso_path")) return g_saso_path.load();
     if (!std::strcmp(name, "spdata_path")) return g_spdata_path.load();
     return 0;
@@ -1012,6 +1014,7 @@ int rb_set_option(const char* name, int64_t value) {
     if (!std::strcmp(name, "saso_fill_path")) { g_saso_fill_path = value; return 0; }
     if (!std::strcmp(name, "tc_splits")) { g_tc_splits = value; return 0; }
     if (!std::strcmp(name, "tc_cluster")) { g_tc_cluster = value; return 0; }
+    if (!std::strcmp(name, "tc_halves")) { g_tc_halves = value; return 0; }
     if (!std::strcmp(name, "saso_path")) { g_saso_path = value; return 0; }
     if (!std::strcmp(name, "spdata_path")) { g_spdata_path = value; return 0; }
     return fail(std::string("unknown option ") + name);

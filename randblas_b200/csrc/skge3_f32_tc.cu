@@ -218,7 +218,11 @@ __device__ __forceinline__ float lo_trunc(float y) { return __fsub_rn(y, __uint_
 // shared memories (st.shared::cluster), arriving on both `ready` barriers; every MMA commit that frees a stage arrives on
 // both `empty` barriers (multicast), so a stage is rewritten only when both tensor cores are done with it. Halves the
 // generator work per flop (the binding resource for Gaussian operators).
-template <bool GAUSS, bool XMAT, int CL = 1>
+// HALF: the two halves of the generator warps own one stage each (half h produces every K step with it % 2 == h: four
+// Philox blocks per thread instead of two, and two step times to finish them), so tiles of two consecutive K steps are
+// being generated at the same time. The generators are latency-bound, not issue-bound (see the cluster note above);
+// this doubles the independent work in flight per scheduler. K-contiguous data, generated operator, no cluster.
+template <bool GAUSS, bool XMAT, int CL = 1, bool HALF = false>
 __global__ void __launch_bounds__(TC_THREADS, 1) skge3_tc_kernel(const __grid_constant__ CUtensorMap tmY,
                                                                  const __grid_constant__ CUtensorMap tmX, const TcArgs a) {
     extern __shared__ uint8_t smem_raw[];
@@ -241,7 +245,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) skge3_tc_kernel(const __grid_co
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(bar_full(s), 1);
             // in a cluster the stage this CTA generates itself gets local arrivals only; the other one also the peer's
-            uint32_t ready_count = GEN_WARPS;
+            uint32_t ready_count = HALF ? GEN_WARPS / 2 : GEN_WARPS;
             if constexpr (CL > 1) {
                 uint32_t rk;
                 asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rk));
@@ -342,8 +346,59 @@ __global__ void __launch_bounds__(TC_THREADS, 1) skge3_tc_kernel(const __grid_co
     } else {
         // ---------------- generators ----------------
         const int gt = threadIdx.x - 64;
-        const int c = gt & 7, r0 = gt >> 3;
         const uint64_t seed_lo = ((uint64_t) a.ctr.c1 << 32) | a.ctr.c0, seed_hi = ((uint64_t) a.ctr.c3 << 32) | a.ctr.c2;
+        if constexpr (HALF) {
+            constexpr int HT = 16 * GEN_WARPS;                 // threads per half
+            constexpr int HB = (BM * BK / 4) / HT;             // Philox blocks per thread and tile
+            const int half = gt / HT, ht = gt % HT;
+            const int hc = ht & 7, hr = ht >> 3;               // 16-byte chunk of the row, first row; rows hr + (HT / 8) * rr
+            uint64_t hoff[HB];
+#pragma unroll
+            for (int rr = 0; rr < HB; ++rr)
+                hoff[rr] = (uint64_t) ((a.v0 + i0 + hr + (HT / 8) * rr) * a.R + a.ublk0 + hc) + 8ull * (uint64_t) (s_begin + half);
+            const uint32_t hxoff = (uint32_t) hr * 128u + (uint32_t) ((hc ^ (hr & 7)) << 4);
+            uint8_t* stage = smem + half * STAGE_BYTES;        // stage == half, always
+            for (int it = half; it < nsteps; it += 2) {
+                const uint32_t ph = (uint32_t) ((it >> 1) & 1);
+                mbar_wait(bar_empty(half), ph ^ 1);
+#pragma unroll
+                for (int rr = 0; rr < HB; ++rr) {
+                    const uint64_t lo = seed_lo + hoff[rr];
+                    const uint64_t hi = seed_hi + (lo < seed_lo ? 1ull : 0ull);
+                    hoff[rr] += 16;
+                    const Ctr128 cc{(uint32_t) lo, (uint32_t) (lo >> 32), (uint32_t) hi, (uint32_t) (hi >> 32)};
+                    float4 f = transform4<GAUSS>(philox4x32_10(cc, a.key), logtab);
+                    if (a.kshift) {
+                        const float4 g = transform4<GAUSS>(philox4x32_10(ctr_add(cc, 1), a.key), logtab);
+                        if (a.kshift == 1) f = make_float4(f.y, f.z, f.w, g.x);
+                        else if (a.kshift == 2) f = make_float4(f.z, f.w, g.x, g.y);
+                        else f = make_float4(f.w, g.x, g.y, g.z);
+                    }
+                    float4 h, l;
+                    split_rn(finish_sample<float, GAUSS>(f.x), h.x, l.x);
+                    split_rn(finish_sample<float, GAUSS>(f.y), h.y, l.y);
+                    split_rn(finish_sample<float, GAUSS>(f.z), h.z, l.z);
+                    split_rn(finish_sample<float, GAUSS>(f.w), h.w, l.w);
+                    *reinterpret_cast<float4*>(stage + hxoff + rr * ((HT / 8) * 128)) = h;
+                    *reinterpret_cast<float4*>(stage + X_BYTES + hxoff + rr * ((HT / 8) * 128)) = l;
+                }
+                mbar_wait(bar_full(half), ph);
+                const uint8_t* ysrc = stage + 2 * X_BYTES;
+                uint8_t* ydst = stage + 2 * X_BYTES + Y_BYTES;
+#pragma unroll
+                for (int q = 0; q < (int) (Y_BYTES / 16) / HT; ++q) {
+                    const uint32_t o = (uint32_t) (ht + HT * q) * 16u;
+                    const float4 y = *reinterpret_cast<const float4*>(ysrc + o);
+                    float4 l;
+                    l.x = lo_trunc(y.x); l.y = lo_trunc(y.y); l.z = lo_trunc(y.z); l.w = lo_trunc(y.w);
+                    *reinterpret_cast<float4*>(ydst + o) = l;
+                }
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_ready(half));
+            }
+        } else {
+        const int c = gt & 7, r0 = gt >> 3;
         constexpr int ROWS_PER_PASS = 4 * GEN_WARPS;      // rows of X covered by one pass of all generator threads
         // In a cluster the two CTAs take turns: CTA r generates the whole tile of every K step whose stage is r and writes
         // it into both shared memories. (Splitting the ROWS of each tile between the CTAs was measured first and did not
@@ -455,6 +510,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) skge3_tc_kernel(const __grid_co
                 }
             }
         }
+        }   // !HALF
         // ---------------- epilogue ----------------
         mbar_wait(bar_accum, 0);
         tc_fence_after();
@@ -632,26 +688,34 @@ int launch_dense_tc_f32(const DenseProblem<float>& p, cudaStream_t st) {
         a.W = (float*) workspace(6, (size_t) splits * a.P_pad * a.Q_pad * sizeof(float));
         if (!a.W) return fail_cuda(cudaErrorMemoryAllocation, "split-K workspace");
     }
-    static bool attr_done[5] = {false, false, false, false, false};
+    static bool attr_done[7] = {};
     const bool gauss = p.family == 'G';
-    const int variant = xmat ? 2 : (cluster ? 3 : 0) + (gauss ? 1 : 0);
+    // tc_halves: 1 (default) = the generator warps work on two K steps at a time where the kernel supports it
+    const bool halves = !xmat && !cluster && !y_mn && get_option("tc_halves") != 0;
+    const int variant = xmat ? 2 : (cluster ? 3 : (halves ? 5 : 0)) + (gauss ? 1 : 0);
+    auto set_attr = [&](auto kern) { return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM); };
     if (!attr_done[variant]) {
         cudaError_t e;
         switch (variant) {
-            case 0: e = cudaFuncSetAttribute(skge3_tc_kernel<false, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM); break;
-            case 1: e = cudaFuncSetAttribute(skge3_tc_kernel<true, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM); break;
-            case 2: e = cudaFuncSetAttribute(skge3_tc_kernel<false, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM); break;
-            case 3: e = cudaFuncSetAttribute(skge3_tc_kernel<false, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM); break;
-            default: e = cudaFuncSetAttribute(skge3_tc_kernel<true, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM); break;
+            case 0: e = set_attr(skge3_tc_kernel<false, false, 1, false>); break;
+            case 1: e = set_attr(skge3_tc_kernel<true, false, 1, false>); break;
+            case 2: e = set_attr(skge3_tc_kernel<false, true, 1, false>); break;
+            case 3: e = set_attr(skge3_tc_kernel<false, false, 2, false>); break;
+            case 4: e = set_attr(skge3_tc_kernel<true, false, 2, false>); break;
+            case 5: e = set_attr(skge3_tc_kernel<false, false, 1, true>); break;
+            default: e = set_attr(skge3_tc_kernel<true, false, 1, true>); break;
         }
         if (e != cudaSuccess) { cudaGetLastError(); return -1; }
         attr_done[variant] = true;
     }
     dim3 grid((unsigned) tiles_q, (unsigned) tiles_p, (unsigned) splits);
-    if (xmat) skge3_tc_kernel<false, true, 1><<<grid, TC_THREADS, TC_SMEM, st>>>(tm, tmx, a);
-    else if (!cluster) {
-        if (gauss) skge3_tc_kernel<true, false, 1><<<grid, TC_THREADS, TC_SMEM, st>>>(tm, tmx, a);
-        else skge3_tc_kernel<false, false, 1><<<grid, TC_THREADS, TC_SMEM, st>>>(tm, tmx, a);
+    if (xmat) skge3_tc_kernel<false, true, 1, false><<<grid, TC_THREADS, TC_SMEM, st>>>(tm, tmx, a);
+    else if (halves) {
+        if (gauss) skge3_tc_kernel<true, false, 1, true><<<grid, TC_THREADS, TC_SMEM, st>>>(tm, tmx, a);
+        else skge3_tc_kernel<false, false, 1, true><<<grid, TC_THREADS, TC_SMEM, st>>>(tm, tmx, a);
+    } else if (!cluster) {
+        if (gauss) skge3_tc_kernel<true, false, 1, false><<<grid, TC_THREADS, TC_SMEM, st>>>(tm, tmx, a);
+        else skge3_tc_kernel<false, false, 1, false><<<grid, TC_THREADS, TC_SMEM, st>>>(tm, tmx, a);
     } else {
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = grid; cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = TC_SMEM; cfg.stream = st;
@@ -659,8 +723,8 @@ int launch_dense_tc_f32(const DenseProblem<float>& p, cudaStream_t st) {
         at[0].id = cudaLaunchAttributeClusterDimension;
         at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
         cfg.attrs = at; cfg.numAttrs = 1;
-        cudaError_t e = gauss ? cudaLaunchKernelEx(&cfg, skge3_tc_kernel<true, false, 2>, tm, tmx, a)
-                              : cudaLaunchKernelEx(&cfg, skge3_tc_kernel<false, false, 2>, tm, tmx, a);
+        cudaError_t e = gauss ? cudaLaunchKernelEx(&cfg, skge3_tc_kernel<true, false, 2, false>, tm, tmx, a)
+                              : cudaLaunchKernelEx(&cfg, skge3_tc_kernel<false, false, 2, false>, tm, tmx, a);
         if (e != cudaSuccess) return fail_cuda(e, "cluster launch of the tensor-core sketch kernel");
     }
     count_launch();
