@@ -471,31 +471,37 @@ def test_example_total_least_squares_matches_reference_pipeline(gpu, port):
     assert relerr(Bg, B) < 1e-12
 
 
-def test_tensor_core_float_sketch_cluster_mode_is_bit_identical(gpu):
-    """The 2-CTA cluster variant of the tcgen05 kernel (neighbouring column tiles take turns generating the operator tile
-    and write it into both shared memories) computes exactly what the single-CTA kernel computes: same values, same
-    MMA order per CTA. Forced on (tc_cluster = 2) for Uniform and Gaussian operators, K- and Q-contiguous data, a window
-    that straddles Philox blocks, an odd number of row tiles."""
+def test_tensor_core_float_sketch_cluster_and_halves_modes_are_bit_identical(gpu):
+    """Two scheduling variants of the tcgen05 kernel compute exactly what the plain kernel computes (same values, same
+    MMA order per CTA): the 2-CTA cluster (neighbouring column tiles take turns generating the operator tile and write
+    it into both shared memories; tc_cluster = 2 forces it) and the two-halves generator (each half of the generator
+    warps owns one stage; tc_halves = 1). Uniform and Gaussian operators, K- and Q-contiguous data, a window that
+    straddles Philox blocks, an odd number of row tiles."""
     import randblas_b200 as rb
     import torch
     g = torch.Generator(device="cuda").manual_seed(3)
-    default_opt = rb.get_option("tc_cluster")
-    for (d, m, n, fam, lay, ro, co) in ((256, 4096, 512, "U", "C", 0, 0), (300, 9000, 1024, "G", "C", 0, 0),
-                                        (300, 9000, 512, "G", "R", 2, 7), (129, 6000, 1536, "U", "R", 1, 4),
-                                        (1024, 20000, 1024, "G", "C", 0, 0)):
-        S = rb.DenseSkOp(rb.DenseDist(d + ro, m + co, fam, "L"), rb.RNGState(77), np.float32)
-        A = torch.randn(m * n, dtype=torch.float32, device="cuda", generator=g)
-        lda, ldb = (m, d) if lay == "C" else (n, n)
-        outs = []
-        for opt in (0, 2):
-            rb.set_option("tc_cluster", opt)
-            B = torch.full((d * n,), float("nan"), dtype=torch.float32, device="cuda")
-            before = rb.counter("tensor_core_launches")
-            rb.sketch_general(lay, "N", "N", d, n, m, 1.0, S, ro, co, A, lda, 0.0, B, ldb)
-            assert rb.counter("tensor_core_launches") > before
-            outs.append(B)
-        rb.set_option("tc_cluster", default_opt)
-        assert torch.equal(outs[0], outs[1]), (d, m, n, fam, lay)
+    d_cluster, d_halves = rb.get_option("tc_cluster"), rb.get_option("tc_halves")
+    try:
+        for (d, m, n, fam, lay, ro, co) in ((256, 4096, 512, "U", "C", 0, 0), (300, 9000, 1024, "G", "C", 0, 0),
+                                            (300, 9000, 512, "G", "R", 2, 7), (129, 6000, 1536, "U", "R", 1, 4),
+                                            (200, 8192, 300, "U", "C", 5, 3), (1024, 20000, 1024, "G", "C", 0, 0)):
+            S = rb.DenseSkOp(rb.DenseDist(d + ro, m + co, fam, "L"), rb.RNGState(77), np.float32)
+            A = torch.randn(m * n, dtype=torch.float32, device="cuda", generator=g)
+            lda, ldb = (m, d) if lay == "C" else (n, n)
+            outs = []
+            for cl, hv in ((0, 0), (2, 0), (0, 1)):
+                rb.set_option("tc_cluster", cl)
+                rb.set_option("tc_halves", hv)
+                B = torch.full((d * n,), float("nan"), dtype=torch.float32, device="cuda")
+                before = rb.counter("tensor_core_launches")
+                rb.sketch_general(lay, "N", "N", d, n, m, 1.0, S, ro, co, A, lda, 0.0, B, ldb)
+                assert rb.counter("tensor_core_launches") > before
+                outs.append(B)
+            assert torch.equal(outs[0], outs[1]), ("cluster", d, m, n, fam, lay)
+            assert torch.equal(outs[0], outs[2]), ("halves", d, m, n, fam, lay)
+    finally:
+        rb.set_option("tc_cluster", d_cluster)
+        rb.set_option("tc_halves", d_halves)
 
 
 def test_sketch_identity_reproduces_operator(gpu, port):

@@ -48,6 +48,13 @@ def main():
         A = torch.randn(m * n, dtype=torch.float32, device="cuda")
         B = torch.zeros(d * n, dtype=torch.float32, device="cuda")
         f = lambda: rb.sketch_general("C", "N", "N", d, n, m, 1.0, S, 0, 0, A, m, 0.0, B, d)
+    elif what == "dense_f32_gauss":
+        d, m, n = 1024, 100000, 1024
+        rb.set_option("tc_cluster", 0)
+        S = rb.DenseSkOp(rb.DenseDist(d, m, rb.ScalarDist.Gaussian), rb.RNGState(1997), np.float32)
+        A = torch.randn(m * n, dtype=torch.float32, device="cuda")
+        B = torch.zeros(d * n, dtype=torch.float32, device="cuda")
+        f = lambda: rb.sketch_general("C", "N", "N", d, n, m, 1.0, S, 0, 0, A, m, 0.0, B, d)
     elif what == "dense_f64":
         d, m, n = 4096, 32768, 512
         S = rb.DenseSkOp(rb.DenseDist(d, 4000000, rb.ScalarDist.Gaussian), rb.RNGState(1997), np.float64)
