@@ -20,7 +20,7 @@ static std::atomic<int64_t> g_dmma_uniform{0};       // 1: DMMA kernel in which 
 static std::atomic<int64_t> g_saso_fill_path{0};   // 1: warp-per-vector SASO fill kernel (the 64-bit-index path)
 static std::atomic<int64_t> g_tc_launches{0};
 static std::atomic<int64_t> g_tc_splits{0};
-static std::atomic<int64_t> g_tc_halves{0};      // generator warps split into two halves, one per stage (skge3_f32_tc.cu)
+static std::atomic<int64_t> g_tc_halves{1};      // generator warps split into two halves, one per stage (skge3_f32_tc.cu)
 static std::atomic<int64_t> g_tc_cluster{1};     // 2-CTA clusters sharing the generated operator tile (skge3_f32_tc.cu)
 static std::atomic<int64_t> g_spdata_path{0};   // 0 auto (k-group kernel), 1 force the column-owner kernel (no atomics)
 static std::atomic<int64_t> g_saso_path{0};     // 0 auto, 1 force the atomic kernel, 2 force the owner kernel
