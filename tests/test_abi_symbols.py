@@ -66,3 +66,24 @@ def test_argument_errors_without_gpu():
         rb.sketch_general("C", "N", "N", 4, 3, 8, 1.0, S, 0, 0, A, 7, 0.0, B, 4)
     with pytest.raises(rb.RandBLASError):  # full-operator overload dimension check (skge.hh:1089-1095)
         rb.sketch_general("C", "N", "N", 3, 3, 8, 1.0, S, A, 8, 0.0, B, 4)
+
+
+def test_sampling_utilities_argument_checks_and_state_arithmetic_without_gpu():
+    """The index-sampling entry points validate their arguments and advance the state before any CUDA call:
+    k == 0 returns the state unchanged (util.hh:505-511, 538-544: no block is consumed), negative sizes are rejected."""
+    import randblas_b200 as rb
+    st = rb.RNGState(7).incr(3456)
+    s = np.zeros(1, np.int64)
+    assert rb.sample_indices_iid_uniform(40, 0, s, st) == st
+    assert rb.sample_indices_iid(1, np.ones(1, np.float32), 0, s, st) == st
+    with pytest.raises(rb.RandBLASError):
+        rb.sample_indices_iid_uniform(40, -1, s, st)
+    with pytest.raises(rb.RandBLASError):
+        rb.sample_indices_iid(-1, np.ones(1, np.float32), 1, s, st)
+    with pytest.raises(rb.RandBLASError):          # int32 samples cannot index 2^40 values
+        rb.sample_indices_iid_uniform(1 << 40, 4, np.zeros(4, np.int32), st)
+    rb.weights_to_cdf(0, np.zeros(0, np.float32))      # empty: nothing to do (util.hh:461-472 with n = 0)
+    assert rb.get_option("tc_cluster") in (0, 1, 2)
+    rb.set_option("tc_cluster", rb.get_option("tc_cluster"))
+    with pytest.raises(rb.RandBLASError):
+        rb.set_option("no_such_option", 1)
