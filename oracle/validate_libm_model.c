@@ -30,7 +30,9 @@ static const double LOGTAB[32] = {
 static double BIG[544][2];
 static inline float uneg11(uint32_t w){ return fmaf((float)(int32_t)w, 0x1p-31f, 0x1p-32f); }
 static inline float u01(uint32_t w){ return fmaf((float)w, 0x1p-32f, 0x1p-33f); }
-static inline double f2d_pos(uint32_t u){ return u2d((uint64_t)u * 0x20000000ull + 0x3800000000000000ull); }
+// the device shifts the float's bits into double position WITHOUT re-biasing the exponent (value * 2^-896) and
+// compensates in the operand it multiplies with: invc * 2^896 in the table, fma(xd', 2^896, t) for the angle
+static inline double f2d_pos_unbiased(uint32_t u){ return u2d((uint64_t)u * 0x20000000ull); }
 
 static const double QT[5] = {0x1.921fb54442d18p+1, 0x1.921fb54442d18p+0, 0.0, -0x1.921fb54442d18p+0, -0x1.921fb54442d18p+1};  // -n pi/2, n = -2..2
 static inline void model_sincos(uint32_t w, float* sn, float* cs){
@@ -40,10 +42,10 @@ static inline void model_sincos(uint32_t w, float* sn, float* cs){
     const uint32_t tb = f2u(fmaf(x, 2.0f, 12582912.0f));
     const int n = (int)(tb - 0x4B400000u);
     const uint32_t u = f2u(th);
-    uint64_t xb = (uint64_t)(u & 0x7fffffffu) * 0x20000000ull + 0x3800000000000000ull;
+    uint64_t xb = (uint64_t)(u & 0x7fffffffu) * 0x20000000ull;
     xb |= (uint64_t)(u & 0x80000000u) << 32;
-    const double xd = u2d(xb);
-    const double xr = xd + QT[n + 2];
+    const double xd = u2d(xb);                      // theta * 2^-896
+    const double xr = fma(xd, 0x1p896, QT[n + 2]);
     const uint32_t sinflip = (tb * 0x40000000u + 0x40000000u) & 0x80000000u;   // (n + 1) & 2
     const uint32_t cosflip = (tb * 0x40000000u) & 0x80000000u;                 // n & 2
     const int swap = tb & 1;                                                   // n & 1
@@ -64,7 +66,7 @@ static inline float model_log(uint32_t w){
     const int32_t tmp = (int32_t)(ix - 0x3f330000u);
     const int idx = (tmp >> 19) + 528;
     const uint32_t iz = ix - ((uint32_t)tmp & 0xff800000u);
-    const double z = f2d_pos(iz);
+    const double z = f2d_pos_unbiased(iz);          // z * 2^-896
     const double r = fma(z, BIG[idx][0], -1.0);
     const double r2 = r * r;
     double y = fma(A1, r, A2);
@@ -75,7 +77,7 @@ static inline float model_log(uint32_t w){
 int main(void){
     for (int k = -33; k <= 0; ++k)
         for (int i = 0; i < 16; ++i) {
-            BIG[(k + 33) * 16 + i][0] = LOGTAB[2 * i];
+            BIG[(k + 33) * 16 + i][0] = ldexp(LOGTAB[2 * i], 896);
             BIG[(k + 33) * 16 + i][1] = fma((double)k, LN2, LOGTAB[2 * i + 1]);
         }
     long bad_sc = 0, bad_log = 0, bad_idx = 0;

@@ -58,7 +58,7 @@ const double2* logf_table_device() {
         std::vector<double2> h(LOGF_TABLE_ENTRIES);
         for (int k = -33; k <= 0; ++k)
             for (int i = 0; i < 16; ++i) {
-                h[(k + 33) * 16 + i].x = h_logf_tab[2 * i];
+                h[(k + 33) * 16 + i].x = std::ldexp(h_logf_tab[2 * i], 896);      // invc * 2^896 (philox.cuh: logf_exact)
                 h[(k + 33) * 16 + i].y = std::fma((double) k, 0x1.62e42fefa39efp-1, h_logf_tab[2 * i + 1]);
             }
         const double hpi = 0x1.921fb54442d18p+0;
