@@ -21,7 +21,8 @@
  *     RandBLAS::Error before touching data, exceptions.hh:57-95); RB_ERR_CUDA = a CUDA error.
  *     rb_last_error() returns the thread-local message. No exception crosses this boundary.
  *   - the library never allocates or frees caller-visible memory. Internal workspace is cached per
- *     device and released by rb_release_workspace().
+ *     (device, stream, calling host thread), so calls on different streams or from different threads
+ *     never share scratch memory; rb_release_workspace() frees it (no call may be in flight).
  */
 #ifndef RANDBLAS_B200_H
 #define RANDBLAS_B200_H
@@ -232,6 +233,55 @@ int rb_rsksp3_f64(int fmt, char layout, char opA, char opS, int64_t m, int64_t d
                   int idx_bytes, int64_t ro_a, int64_t co_a, int64_t D_rows, int64_t D_cols, char family,
                   char major_axis, const uint32_t ctr[4], const uint32_t key[2], int64_t ro_s, int64_t co_s,
                   double beta, double* B, int64_t ldb, void* stream);
+
+/* ---- multi-GPU: the m-sharded left sketch and its one exchange step ----
+ * Distributes the reference's own blocked form of a left sketch (RandBLAS/skge.hh:174-181; rtd/source/tutorial/
+ * sketch_updates.rst:198-213: row blocks of A against column blocks of S selected with (ro_s, co_s), block products
+ * accumulated with beta = 1): the m_total rows of op(A) are split into nranks contiguous blocks whose starts are
+ * multiples of 4 (rb_mshard_block), GPU g holds block g as A_local (m_local x n in `layout`, leading dimension lda)
+ * and regenerates only the matching columns of the operator; the d x n partial products are summed over NVLink by
+ * one NCCL collective inside the library:
+ *   mode 0: reduce-scatter -- B_out (d*n / nranks entries, requires d*n % nranks == 0) is this rank's contiguous
+ *           slice, in memory order, of the packed result (ldb = d for ColMajor, n for RowMajor);
+ *   mode 1: all-reduce     -- B_out (d*n entries) is the whole packed result on every rank.
+ * B_out = alpha * op(S[ro_s:, co_s:]) * op(A) + beta * B_out. All data pointers are DEVICE pointers of the
+ * communicator's GPU, which must be the current device; the call is ordered on `stream` and asynchronous.
+ * The sum order differs from the single-GPU kernel's, so results agree to rounding (1e-12 double / 1e-5 float
+ * relative Frobenius), not bit for bit. NCCL is loaded at run time (dlopen libnccl.so.2); a communicator of one
+ * rank needs no NCCL.
+ *
+ * One process per GPU: rank 0 calls rb_comm_unique_id, ships the RB_COMM_ID_BYTES bytes to the other ranks by any
+ * means (MPI, a file, torch.distributed), every rank calls rb_comm_init_rank with its GPU current.
+ * One process for all GPUs: rb_comm_init(ndev, devices or NULL = 0..ndev-1, comms[ndev]) and the _all entry point,
+ * which takes one A_local / lda / B_out / stream per GPU and issues the collective as one NCCL group. */
+#define RB_COMM_ID_BYTES 128
+typedef struct rb_comm* rb_comm_t;
+int rb_comm_unique_id(void* id128);
+int rb_comm_init_rank(int nranks, int rank, const void* id128, rb_comm_t* comm);
+int rb_comm_init(int ndev, const int* devices, rb_comm_t* comms);
+int rb_comm_destroy(rb_comm_t comm);
+/* info = {nranks, rank, device, NCCL version code (0 if NCCL is not loaded)} */
+int rb_comm_info(rb_comm_t comm, int64_t info[4]);
+/* rows [start, start + count) of op(A) owned by `rank` (pure arithmetic) */
+int rb_mshard_block(int64_t m_total, int nranks, int rank, int64_t* start, int64_t* count);
+int rb_lskge3_mshard_f32(rb_comm_t comm, char layout, char opS, char opA, int64_t d, int64_t n, int64_t m_total,
+                         float alpha, int64_t D_rows, int64_t D_cols, char family, char major_axis,
+                         const uint32_t ctr[4], const uint32_t key[2], int64_t ro_s, int64_t co_s, const float* A_local,
+                         int64_t lda, float beta, float* B_out, int mode, void* stream);
+int rb_lskge3_mshard_f64(rb_comm_t comm, char layout, char opS, char opA, int64_t d, int64_t n, int64_t m_total,
+                         double alpha, int64_t D_rows, int64_t D_cols, char family, char major_axis,
+                         const uint32_t ctr[4], const uint32_t key[2], int64_t ro_s, int64_t co_s, const double* A_local,
+                         int64_t lda, double beta, double* B_out, int mode, void* stream);
+int rb_lskge3_mshard_all_f32(int ndev, const rb_comm_t* comms, char layout, char opS, char opA, int64_t d, int64_t n,
+                             int64_t m_total, float alpha, int64_t D_rows, int64_t D_cols, char family, char major_axis,
+                             const uint32_t ctr[4], const uint32_t key[2], int64_t ro_s, int64_t co_s,
+                             const float* const* A_local, const int64_t* lda, float beta, float* const* B_out, int mode,
+                             void* const* streams);
+int rb_lskge3_mshard_all_f64(int ndev, const rb_comm_t* comms, char layout, char opS, char opA, int64_t d, int64_t n,
+                             int64_t m_total, double alpha, int64_t D_rows, int64_t D_cols, char family, char major_axis,
+                             const uint32_t ctr[4], const uint32_t key[2], int64_t ro_s, int64_t co_s,
+                             const double* const* A_local, const int64_t* lda, double beta, double* const* B_out,
+                             int mode, void* const* streams);
 
 /* ---- tuning / introspection (not part of the reference's surface) ----
  * rb_set_option("dense_path", v): 0 = auto (tensor-core kernels where the shape allows), 1 = force the

@@ -212,20 +212,45 @@ def _dtype_of(x):
 
 
 def _ptr(x):
+    """Address of a buffer. Buffers are raw memory with explicit leading dimensions, as in the reference, so a
+    strided view (A.T, a slice) would be read as if it were dense: reject it."""
     if x is None:
         return 0
     if torch is not None and isinstance(x, torch.Tensor):
+        if not x.is_contiguous():
+            raise RandBLASError("buffers must be contiguous tensors (pass layout / leading dimensions, not strided views)")
         return x.data_ptr()
-    assert isinstance(x, np.ndarray)
+    if not isinstance(x, np.ndarray):
+        raise RandBLASError(f"unsupported buffer type {type(x).__name__}: expected a torch tensor or a numpy array")
+    if not (x.flags.c_contiguous or x.flags.f_contiguous):
+        raise RandBLASError("buffers must be contiguous arrays (pass layout / leading dimensions, not strided views)")
     return x.ctypes.data
 
 
 def _stream(*bufs):
+    """Current stream of the device the CUDA buffers live on (0 = default stream for host buffers). All CUDA
+    buffers of one call must live on one device, and that device must be the current one."""
+    dev = None
     if torch is not None:
         for b in bufs:
             if isinstance(b, torch.Tensor) and b.is_cuda:
-                return torch.cuda.current_stream(b.device).cuda_stream
+                if dev is None:
+                    dev = b.device
+                elif b.device != dev:
+                    raise RandBLASError(f"buffers live on different devices ({dev} and {b.device})")
+        if dev is not None:
+            if dev.index is not None and dev.index != torch.cuda.current_device():
+                raise RandBLASError(f"buffers live on {dev} but the current device is cuda:{torch.cuda.current_device()}")
+            return torch.cuda.current_stream(dev).cuda_stream
     return 0
+
+
+def _same_dtype(*bufs):
+    """The scalar type shared by the data buffers of a call (the reference's template parameter T)."""
+    dts = {np.dtype(_dtype_of(b)) for b in bufs if b is not None}
+    if len(dts) != 1:
+        raise RandBLASError(f"buffers of one call must share one scalar type, got {sorted(str(d) for d in dts)}")
+    return dts.pop()
 
 
 def _sfx(dt):
@@ -380,8 +405,8 @@ def sketch_general(layout, op1, op2, x, y, z, alpha, *rest):
 
 
 def _skge(left, layout, opS, opA, d, n, m, alpha, S, ro_s, co_s, A, lda, beta, B, ldb):
-    sfx, t = _sfx(_dtype_of(B))
-    st = _stream(A, B)
+    sfx, t = _sfx(_same_dtype(A, B, getattr(S, "buff", None), getattr(S, "vals", None) if getattr(S, "nnz", -1) >= 0 else None))
+    st = _stream(A, B, getattr(S, "buff", None))
     seed = S.seed_state
     if isinstance(S, DenseSkOp):
         D = S.dist
@@ -498,7 +523,7 @@ def left_spmm(layout, opA, opB, d, n, m, alpha, A, ro_a, co_a, B, ldb, beta, C, 
     """RandBLAS::sparse_data::left_spmm (RandBLAS/sparse_data/spmm_dispatch.hh:52-178):
     C(d x n) = alpha * op(A_sp[ro_a:, co_a:])(d x m) * op(B)(m x n) + beta * C."""
     _require(A.index_base == 0, "A.index_base == IndexBase::Zero")      # spmm_dispatch.hh:92
-    sfx, t = _sfx(_dtype_of(C))
+    sfx, t = _sfx(_same_dtype(A.vals, B, C))
     ib = np.dtype(_dtype_of(A._idx0)).itemsize
     call(f"rb_spmm_{sfx}", "iicccqqq" + t + "qqqpppi" + "qqpq" + t + "pqp", 1, A._fmt, layout, opA, opB, int(d), int(n),
          int(m), alpha, A.n_rows, A.n_cols, A.nnz, _ptr(A.vals), _ptr(A._idx0), _ptr(A._idx1), ib, int(ro_a), int(co_a),
@@ -509,7 +534,7 @@ def right_spmm(layout, opA, opB, m, d, n, alpha, A, lda, B, i_off, j_off, beta, 
     """RandBLAS::sparse_data::right_spmm (spmm_dispatch.hh:180-219):
     C(m x d) = alpha * op(A)(m x n) * op(B_sp[i_off:, j_off:])(n x d) + beta * C, A dense, B sparse."""
     _require(B.index_base == 0, "B.index_base == IndexBase::Zero")
-    sfx, t = _sfx(_dtype_of(C))
+    sfx, t = _sfx(_same_dtype(B.vals, A, C))
     ib = np.dtype(_dtype_of(B._idx0)).itemsize
     call(f"rb_spmm_{sfx}", "iicccqqq" + t + "qqqpppi" + "qqpq" + t + "pqp", 0, B._fmt, layout, opB, opA, int(d), int(n),
          int(m), alpha, B.n_rows, B.n_cols, B.nnz, _ptr(B.vals), _ptr(B._idx0), _ptr(B._idx1), ib, int(i_off), int(j_off),
@@ -530,9 +555,9 @@ def sketch_sparse(layout, op1, op2, x, y, z, alpha, *rest):
         left, opA, opS, m, d, n = False, op1, op2, int(x), int(y), int(z)
     _require(isinstance(S, DenseSkOp), "S is a DenseSkOp")
     _require(A.index_base == 0, "A.index_base == IndexBase::Zero")      # spmm_dispatch.hh:92
-    sfx, t = _sfx(_dtype_of(B))
+    sfx, t = _sfx(_same_dtype(A.vals, B))
     D, seed = S.dist, S.seed_state
-    st = _stream(B, A.vals)
+    st = _stream(B, A.vals, A._idx0, A._idx1)
     ib = np.dtype(_dtype_of(A._idx0)).itemsize
     if left:
         call(f"rb_lsksp3_{sfx}", "icccqqq" + t + "qqccpp" + "qq" + "qqqpppi" + "qq" + t + "pqp", A._fmt, layout, opS,

@@ -4,7 +4,9 @@
 #include <atomic>
 #include <cmath>
 #include <cstring>
+#include <map>
 #include <mutex>
+#include <thread>
 #include <string>
 #include <vector>
 #include "../../include/randblas_b200.h"
@@ -23,6 +25,7 @@ static std::atomic<int64_t> g_tc_splits{0};
 static std::atomic<int64_t> g_tc_halves{1};      // generator warps split into two halves, one per stage (skge3_f32_tc.cu)
 static std::atomic<int64_t> g_tc_cluster{1};     // 2-CTA clusters sharing the generated operator tile (skge3_f32_tc.cu)
 static std::atomic<int64_t> g_spdata_path{0};   // 0 auto (k-group kernel), 1 force the column-owner kernel (no atomics)
+static std::atomic<int64_t> g_h2d_chunk_mb{64};   // block size of the host-pointer sketch pipeline (MB of A per block)
 static std::atomic<int64_t> g_saso_path{0};     // 0 auto, 1 force the atomic kernel, 2 force the owner kernel
 
 void set_error(const std::string& m) { g_err = m; }
@@ -82,41 +85,86 @@ int64_t get_option(const char* name) {
     if (!std::strcmp(name, "tc_cluster")) return g_tc_cluster.load();
     if (!std::strcmp(name, "tc_halves")) return g_tc_halves.load();
     if (!std::strcmp(name, "saso_path")) return g_saso_path.load();
+    if (!std::strcmp(name, "h2d_chunk_mb")) return g_h2d_chunk_mb.load();
     if (!std::strcmp(name, "spdata_path")) return g_spdata_path.load();
     return 0;
 }
 
-// ---- cached workspace: per device, 8 slots, grow-only ----
+// ---- cached workspace: grow-only buffers owned by one (device, stream, host thread) ----
+// Every call's intermediates (split-K partials, bucket arrays, scan scratch, staging) live in buffers keyed by the
+// device, the stream the call is ordered on and the calling host thread, so calls on different streams or from
+// different threads never share scratch memory (the reference is re-entrant; SURVEY.md section 8b "Threading").
+// Calls on ONE stream from ONE thread reuse the same buffers, which is safe because they are stream-ordered.
+struct WsKey {
+    int dev; cudaStream_t st; std::thread::id tid;
+    bool operator<(const WsKey& o) const {
+        if (dev != o.dev) return dev < o.dev;
+        if (st != o.st) return st < o.st;
+        return tid < o.tid;
+    }
+};
 struct WsSlot { void* p = nullptr; size_t bytes = 0; };
+struct WsSet { WsSlot s[RB_WS_SLOTS]; };
 static std::mutex g_ws_mu;
-static WsSlot g_ws[64][8];
+static std::map<WsKey, WsSet> g_ws;
 
-void* workspace(int slot, size_t bytes) {
+void* workspace(int slot, size_t bytes, cudaStream_t st) {
     int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64 || slot < 0 || slot >= 8) return nullptr;
-    std::lock_guard<std::mutex> lk(g_ws_mu);
-    WsSlot& s = g_ws[dev][slot];
+    if (cudaGetDevice(&dev) != cudaSuccess || slot < 0 || slot >= RB_WS_SLOTS) { cudaGetLastError(); return nullptr; }
     if (bytes == 0) bytes = 16;
-    if (s.bytes < bytes) {
-        if (s.p) { cudaDeviceSynchronize(); cudaFree(s.p); s.p = nullptr; s.bytes = 0; }
+    WsSlot* s;
+    {
+        std::lock_guard<std::mutex> lk(g_ws_mu);
+        s = &g_ws[WsKey{dev, st, std::this_thread::get_id()}].s[slot];     // std::map: references stay valid
+    }
+    if (s->bytes < bytes) {
+        // only this thread's earlier calls on this stream can still be using the old buffer
+        if (s->p) { cudaStreamSynchronize(st); cudaFree(s->p); s->p = nullptr; s->bytes = 0; }
         size_t want = bytes + bytes / 8;
-        if (cudaMalloc(&s.p, want) != cudaSuccess) {
+        if (cudaMalloc(&s->p, want) != cudaSuccess) {
             cudaGetLastError();
-            if (cudaMalloc(&s.p, bytes) != cudaSuccess) { cudaGetLastError(); s.p = nullptr; return nullptr; }
+            if (cudaMalloc(&s->p, bytes) != cudaSuccess) { cudaGetLastError(); s->p = nullptr; return nullptr; }
             want = bytes;
         }
-        s.bytes = want;
+        s->bytes = want;
     }
-    return s.p;
+    return s->p;
 }
+// Frees every cached buffer of every device (no call of the library may be in flight on another thread).
 void release_workspace() {
     std::lock_guard<std::mutex> lk(g_ws_mu);
     int cur = 0;
     cudaGetDevice(&cur);
-    for (int d = 0; d < 64; ++d)
-        for (int s = 0; s < 8; ++s)
-            if (g_ws[d][s].p) { cudaSetDevice(d); cudaDeviceSynchronize(); cudaFree(g_ws[d][s].p); g_ws[d][s] = WsSlot(); }
+    for (auto& kv : g_ws) {
+        bool any = false;
+        for (auto& sl : kv.second.s) any = any || sl.p;
+        if (!any) continue;
+        cudaSetDevice(kv.first.dev);
+        cudaDeviceSynchronize();
+        for (auto& sl : kv.second.s) if (sl.p) { cudaFree(sl.p); sl = WsSlot(); }
+    }
+    g_ws.clear();
     cudaSetDevice(cur);
+    cudaGetLastError();
+}
+
+// Copy stream + events of the host-destination fill_dense pipeline, cached per (device, host thread).
+struct CopyPipe { cudaStream_t st = nullptr; cudaEvent_t gen_done[2] = {nullptr, nullptr}, copy_done[2] = {nullptr, nullptr}; };
+static CopyPipe* copy_pipe() {
+    static std::mutex mu;
+    static std::map<std::pair<int, std::thread::id>, CopyPipe> pipes;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    std::lock_guard<std::mutex> lk(mu);
+    CopyPipe& c = pipes[{dev, std::this_thread::get_id()}];
+    if (!c.st) {
+        if (cudaStreamCreateWithFlags(&c.st, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); c.st = nullptr; return nullptr; }
+        for (int i = 0; i < 2; ++i) {
+            cudaEventCreateWithFlags(&c.gen_done[i], cudaEventDisableTiming);
+            cudaEventCreateWithFlags(&c.copy_done[i], cudaEventDisableTiming);
+        }
+    }
+    return &c;
 }
 
 // ---- host/device pointer handling ----
@@ -220,16 +268,14 @@ static int fill_dense_impl(char layout, int64_t D_rows, int64_t D_cols, char fam
     if (chunk < 1) chunk = 1;
     if (chunk > outer) chunk = outer;
     T* stage[2];
-    stage[0] = (T*) workspace(0, (size_t) chunk * slice_bytes);
-    stage[1] = (outer > chunk) ? (T*) workspace(1, (size_t) chunk * slice_bytes) : stage[0];
+    stage[0] = (T*) workspace(0, (size_t) chunk * slice_bytes, st);
+    stage[1] = (outer > chunk) ? (T*) workspace(1, (size_t) chunk * slice_bytes, st) : stage[0];
     if (!stage[0] || !stage[1]) return fail_cuda(cudaErrorMemoryAllocation, "fill_dense staging");
-    cudaStream_t copy_st;
-    RB_CUDA(cudaStreamCreateWithFlags(&copy_st, cudaStreamNonBlocking));
-    cudaEvent_t gen_done[2], copy_done[2];
-    for (int i = 0; i < 2; ++i) {
-        cudaEventCreateWithFlags(&gen_done[i], cudaEventDisableTiming);
-        cudaEventCreateWithFlags(&copy_done[i], cudaEventDisableTiming);
-    }
+    CopyPipe* pipe = copy_pipe();
+    if (!pipe) return fail_cuda(cudaErrorUnknown, "fill_dense copy stream");
+    cudaStream_t copy_st = pipe->st;
+    cudaEvent_t* gen_done = pipe->gen_done;
+    cudaEvent_t* copy_done = pipe->copy_done;
     int rc = 0, it = 0;
     const bool outer_is_v = (layout == 'R') == nat_row;   // does a slice of the destination hold one vector?
     for (int64_t o = 0; o < outer && rc == 0; o += chunk, ++it) {
@@ -248,8 +294,6 @@ static int fill_dense_impl(char layout, int64_t D_rows, int64_t D_cols, char fam
     }
     cudaStreamSynchronize(copy_st);
     cudaStreamSynchronize(st);
-    for (int i = 0; i < 2; ++i) { cudaEventDestroy(gen_done[i]); cudaEventDestroy(copy_done[i]); }
-    cudaStreamDestroy(copy_st);
     return rc;
 }
 
@@ -307,38 +351,86 @@ static int skge3_impl(bool left, char layout, char opS, char opA, int64_t d, int
     Staged sA, sB, sS;
     const int64_t A_outer = (layout == 'C') ? cols_A : rows_A, A_inner = (layout == 'C') ? rows_A : cols_A;
     const int64_t B_outer = (layout == 'C') ? cols_B : rows_B, B_inner = (layout == 'C') ? rows_B : cols_B;
-    int rc = sA.open(A, sizeof(T), A_outer, A_inner, lda, true, false, st);
-    if (rc) return rc;
+    const int64_t Ktot = left ? m : n;                       // contraction length
+    // Host-resident A with a generated operator: stream A through two staging buffers in blocks along the
+    // contraction dimension (the reference's own blocked form, skge.hh:174-181: block k0 uses the operator window
+    // shifted by k0 and accumulates with beta = 1), so the host->device copy of block i+1 overlaps the kernel of block i.
+    const bool chunked = A != nullptr && S_buff == nullptr && !on_device(A) && Ktot > 0 &&
+                         (size_t) rows_A * (size_t) cols_A * sizeof(T) >= (g_h2d_chunk_mb.load() << 20) * 2ull;
+    int rc = 0;
+    if (!chunked) { rc = sA.open(A, sizeof(T), A_outer, A_inner, lda, true, false, st); if (rc) return rc; }
     rc = sB.open(B, sizeof(T), B_outer, B_inner, ldb, beta != (T) 0, true, st);
     if (rc) return rc;
     rc = sS.open(S_buff, sizeof(T), D.dim_minor, D.dim_major, D.dim_major, true, false, st);
     if (rc) return rc;
 
-    DenseProblem<T> p;
-    p.alpha = alpha; p.beta = beta;
-    p.gen = make_dense_gen(D, ctr, key);
-    p.family = family;
-    p.S_buff = (const T*) sS.dev;
-    p.S_ld = D.dim_major;
-    const int64_t ars = (layout == 'C') ? 1 : lda, acs = (layout == 'C') ? lda : 1;
+    const DenseGen gen = make_dense_gen(D, ctr, key);
     const int64_t brs = (layout == 'C') ? 1 : ldb, bcs = (layout == 'C') ? ldb : 1;
-    p.Y = (const T*) sA.dev;
-    p.C = (T*) sB.dev;
-    OpWindow w;
-    if (left) {
-        p.P = d; p.Q = n; p.K = m;
-        w = op_window(p.gen.nat_row, opS, ro_s, co_s);
-        p.yrs = (opA == 'N') ? ars : acs; p.ycs = (opA == 'N') ? acs : ars;
-        p.crs = brs; p.ccs = bcs;
+    // canonical problem for the contraction block [k0, k0 + kc) with A (or its staged block) at Adev / lda_dev
+    auto problem = [&](const T* Adev, int64_t lda_dev, int64_t k0, int64_t kc, T beta_blk) {
+        DenseProblem<T> p;
+        p.alpha = alpha; p.beta = beta_blk;
+        p.gen = gen;
+        p.family = family;
+        p.S_buff = (const T*) sS.dev;
+        p.S_ld = D.dim_major;
+        const int64_t ars = (layout == 'C') ? 1 : lda_dev, acs = (layout == 'C') ? lda_dev : 1;
+        p.Y = Adev;
+        p.C = (T*) sB.dev;
+        OpWindow w;
+        if (left) {
+            p.P = d; p.Q = n; p.K = kc;
+            w = op_window(p.gen.nat_row, opS, ro_s, co_s);
+            p.yrs = (opA == 'N') ? ars : acs; p.ycs = (opA == 'N') ? acs : ars;
+            p.crs = brs; p.ccs = bcs;
+        } else {
+            // transpose the problem: B^T (d x m) = op(S)^T (d x n) * op(A)^T (n x m)
+            p.P = d; p.Q = m; p.K = kc;
+            w = op_window(p.gen.nat_row, opS == 'N' ? 'T' : 'N', ro_s, co_s);
+            p.yrs = (opA == 'N') ? acs : ars; p.ycs = (opA == 'N') ? ars : acs;
+            p.crs = bcs; p.ccs = brs;
+        }
+        p.v0 = w.v0 + k0 * w.vk; p.u0 = w.u0 + k0 * w.uk; p.vi = w.vi; p.ui = w.ui; p.vk = w.vk; p.uk = w.uk;
+        return p;
+    };
+
+    if (!chunked) {
+        DenseProblem<T> p = problem((const T*) sA.dev, lda, 0, Ktot, beta);
+        rc = run_dense<T>(p, st);
     } else {
-        // transpose the problem: B^T (d x m) = op(S)^T (d x n) * op(A)^T (n x m)
-        p.P = d; p.Q = m; p.K = n;
-        w = op_window(p.gen.nat_row, opS == 'N' ? 'T' : 'N', ro_s, co_s);
-        p.yrs = (opA == 'N') ? acs : ars; p.ycs = (opA == 'N') ? ars : acs;
-        p.crs = bcs; p.ccs = brs;
+        const bool k_on_rows = left ? (opA == 'N') : (opA == 'T');          // contraction index runs over rows of A?
+        const bool k_inner = (layout == 'C') == k_on_rows;                  // ... and is it the contiguous index?
+        const int64_t other = k_inner ? A_outer : A_inner;                  // extent of the non-contracted index
+        const size_t target = (size_t) g_h2d_chunk_mb.load() << 20;
+        int64_t kc_max = (int64_t) (target / ((size_t) other * sizeof(T)));
+        kc_max = (kc_max / 1024) * 1024;
+        if (kc_max < 1024) kc_max = 1024;
+        if (kc_max > Ktot) kc_max = Ktot;
+        const int64_t pad = 16 / (int64_t) sizeof(T);
+        const int64_t ld_stage = k_inner ? ((kc_max + pad - 1) / pad) * pad : ((A_inner + pad - 1) / pad) * pad;
+        const size_t stage_bytes = (size_t) ld_stage * (size_t) (k_inner ? A_outer : kc_max) * sizeof(T);
+        T* stage[2] = {(T*) workspace(8, stage_bytes, st), (T*) workspace(9, stage_bytes, st)};
+        CopyPipe* pipe = copy_pipe();
+        if (!stage[0] || !stage[1] || !pipe) rc = fail_cuda(cudaErrorMemoryAllocation, "sketch staging");
+        int it = 0;
+        for (int64_t k0 = 0; k0 < Ktot && rc == 0; k0 += kc_max, ++it) {
+            const int b = it & 1;
+            const int64_t kc = (Ktot - k0 < kc_max) ? Ktot - k0 : kc_max;
+            if (it >= 2) cudaStreamWaitEvent(pipe->st, pipe->gen_done[b], 0);      // kernel it-2 has released the buffer
+            cudaError_t e;
+            if (k_inner) e = cudaMemcpy2DAsync(stage[b], (size_t) ld_stage * sizeof(T), A + k0, (size_t) lda * sizeof(T),
+                                               (size_t) kc * sizeof(T), (size_t) A_outer, cudaMemcpyHostToDevice, pipe->st);
+            else e = cudaMemcpy2DAsync(stage[b], (size_t) ld_stage * sizeof(T), A + k0 * lda, (size_t) lda * sizeof(T),
+                                       (size_t) A_inner * sizeof(T), (size_t) kc, cudaMemcpyHostToDevice, pipe->st);
+            if (e != cudaSuccess) { rc = fail_cuda(e, "sketch H2D"); break; }
+            cudaEventRecord(pipe->copy_done[b], pipe->st);
+            cudaStreamWaitEvent(st, pipe->copy_done[b], 0);
+            DenseProblem<T> p = problem(stage[b], ld_stage, k0, kc, it == 0 ? beta : (T) 1);
+            rc = run_dense<T>(p, st);
+            cudaEventRecord(pipe->gen_done[b], st);
+        }
+        if (pipe) cudaStreamSynchronize(pipe->st);
     }
-    p.v0 = w.v0; p.u0 = w.u0; p.vi = w.vi; p.ui = w.ui; p.vk = w.vk; p.uk = w.uk;
-    rc = run_dense<T>(p, st);
     int rc2 = sS.close(); if (!rc) rc = rc2;
     rc2 = sA.close(); if (!rc) rc = rc2;
     rc2 = sB.close(); if (!rc) rc = rc2;
@@ -462,9 +554,9 @@ static int skges_impl(bool left, char layout, char opS, char opA, int64_t d, int
     rc = launch_saso_apply<T>(p, st);
     if (rc == -1) {
         // vec_nnz > 32: sample the operator into workspace COO arrays (int64) and use the COO kernel
-        int64_t* maj = (int64_t*) workspace(3, (size_t) D.full_nnz * 8);
-        int64_t* mnr = (int64_t*) workspace(4, (size_t) D.full_nnz * 8);
-        T* vv = (T*) workspace(5, (size_t) D.full_nnz * sizeof(T));
+        int64_t* maj = (int64_t*) workspace(3, (size_t) D.full_nnz * 8, st);
+        int64_t* mnr = (int64_t*) workspace(4, (size_t) D.full_nnz * 8, st);
+        T* vv = (T*) workspace(5, (size_t) D.full_nnz * sizeof(T), st);
         if (!maj || !mnr || !vv) rc = fail_cuda(cudaErrorMemoryAllocation, "SASO workspace");
         else rc = launch_saso(p.ctr, p.key, vec_nnz, D.dim_major, D.dim_minor, maj, mnr, 8, vv, (int) sizeof(T), st);
         if (!rc) {
@@ -542,7 +634,7 @@ static int require_symmetric_impl(char layout, const T* A, int64_t n, int64_t ld
     RB_REQUIRE(A != nullptr);
     Staged sA;
     int rc = sA.open(A, sizeof(T), n, n, lda, true, false, st); if (rc) return rc;
-    unsigned long long* first = (unsigned long long*) workspace(2, 8);
+    unsigned long long* first = (unsigned long long*) workspace(2, 8, st);
     if (!first) return fail_cuda(cudaErrorMemoryAllocation, "symmetry check workspace");
     const int64_t rs = (layout == 'C') ? 1 : lda, cs = (layout == 'C') ? lda : 1;
     rc = launch_symmetry_check<T>((const T*) sA.dev, n, rs, cs, tol, first, st);
@@ -594,7 +686,7 @@ static int spmm_impl(int left, int fmt, char layout, char opA, char opB, int64_t
     RB_REQUIRE(ptr != nullptr || n_major == 0);
     Staged sp;
     int rc = sp.open(ptr, (size_t) idx_bytes, 1, n_major + 1, n_major + 1, true, false, st); if (rc) return rc;
-    void* expanded = workspace(3, (size_t) (nnz > 0 ? nnz : 1) * (size_t) idx_bytes);
+    void* expanded = workspace(3, (size_t) (nnz > 0 ? nnz : 1) * (size_t) idx_bytes, st);
     if (!expanded) return fail_cuda(cudaErrorMemoryAllocation, "spmm index workspace");
     rc = launch_expand_ptr(n_major, sp.dev, expanded, idx_bytes, st);
     int rc2 = sp.close(); if (!rc) rc = rc2;
@@ -1016,6 +1108,7 @@ int rb_set_option(const char* name, int64_t value) {
     if (!std::strcmp(name, "tc_cluster")) { g_tc_cluster = value; return 0; }
     if (!std::strcmp(name, "tc_halves")) { g_tc_halves = value; return 0; }
     if (!std::strcmp(name, "saso_path")) { g_saso_path = value; return 0; }
+    if (!std::strcmp(name, "h2d_chunk_mb")) { RB_REQUIRE(value >= 1 && value <= 4096); g_h2d_chunk_mb = value; return 0; }
     if (!std::strcmp(name, "spdata_path")) { g_spdata_path = value; return 0; }
     return fail(std::string("unknown option ") + name);
 }

@@ -1,5 +1,6 @@
 // Shared host/device helpers for the C-ABI translation units.
 #pragma once
+#include <atomic>
 #include <cstdint>
 #include <cstdio>
 #include <string>
@@ -68,6 +69,15 @@ inline void store_ctr(Ctr128 c, uint32_t* out) {
 }
 
 int sm_count();   // SMs of the current device (cached)
+
+// One-time initialisation flag PER DEVICE (function attributes such as the dynamic shared-memory opt-in belong to a
+// device's context, not to the process): need() is true until done() was called on the current device.
+struct DevOnce {
+    std::atomic<uint64_t> mask{0};
+    static int dev() { int d = 0; if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= 64) { cudaGetLastError(); return -1; } return d; }
+    bool need() const { const int d = dev(); return d < 0 || !(mask.load(std::memory_order_acquire) & (1ull << d)); }
+    void done() { const int d = dev(); if (d >= 0) mask.fetch_or(1ull << d, std::memory_order_release); }
+};
 // device copy of the folded logf table (philox.cuh), built once per device; nullptr on failure
 const double2* logf_table_device();
 

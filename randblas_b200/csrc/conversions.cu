@@ -33,10 +33,11 @@ __global__ void __launch_bounds__(256) coo_gather_kernel(int64_t nnz, const unsi
                                                          const unsigned int* __restrict__ pos, int64_t n_minor,
                                                          const VAL* __restrict__ vals, VAL* __restrict__ ovals,
                                                          IDX* __restrict__ ominor, IDX* __restrict__ omajor,
-                                                         unsigned long long* __restrict__ counts) {
+                                                         unsigned long long* __restrict__ counts, unsigned long long n_major) {
     for (int64_t e = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; e < nnz; e += (int64_t) gridDim.x * blockDim.x) {
         const unsigned long long k = keys[e];
-        const unsigned long long mj = k / (unsigned long long) n_minor;
+        unsigned long long mj = k / (unsigned long long) n_minor;
+        if (mj >= n_major) mj = n_major - 1;      // out-of-range input index (invalid matrix): never write outside counts[]
         ominor[e] = (IDX) (k - mj * (unsigned long long) n_minor);
         if (omajor) omajor[e] = (IDX) mj;
         ovals[e] = vals[pos[e]];
@@ -57,9 +58,13 @@ int coo_to_compressed_t(int64_t n_major, int64_t n_minor, int64_t nnz, const voi
     int64_t grid = (nnz + 255) / 256;
     if (grid > cap) grid = cap;
     if (grid < 1) grid = 1;
-    unsigned long long* keys = (unsigned long long*) workspace(0, (size_t) (nnz + 1) * 8 * 2);
-    unsigned int* pos = (unsigned int*) workspace(1, (size_t) (nnz + 1) * 4 * 2);
-    unsigned long long* counts = (unsigned long long*) workspace(2, (size_t) (n_major + 2) * 8 * 2);
+    // the sort key is major * n_minor + minor in 64 bits
+    unsigned long long prod = 0;
+    if (__builtin_mul_overflow((unsigned long long) (n_major > 0 ? n_major : 1), (unsigned long long) (n_minor > 0 ? n_minor : 1), &prod))
+        return fail("coo_to_compressed: n_rows * n_cols must be below 2^64");
+    unsigned long long* keys = (unsigned long long*) workspace(0, (size_t) (nnz + 1) * 8 * 2, st);
+    unsigned int* pos = (unsigned int*) workspace(1, (size_t) (nnz + 1) * 4 * 2, st);
+    unsigned long long* counts = (unsigned long long*) workspace(2, (size_t) (n_major + 2) * 8 * 2, st);
     if (!keys || !pos || !counts) return fail_cuda(cudaErrorMemoryAllocation, "conversion workspace");
     unsigned long long* keys2 = keys + nnz + 1;
     unsigned int* pos2 = pos + nnz + 1;
@@ -75,17 +80,18 @@ int coo_to_compressed_t(int64_t n_major, int64_t n_minor, int64_t nnz, const voi
         }
         size_t tmp_bytes = 0;
         cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys, keys2, pos, pos2, (int) nnz, 0, end_bit, st);
-        void* tmp = workspace(3, tmp_bytes);
+        void* tmp = workspace(3, tmp_bytes, st);
         if (!tmp) return fail_cuda(cudaErrorMemoryAllocation, "sort workspace");
         RB_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys, keys2, pos, pos2, (int) nnz, 0, end_bit, st));
         count_launch();
         coo_gather_kernel<IDX, VAL><<<(unsigned) grid, 256, 0, st>>>(nnz, keys2, pos2, n_minor, (const VAL*) vals, (VAL*) ovals,
-                                                                    (IDX*) ominor, (IDX*) omajor, counts);
+                                                                    (IDX*) ominor, (IDX*) omajor, counts,
+                                                                    (unsigned long long) n_major);
         count_launch();
     }
     size_t tmp_bytes = 0;
     cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, counts, scan, (int) (n_major + 1), st);
-    void* tmp = workspace(4, tmp_bytes);
+    void* tmp = workspace(4, tmp_bytes, st);
     if (!tmp) return fail_cuda(cudaErrorMemoryAllocation, "scan workspace");
     RB_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, counts, scan, (int) (n_major + 1), st));
     count_launch();

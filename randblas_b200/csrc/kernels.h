@@ -151,8 +151,9 @@ struct SpDataProblem {
 template <typename T>
 int launch_spdata(const SpDataProblem<T>& p, cudaStream_t st);
 
-// cached device workspace (grow-only), slot in [0, 8)
-void* workspace(int slot, size_t bytes);
+// cached device workspace (grow-only), slot in [0, RB_WS_SLOTS), owned by (current device, stream, calling thread)
+#define RB_WS_SLOTS 10
+void* workspace(int slot, size_t bytes, cudaStream_t st);
 void release_workspace();
 
 int64_t get_option(const char* name);

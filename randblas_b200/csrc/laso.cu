@@ -117,12 +117,12 @@ __global__ void laso_thread_kernel(Ctr128 ctr, PhiloxKey key, int64_t k, int64_t
 template <typename IDX, typename VAL>
 int launch_laso_t(Ctr128 ctr, PhiloxKey key, int64_t k, int64_t dim_major, int64_t dim_minor, void* lng, void* sht,
                   void* vals, int64_t* nnz_host, cudaStream_t st) {
-    int64_t* counts = (int64_t*) workspace(0, (size_t) (dim_minor + 1) * 8);
-    int64_t* offs = (int64_t*) workspace(1, (size_t) (dim_minor + 1) * 8);
+    int64_t* counts = (int64_t*) workspace(0, (size_t) (dim_minor + 1) * 8, st);
+    int64_t* offs = (int64_t*) workspace(1, (size_t) (dim_minor + 1) * 8, st);
     if (!counts || !offs) return fail_cuda(cudaErrorMemoryAllocation, "LASO count workspace");
     size_t tmp_bytes = 0;
     cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, counts, offs, (int) (dim_minor + 1), st);
-    void* tmp = workspace(2, tmp_bytes);
+    void* tmp = workspace(2, tmp_bytes, st);
     if (!tmp) return fail_cuda(cudaErrorMemoryAllocation, "scan workspace");
     RB_CUDA(cudaMemsetAsync(counts + dim_minor, 0, 8, st));     // so that offs[dim_minor] is the total
     const int64_t cap = (int64_t) sm_count() * 8;
@@ -140,7 +140,7 @@ int launch_laso_t(Ctr128 ctr, PhiloxKey key, int64_t k, int64_t dim_major, int64
     } else {
         int64_t grid = (dim_minor + 127) / 128;
         if (grid > cap) grid = cap;
-        int64_t* scratch = (int64_t*) workspace(7, (size_t) (grid * 128 * k) * 8);
+        int64_t* scratch = (int64_t*) workspace(7, (size_t) (grid * 128 * k) * 8, st);
         if (!scratch) return fail_cuda(cudaErrorMemoryAllocation, "LASO scratch");
         laso_thread_kernel<IDX, VAL, false><<<(unsigned) grid, 128, 0, st>>>(ctr, key, k, dim_major, dim_minor, counts,
                                                                            nullptr, nullptr, nullptr, nullptr, scratch);

@@ -162,7 +162,7 @@ int launch_weights_to_cdf(int64_t n, T* w, T error_if_below, cudaStream_t st) {
         // the loop is empty and sum = 0 < sqrt(n) * eps fails only for n > 0; n == 0: 0 >= 0 holds, scal of nothing
         return n == 0 ? 0 : fail("(n >= 0) was required, but did not hold, in function weights_to_cdf");
     }
-    char* ws = (char*) workspace(0, 64);
+    char* ws = (char*) workspace(0, 64, st);
     if (!ws) return fail_cuda(cudaErrorMemoryAllocation, "weights_to_cdf workspace");
     T* d_sum = (T*) ws;
     int64_t* d_bad = (int64_t*) (ws + 16);

@@ -334,13 +334,13 @@ __global__ void __launch_bounds__(BN_THREADS, 1) saso_binned_kernel(const __grid
 
 template <int G>
 int launch_bin(const BinArgs& a, size_t smem, cudaStream_t st) {
-    static bool attr_done = false;
-    if (!attr_done) {
+    static DevOnce attr_done;
+    if (attr_done.need()) {
         if (cudaFuncSetAttribute(saso_bin_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024) != cudaSuccess) {
             cudaGetLastError();
             return -1;
         }
-        attr_done = true;
+        attr_done.done();
     }
     int64_t grid = a.nchunks;
     const int64_t cap = (int64_t) sm_count() * 4;
@@ -369,13 +369,13 @@ int launch_saso_binned_f32(const SasoProblem<float>& p, cudaStream_t st) {
     tma::EncodeTiledFn enc = tma::encode_tiled_fn();
     if (!enc) return -1;
     {
-        static bool attr_done = false;
-        if (!attr_done) {
+        static DevOnce attr_done;
+        if (attr_done.need()) {
             if (cudaFuncSetAttribute(saso_binned_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BN_SMEM) != cudaSuccess) {
                 cudaGetLastError();
                 return -1;
             }
-            attr_done = true;
+            attr_done.done();
         }
     }
     const int k = (int) p.vec_nnz;
@@ -394,8 +394,8 @@ int launch_saso_binned_f32(const SasoProblem<float>& p, cudaStream_t st) {
     for (int64_t v0 = 0; v0 < nvec; v0 += seg_vecs) {
         const int64_t nv = (nvec - v0 < seg_vecs) ? nvec - v0 : seg_vecs;
         const int64_t nchunks = (nv + Kc - 1) / Kc;
-        uint32_t* sorted = (uint32_t*) workspace(7, (size_t) nchunks * BN_ENT_CAP * 4);
-        uint16_t* offs16 = (uint16_t*) workspace(6, (size_t) nchunks * Ppad * 2 + 64);
+        uint32_t* sorted = (uint32_t*) workspace(7, (size_t) nchunks * BN_ENT_CAP * 4, st);
+        uint16_t* offs16 = (uint16_t*) workspace(6, (size_t) nchunks * Ppad * 2 + 64, st);
         if (!sorted || !offs16) return fail_cuda(cudaErrorMemoryAllocation, "SASO binning workspace");
 
         BinArgs b;

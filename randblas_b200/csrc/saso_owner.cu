@@ -270,13 +270,13 @@ int launch_saso_owner_f32(const SasoProblem<float>& p, cudaStream_t st) {
     tma::EncodeTiledFn enc = tma::encode_tiled_fn();
     if (!enc) return -1;
     {
-        static bool attr_done = false;
-        if (!attr_done) {
+        static DevOnce attr_done;
+        if (attr_done.need()) {
             if (cudaFuncSetAttribute(saso_owner_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, OW_SMEM) != cudaSuccess) {
                 cudaGetLastError();
                 return -1;
             }
-            attr_done = true;
+            attr_done.done();
         }
     }
     const int k = (int) p.vec_nnz;
@@ -289,7 +289,7 @@ int launch_saso_owner_f32(const SasoProblem<float>& p, cudaStream_t st) {
     int64_t seg_vecs = ((int64_t) 1 << 28) / k / Kc * Kc;
     for (int64_t v0 = 0; v0 < nvec; v0 += seg_vecs) {
         const int64_t nv = (nvec - v0 < seg_vecs) ? nvec - v0 : seg_vecs;
-        uint32_t* entries = (uint32_t*) workspace(7, (size_t) nv * k * 4);
+        uint32_t* entries = (uint32_t*) workspace(7, (size_t) nv * k * 4, st);
         if (!entries) return fail_cuda(cudaErrorMemoryAllocation, "SASO entry workspace");
         if (k <= 1) launch_entries<1>(p, w0 + v0, nv, m0, entries, st);
         else if (k <= 2) launch_entries<2>(p, w0 + v0, nv, m0, entries, st);

@@ -182,6 +182,7 @@ int launch_dense_generic(const DenseProblem<T>& p, cudaStream_t st) {
     dim3 grid((unsigned) ((p.Q + TJ - 1) / TJ), (unsigned) ((p.P + TI - 1) / TI));
     if (grid.y > 65535u) return fail("dense_generic: more than 65535 row tiles is not supported");
     const bool gauss = p.family == 'G';
+    if (gauss && !p.S_buff && !p.gen.logtab) return fail_cuda(cudaErrorMemoryAllocation, "logf table of the Gaussian generator");
     if (p.S_buff) dense_generic_kernel<T, false, true><<<grid, NT, 0, st>>>(p);
     else if (gauss) dense_generic_kernel<T, true, false><<<grid, NT, 0, st>>>(p);
     else dense_generic_kernel<T, false, false><<<grid, NT, 0, st>>>(p);

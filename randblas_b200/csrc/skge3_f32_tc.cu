@@ -685,16 +685,16 @@ int launch_dense_tc_f32(const DenseProblem<float>& p, cudaStream_t st) {
     a.P_pad = tiles_p * BM; a.Q_pad = tiles_q * BN;
     a.W = nullptr;
     if (splits > 1) {
-        a.W = (float*) workspace(6, (size_t) splits * a.P_pad * a.Q_pad * sizeof(float));
+        a.W = (float*) workspace(6, (size_t) splits * a.P_pad * a.Q_pad * sizeof(float), st);
         if (!a.W) return fail_cuda(cudaErrorMemoryAllocation, "split-K workspace");
     }
-    static bool attr_done[7] = {};
+    static DevOnce attr_done[7];
     const bool gauss = p.family == 'G';
     // tc_halves: 1 (default) = the generator warps work on two K steps at a time where the kernel supports it
     const bool halves = !xmat && !cluster && !y_mn && get_option("tc_halves") != 0;
     const int variant = xmat ? 2 : (cluster ? 3 : (halves ? 5 : 0)) + (gauss ? 1 : 0);
     auto set_attr = [&](auto kern) { return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM); };
-    if (!attr_done[variant]) {
+    if (attr_done[variant].need()) {
         cudaError_t e;
         switch (variant) {
             case 0: e = set_attr(skge3_tc_kernel<false, false, 1, false>); break;
@@ -706,7 +706,7 @@ int launch_dense_tc_f32(const DenseProblem<float>& p, cudaStream_t st) {
             default: e = set_attr(skge3_tc_kernel<true, false, 1, true>); break;
         }
         if (e != cudaSuccess) { cudaGetLastError(); return -1; }
-        attr_done[variant] = true;
+        attr_done[variant].done();
     }
     dim3 grid((unsigned) tiles_q, (unsigned) tiles_p, (unsigned) splits);
     if (xmat) skge3_tc_kernel<false, true, 1, false><<<grid, TC_THREADS, TC_SMEM, st>>>(tm, tmx, a);

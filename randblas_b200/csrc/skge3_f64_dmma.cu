@@ -514,32 +514,32 @@ int launch_dense_dmma_f64(const DenseProblem<double>& p, cudaStream_t st) {
     a.x_al = (xmat && (reinterpret_cast<uintptr_t>(p.S_buff) & 15) == 0 && (p.S_ld & 1) == 0 && (p.u0 & 1) == 0) ? 1 : 0;
     a.W = nullptr;
     if (splits > 1) {
-        a.W = (double*) workspace(6, (size_t) splits * a.P_pad * a.Q_pad * sizeof(double));
+        a.W = (double*) workspace(6, (size_t) splits * a.P_pad * a.Q_pad * sizeof(double), st);
         if (!a.W) return fail_cuda(cudaErrorMemoryAllocation, "split-K workspace");
     }
     const size_t smem = wide ? TileWide::smem : TileSquare::smem;
     const bool gauss = p.family == 'G';
     dim3 grid((unsigned) tiles_q, (unsigned) tiles_p, (unsigned) splits);
-    auto launch = [&](auto kern, bool& attr_done) -> int {
-        if (!attr_done) {
+    auto launch = [&](auto kern, DevOnce& attr_done) -> int {
+        if (attr_done.need()) {
             if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem) != cudaSuccess) {
                 cudaGetLastError();
                 return -1;
             }
-            attr_done = true;
+            attr_done.done();
         }
         kern<<<grid, D_THREADS, smem, st>>>(a);
         return 0;
     };
-    static bool attr_done[20] = {};
+    static DevOnce attr_done[20];
     const bool ws = get_option("dmma_uniform_warps") == 0;    // default: warp-specialised kernel
-    auto launch_ws = [&](auto kern, bool& done) -> int {
-        if (!done) {
+    auto launch_ws = [&](auto kern, DevOnce& done) -> int {
+        if (done.need()) {
             if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem) != cudaSuccess) {
                 cudaGetLastError();
                 return -1;
             }
-            done = true;
+            done.done();
         }
         kern<<<grid, WS_THREADS, smem, st>>>(a);
         return 0;

@@ -174,7 +174,7 @@ int launch_saso_t(Ctr128 ctr, PhiloxKey key, int64_t k, int64_t dim_major, int64
         int64_t grid = (dim_minor + threads - 1) / threads;
         int64_t cap = (int64_t) sm_count() * 4;
         if (grid > cap) grid = cap;
-        int64_t* scratch = (int64_t*) workspace(7, (size_t) (grid * threads * k) * sizeof(int64_t));
+        int64_t* scratch = (int64_t*) workspace(7, (size_t) (grid * threads * k) * sizeof(int64_t), st);
         if (!scratch) return fail_cuda(cudaErrorMemoryAllocation, "workspace for Fisher-Yates pivots");
         saso_fill_thread_kernel<IDX, VAL><<<(unsigned) grid, (unsigned) threads, 0, st>>>(
             ctr, key, k, dim_major, dim_minor, (IDX*) maj, (IDX*) mnr, (VAL*) vals, scratch);

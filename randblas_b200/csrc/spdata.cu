@@ -275,11 +275,11 @@ template <typename T, typename IDX, bool BYK>
 int rebucket(const SpDataProblem<T>& p, cudaStream_t st, const int64_t** ptr_out, const IDX** oidx_out, const T** vals_out) {
     const int64_t nseg = (BYK ? p.K : p.Q) + 1;
     if (nseg > 2147483647LL) return fail("sketch_sparse: re-bucketing more than 2^31-2 segments is not supported");
-    unsigned long long* cnt = (unsigned long long*) workspace(0, (size_t) nseg * 8);
-    unsigned long long* ptr = (unsigned long long*) workspace(1, (size_t) nseg * 8);
-    unsigned long long* cur = (unsigned long long*) workspace(2, (size_t) nseg * 8);
-    IDX* bk = (IDX*) workspace(3, (size_t) (p.nnz > 0 ? p.nnz : 1) * sizeof(IDX));
-    T* bv = (T*) workspace(4, (size_t) (p.nnz > 0 ? p.nnz : 1) * sizeof(T));
+    unsigned long long* cnt = (unsigned long long*) workspace(0, (size_t) nseg * 8, st);
+    unsigned long long* ptr = (unsigned long long*) workspace(1, (size_t) nseg * 8, st);
+    unsigned long long* cur = (unsigned long long*) workspace(2, (size_t) nseg * 8, st);
+    IDX* bk = (IDX*) workspace(3, (size_t) (p.nnz > 0 ? p.nnz : 1) * sizeof(IDX), st);
+    T* bv = (T*) workspace(4, (size_t) (p.nnz > 0 ? p.nnz : 1) * sizeof(T), st);
     if (!cnt || !ptr || !cur || !bk || !bv) return fail_cuda(cudaErrorMemoryAllocation, "sketch_sparse bucket workspace");
     RB_CUDA(cudaMemsetAsync(cnt, 0, (size_t) nseg * 8, st));
     int64_t units = (p.fmt == 0) ? p.A_rows : (p.fmt == 1 ? p.A_cols : (p.nnz + 31) / 32);
@@ -291,7 +291,7 @@ int rebucket(const SpDataProblem<T>& p, cudaStream_t st, const int64_t** ptr_out
     count_launch();
     size_t tmp_bytes = 0;
     cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, cnt, ptr, (int) nseg, st);
-    void* tmp = workspace(5, tmp_bytes);
+    void* tmp = workspace(5, tmp_bytes, st);
     if (!tmp) return fail_cuda(cudaErrorMemoryAllocation, "scan workspace");
     RB_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, cnt, ptr, (int) nseg, st));
     count_launch();
@@ -396,6 +396,7 @@ int launch_spdata(const SpDataProblem<T>& p, cudaStream_t st) {
     if (p.P <= 0 || p.Q <= 0) return 0;
     if (p.K <= 0 || p.alpha == (T) 0 || p.nnz <= 0) return launch_scale<T>(p.P, p.Q, p.beta, p.C, p.crs, p.ccs, st);
     if (p.Q > 2147483647LL) return fail("sketch_sparse: more than 2^31-1 output columns is not supported");
+    if (p.family == 'G' && !p.gen.logtab) return fail_cuda(cudaErrorMemoryAllocation, "logf table of the Gaussian generator");
     if (get_option("spdata_path") == 1) {
         if (p.idx_bytes == 4) return launch_spdata_t<T, int32_t>(p, st);
         return launch_spdata_t<T, int64_t>(p, st);
