@@ -7,3 +7,4 @@
 #include "RandBLAS/sparse_data.hh"
 #include "RandBLAS/sketch.hh"
 #include "RandBLAS/util.hh"
+#include "RandBLAS/multi_gpu.hh"

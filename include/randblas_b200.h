@@ -234,6 +234,35 @@ int rb_rsksp3_f64(int fmt, char layout, char opA, char opS, int64_t m, int64_t d
                   char major_axis, const uint32_t ctr[4], const uint32_t key[2], int64_t ro_s, int64_t co_s,
                   double beta, double* B, int64_t ldb, void* stream);
 
+/* ---- random sparse matrices and column partition ----
+ * rb_random_coo_* replaces RandBLAS::sparse_data::random_coo<T, sint_t> (RandBLAS/sparse_data/random_matrix.hh:290-355):
+ * an m x n COO matrix in CSR sort order whose entries are stored independently with probability `density`
+ * (geometric skips over the row-major linearised index, PhiloxStream :64-121) with iid N(0,1) values. The
+ * reference's sequential stream is reproduced bit for bit in parallel: stored entries 2b and 2b+1 consume exactly the
+ * four words of Philox block ctr + b (skip, Box-Muller pair, skip). Two-call protocol: *nnz always receives the
+ * number of stored entries and next_ctr the reference's returned state; vals/rows/cols are written only for
+ * entries below `capacity` (call with capacity 0 to size the arrays). *ambiguous (may be NULL) counts skips whose
+ * log(1-u)/log(1-p) fell within 8 ulp of an integer, where the device's and the host's double-precision log could
+ * round differently: 0 (the overwhelmingly common case) certifies equality with the reference. density in [0, 1).
+ * Synchronises. The row-restarting random_csr / random_csc streams (:136-288) are sequential by construction; the
+ * host layers build CSR / CSC from this matrix with rb_sorted_idxs_to_ptr (same distribution, not the same stream). */
+int rb_random_coo_f32(int64_t m, int64_t n, double density, const uint32_t ctr[4], const uint32_t key[2], int64_t capacity,
+                      float* vals, void* rows, void* cols, int idx_bytes, int64_t* nnz, uint32_t next_ctr[4],
+                      int64_t* ambiguous, void* stream);
+int rb_random_coo_f64(int64_t m, int64_t n, double density, const uint32_t ctr[4], const uint32_t key[2], int64_t capacity,
+                      double* vals, void* rows, void* cols, int idx_bytes, int64_t* nnz, uint32_t next_ctr[4],
+                      int64_t* ambiguous, void* stream);
+/* sorted_idxs_to_compressed_ptr (RandBLAS/sparse_data/base.hh:279-301): ptr[i] = number of entries of the sorted
+ * index array idxs[nnz] that are < i, i in [0, n_major]. Device pointers. */
+int rb_sorted_idxs_to_ptr(int64_t n_major, int64_t nnz, const void* idxs, int idx_bytes, void* ptr, void* stream);
+/* Column block [c0, c1) of a CSR matrix as a new n_rows x (c1 - c0) CSR matrix (column indices shifted by -c0, order
+ * inside each row kept): the partition step in front of a column-sharded sketch_sparse. Device
+ * pointers. out_rowptr[n_rows + 1] and *nnz_out are always written; out_vals / out_colidxs only if capacity >= the
+ * block's entry count (call with capacity 0 to size them). Synchronises. */
+int rb_csr_column_block(int64_t n_rows, int64_t n_cols, int64_t nnz, const void* vals, int val_bytes, const void* rowptr,
+                        const void* colidxs, int idx_bytes, int64_t c0, int64_t c1, int64_t capacity, void* out_vals,
+                        void* out_rowptr, void* out_colidxs, int64_t* nnz_out, void* stream);
+
 /* ---- multi-GPU: the m-sharded left sketch and its one exchange step ----
  * Distributes the reference's own blocked form of a left sketch (RandBLAS/skge.hh:174-181; rtd/source/tutorial/
  * sketch_updates.rst:198-213: row blocks of A against column blocks of S selected with (ro_s, co_s), block products

@@ -10,6 +10,7 @@
 // validation, exceptions.hh:57-95), 2 for any other exception; message via rbref_last_error().
 
 #include <RandBLAS.hh>
+#include <RandBLAS/sparse_data/random_matrix.hh>
 #include <omp.h>
 #include <cstdint>
 #include <cstring>
@@ -353,3 +354,121 @@ int rbref_repeated_fisher_yates_i64(int64_t k, int64_t n, int64_t r, int64_t* sa
 }
 
 } // extern "C"
+
+// public left_spmm / right_spmm on sparse DATA (sparse_data/spmm_dispatch.hh:52-219). fmt as in sksp_t. int64 indices.
+template <typename T>
+static int spmm_t(int side_left, int fmt, char layout, char op1, char op2, int64_t x, int64_t y, int64_t z, T alpha,
+                  int64_t Ar, int64_t Ac, int64_t nnz, T* vals, int64_t* idx0, int64_t* idx1, int64_t ro_a, int64_t co_a,
+                  const T* B, int64_t ldb, T beta, T* C, int64_t ldc) {
+    RBREF_TRY
+    using namespace RandBLAS::sparse_data;
+    auto run = [&](auto& Asp) {
+        if (side_left)   // (layout, opA, opB, d, n, m, alpha, A, ro_a, co_a, B, ldb, beta, C, ldc)
+            left_spmm((Layout) layout, (Op) op1, (Op) op2, x, y, z, alpha, Asp, ro_a, co_a, B, ldb, beta, C, ldc);
+        else             // (layout, opA(dense), opB(sparse), m, d, n, alpha, A, lda, B, i_off, j_off, beta, C, ldc)
+            right_spmm((Layout) layout, (Op) op1, (Op) op2, x, y, z, alpha, B, ldb, Asp, ro_a, co_a, beta, C, ldc);
+    };
+    if (fmt == 0) { CSRMatrix<T, int64_t> Asp(Ar, Ac, nnz, vals, idx0, idx1); run(Asp); }
+    else if (fmt == 1) { CSCMatrix<T, int64_t> Asp(Ar, Ac, nnz, vals, idx0, idx1); run(Asp); }
+    else { COOMatrix<T, int64_t> Asp(Ar, Ac, nnz, vals, idx0, idx1); run(Asp); }
+    RBREF_CATCH
+}
+
+// coo_to_csr / coo_to_csc (sparse_data/conversions.hh:79-121). Outputs: ovals[nnz], oidx[nnz], optr[n_major + 1].
+template <typename T>
+static int coo_to_compressed_t(int to_csc, int64_t Ar, int64_t Ac, int64_t nnz, T* vals, int64_t* rows, int64_t* cols,
+                               T* ovals, int64_t* oidx, int64_t* optr) {
+    RBREF_TRY
+    using namespace RandBLAS::sparse_data;
+    COOMatrix<T, int64_t> coo(Ar, Ac, nnz, vals, rows, cols);
+    const int64_t n_major = to_csc ? Ac : Ar;
+    for (int64_t i = 0; i <= n_major; ++i) optr[i] = 0;
+    if (to_csc) {
+        CSCMatrix<T, int64_t> out(Ar, Ac);
+        coo_to_csc(coo, out);
+        if (out.nnz > 0) {
+            std::copy(out.vals, out.vals + out.nnz, ovals);
+            std::copy(out.rowidxs, out.rowidxs + out.nnz, oidx);
+            std::copy(out.colptr, out.colptr + Ac + 1, optr);
+        }
+    } else {
+        CSRMatrix<T, int64_t> out(Ar, Ac);
+        coo_to_csr(coo, out);
+        if (out.nnz > 0) {
+            std::copy(out.vals, out.vals + out.nnz, ovals);
+            std::copy(out.colidxs, out.colidxs + out.nnz, oidx);
+            std::copy(out.rowptr, out.rowptr + Ar + 1, optr);
+        }
+    }
+    RBREF_CATCH
+}
+
+// csr_to_coo / csc_to_coo (conversions.hh:49-75): only the expanded index array is new
+template <typename T>
+static int compressed_to_coo_t(int from_csc, int64_t Ar, int64_t Ac, int64_t nnz, T* vals, int64_t* idx, int64_t* ptr,
+                               int64_t* expanded) {
+    RBREF_TRY
+    using namespace RandBLAS::sparse_data;
+    COOMatrix<T, int64_t> coo(Ar, Ac);
+    if (from_csc) { CSCMatrix<T, int64_t> in(Ar, Ac, nnz, vals, idx, ptr); csc_to_coo(in, coo); std::copy(coo.cols, coo.cols + nnz, expanded); }
+    else { CSRMatrix<T, int64_t> in(Ar, Ac, nnz, vals, ptr, idx); csr_to_coo(in, coo); std::copy(coo.rows, coo.rows + nnz, expanded); }
+    RBREF_CATCH
+}
+
+// random_csr / random_csc / random_coo (sparse_data/random_matrix.hh:136-355). which: 0 CSR, 1 CSC, 2 COO.
+// Two-call protocol: capacity < nnz => only *nnz_out and next_ctr are written.
+// Outputs follow the C-ABI's (vals, idx0, idx1) convention of sksp_t.
+template <typename T>
+static int random_sparse_t(int which, int64_t m, int64_t n, double density, const uint32_t* ctr, const uint32_t* key,
+                           int64_t capacity, T* vals, int64_t* idx0, int64_t* idx1, int64_t* nnz_out, uint32_t* next_ctr) {
+    RBREF_TRY
+    using namespace RandBLAS::sparse_data;
+    auto st = mk_state(ctr, key);
+    if (which == 0) {
+        auto [A, nx] = random_csr<T, int64_t>(m, n, density, st);
+        put_ctr(nx, next_ctr); *nnz_out = A.nnz;
+        if (capacity >= A.nnz) {
+            if (A.rowptr) std::copy(A.rowptr, A.rowptr + m + 1, idx0); else for (int64_t i = 0; i <= m; ++i) idx0[i] = 0;
+            std::copy(A.vals, A.vals + A.nnz, vals); std::copy(A.colidxs, A.colidxs + A.nnz, idx1);
+        }
+    } else if (which == 1) {
+        auto [A, nx] = random_csc<T, int64_t>(m, n, density, st);
+        put_ctr(nx, next_ctr); *nnz_out = A.nnz;
+        if (capacity >= A.nnz) {
+            if (A.colptr) std::copy(A.colptr, A.colptr + n + 1, idx1); else for (int64_t i = 0; i <= n; ++i) idx1[i] = 0;
+            std::copy(A.vals, A.vals + A.nnz, vals); std::copy(A.rowidxs, A.rowidxs + A.nnz, idx0);
+        }
+    } else {
+        auto [A, nx] = random_coo<T, int64_t>(m, n, density, st);
+        put_ctr(nx, next_ctr); *nnz_out = A.nnz;
+        if (capacity >= A.nnz) {
+            std::copy(A.vals, A.vals + A.nnz, vals); std::copy(A.rows, A.rows + A.nnz, idx0); std::copy(A.cols, A.cols + A.nnz, idx1);
+        }
+    }
+    RBREF_CATCH
+}
+
+extern "C" {
+#define DEF_SP_FOR_T(T, sfx)                                                                                            \
+    int rbref_spmm_##sfx(int side_left, int fmt, char layout, char op1, char op2, int64_t x, int64_t y, int64_t z,      \
+                         T alpha, int64_t Ar, int64_t Ac, int64_t nnz, T* vals, int64_t* idx0, int64_t* idx1,           \
+                         int64_t ro_a, int64_t co_a, const T* B, int64_t ldb, T beta, T* C, int64_t ldc) {              \
+        return spmm_t<T>(side_left, fmt, layout, op1, op2, x, y, z, alpha, Ar, Ac, nnz, vals, idx0, idx1, ro_a, co_a,   \
+                         B, ldb, beta, C, ldc);                                                                         \
+    }                                                                                                                   \
+    int rbref_coo_to_compressed_##sfx(int to_csc, int64_t Ar, int64_t Ac, int64_t nnz, T* vals, int64_t* rows,          \
+                                      int64_t* cols, T* ovals, int64_t* oidx, int64_t* optr) {                          \
+        return coo_to_compressed_t<T>(to_csc, Ar, Ac, nnz, vals, rows, cols, ovals, oidx, optr);                        \
+    }                                                                                                                   \
+    int rbref_compressed_to_coo_##sfx(int from_csc, int64_t Ar, int64_t Ac, int64_t nnz, T* vals, int64_t* idx,         \
+                                      int64_t* ptr, int64_t* expanded) {                                                \
+        return compressed_to_coo_t<T>(from_csc, Ar, Ac, nnz, vals, idx, ptr, expanded);                                 \
+    }                                                                                                                   \
+    int rbref_random_sparse_##sfx(int which, int64_t m, int64_t n, double density, const uint32_t* ctr,                 \
+                                  const uint32_t* key, int64_t capacity, T* vals, int64_t* idx0, int64_t* idx1,         \
+                                  int64_t* nnz_out, uint32_t* next_ctr) {                                               \
+        return random_sparse_t<T>(which, m, n, density, ctr, key, capacity, vals, idx0, idx1, nnz_out, next_ctr);       \
+    }
+DEF_SP_FOR_T(float, f32)
+DEF_SP_FOR_T(double, f64)
+}  // extern "C"

@@ -8,5 +8,7 @@ from .api import (Axis, COOMatrix, CSCMatrix, CSRMatrix, DenseDist, DenseSkOp, L
                   SparseDist, SparseSkOp, fill_dense, fill_dense_unpacked, fill_sparse, fill_sparse_unpacked_nosub,
                   philox_words, boxmuller_words, repeated_fisher_yates, sketch_general, sketch_sparse, sketch_vector,
                   left_spmm, right_spmm, coo_to_csr, coo_to_csc, csr_to_coo, csc_to_coo,
-                  sketch_symmetric, sample_indices_iid, sample_indices_iid_uniform, weights_to_cdf)
+                  sketch_symmetric, sample_indices_iid, sample_indices_iid_uniform, weights_to_cdf,
+                  random_coo, random_csr, random_csc, sorted_idxs_to_compressed_ptr, csr_column_block,
+                  csc_column_block)
 from ._lib import RandBLASError, counter, get_option, set_option  # noqa

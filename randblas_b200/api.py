@@ -569,3 +569,83 @@ def sketch_sparse(layout, op1, op2, x, y, z, alpha, *rest):
              opS, m, d, n, alpha, A.n_rows, A.n_cols, A.nnz, _ptr(A.vals), _ptr(A._idx0), _ptr(A._idx1), ib, 0, 0,
              D.n_rows, D.n_cols, D.family, D.major_axis, _addr(seed._c()), _addr(seed._k()), int(ro_s), int(co_s),
              beta, _ptr(B), int(ldb), st)
+
+
+# ------------------------------------------------------------------------------------------------
+# random sparse matrices (RandBLAS/sparse_data/random_matrix.hh) and the column partition of CSR / CSC data
+def _torch_dt(np_dt):
+    return {np.float32: torch.float32, np.float64: torch.float64, np.int32: torch.int32, np.int64: torch.int64}[np.dtype(np_dt).type]
+
+
+def random_coo(m, n, density, state, dtype=np.float32, index_dtype=np.int64, device="cuda"):
+    """RandBLAS::sparse_data::random_coo<T, sint_t>(m, n, density, state) (random_matrix.hh:290-355).
+    Returns (COOMatrix on the device, next_state); the matrix equals the reference's bit for bit (rb_random_coo_*).
+    `.ambiguous` on the result counts skips whose rounding could not be certified (0 in practice)."""
+    _require(torch is not None, "torch available to allocate the COO arrays")
+    sfx, _ = _sfx(dtype)
+    ib = np.dtype(index_dtype).itemsize
+    nnz, amb, nxt = ctypes.c_int64(0), ctypes.c_int64(0), (ctypes.c_uint32 * 4)()
+    st = torch.cuda.current_stream().cuda_stream
+    call(f"rb_random_coo_{sfx}", "qqdppqpppipppp", int(m), int(n), float(density), _addr(state._c()), _addr(state._k()), 0, 0,
+         0, 0, ib, _addr(nnz), _addr(nxt), _addr(amb), st)
+    k = int(nnz.value)
+    vals = torch.empty(k, dtype=_torch_dt(dtype), device=device)
+    rows = torch.empty(k, dtype=_torch_dt(index_dtype), device=device)
+    cols = torch.empty(k, dtype=_torch_dt(index_dtype), device=device)
+    if k > 0:
+        call(f"rb_random_coo_{sfx}", "qqdppqpppipppp", int(m), int(n), float(density), _addr(state._c()), _addr(state._k()),
+             k, _ptr(vals), _ptr(rows), _ptr(cols), ib, _addr(nnz), _addr(nxt), _addr(amb), st)
+    A = COOMatrix(m, n, k, vals, rows, cols)
+    A.sort = "CSR"
+    A.ambiguous = int(amb.value)
+    return A, RNGState(counter=list(nxt), key=state.key)
+
+
+def sorted_idxs_to_compressed_ptr(n_major, idxs):
+    """RandBLAS/sparse_data/base.hh:279-301 on the device."""
+    ptr = _like(idxs, n_major + 1)
+    nnz = int(idxs.numel()) if hasattr(idxs, "numel") else int(idxs.size)
+    call("rb_sorted_idxs_to_ptr", "qqpipp", int(n_major), nnz, _ptr(idxs), np.dtype(_dtype_of(idxs)).itemsize, _ptr(ptr),
+         _stream(idxs))
+    return ptr
+
+
+def random_csr(m, n, density, state, dtype=np.float32, index_dtype=np.int64):
+    """An m x n CSR matrix with iid Bernoulli(density) pattern and N(0,1) values: the CSR form of random_coo's matrix.
+    Same distribution as the reference's random_csr (random_matrix.hh:136-209) but not the same stream -- that one
+    restarts its column walk per row, which is sequential by construction. Returns (CSRMatrix, next_state)."""
+    coo, nxt = random_coo(m, n, density, state, dtype, index_dtype)
+    A = CSRMatrix(m, n, coo.nnz, coo.vals, sorted_idxs_to_compressed_ptr(m, coo.rows), coo.cols)
+    A.ambiguous = coo.ambiguous
+    return A, nxt
+
+
+def random_csc(m, n, density, state, dtype=np.float32, index_dtype=np.int64):
+    """CSC counterpart of random_csr (random_matrix.hh:218-288): the transpose of random_coo(n, m, ...) read column-wise."""
+    coo, nxt = random_coo(n, m, density, state, dtype, index_dtype)
+    A = CSCMatrix(m, n, coo.nnz, coo.vals, coo.cols, sorted_idxs_to_compressed_ptr(n, coo.rows))
+    A.ambiguous = coo.ambiguous
+    return A, nxt
+
+
+def csr_column_block(A, c0, c1):
+    """Columns [c0, c1) of a device CSR matrix as a new CSRMatrix (indices shifted by -c0): the partition step in
+    front of a column-sharded sketch_sparse (rb_csr_column_block)."""
+    _require(A.index_base == 0, "A.index_base == IndexBase::Zero")
+    vb, ib = np.dtype(_dtype_of(A.vals)).itemsize, np.dtype(_dtype_of(A.rowptr)).itemsize
+    nnz = ctypes.c_int64(0)
+    rowptr = _like(A.rowptr, A.n_rows + 1)
+    st = _stream(A.vals, A.rowptr, A.colidxs)
+    args = (A.n_rows, A.n_cols, A.nnz, _ptr(A.vals), vb, _ptr(A.rowptr), _ptr(A.colidxs), ib, int(c0), int(c1))
+    call("rb_csr_column_block", "qqqpippiqqqppppp", *args, 0, 0, _ptr(rowptr), 0, _addr(nnz), st)
+    k = int(nnz.value)
+    vals, cols = _like(A.vals, k), _like(A.colidxs, k)
+    if k > 0:
+        call("rb_csr_column_block", "qqqpippiqqqppppp", *args, k, _ptr(vals), _ptr(rowptr), _ptr(cols), _addr(nnz), st)
+    return CSRMatrix(A.n_rows, int(c1) - int(c0), k, vals, rowptr, cols)
+
+
+def csc_column_block(A, c0, c1):
+    """Columns [c0, c1) of a CSC matrix: views of vals / rowidxs plus a rebased colptr (no kernel needed)."""
+    lo, hi = int(A.colptr[c0]), int(A.colptr[c1])
+    return CSCMatrix(A.n_rows, int(c1) - int(c0), hi - lo, A.vals[lo:hi], A.rowidxs[lo:hi], A.colptr[c0:c1 + 1] - lo)

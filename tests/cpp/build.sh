@@ -4,5 +4,5 @@ set -e
 HERE="$(cd "$(dirname "$0")" && pwd)"
 ROOT="$(cd "$HERE/../.." && pwd)"
 LIBDIR="$ROOT/randblas_b200"
-g++ -std=c++17 -O2 -Wall -I "$ROOT/include" -o "$HERE/test_dropin" "$HERE/test_dropin.cc" \
-    -L "$LIBDIR" -lrandblas_b200 -Wl,-rpath,"$LIBDIR" -Wl,-rpath,/usr/local/cuda/lib64
+g++ -std=c++17 -O2 -Wall -I "$ROOT/include" -I /usr/local/cuda/include -o "$HERE/test_dropin" "$HERE/test_dropin.cc" \
+    -L "$LIBDIR" -lrandblas_b200 -L /usr/local/cuda/lib64 -lcudart -Wl,-rpath,"$LIBDIR" -Wl,-rpath,/usr/local/cuda/lib64

@@ -11,6 +11,7 @@
 #include <limits>
 #include <set>
 #include <vector>
+#include <cuda_runtime_api.h>   // device buffers of the multi-GPU check only
 #include "RandBLAS.hh"
 
 using namespace RandBLAS;
@@ -291,11 +292,67 @@ static void device_checks() {
                                             0, I.data(), m - 1, T(0), B.data(), m); }));
 }
 
+// --- multi-GPU left sketch through the drop-in header (include/RandBLAS/multi_gpu.hh): all GPUs of this process
+// (one is enough: a communicator set of one rank needs no NCCL), device buffers, against the single-call sketch.
+template <typename T>
+static void multi_gpu_checks() {
+    using namespace RandBLAS::multi_gpu;
+    int have = 0;
+    if (cudaGetDeviceCount(&have) != cudaSuccess || have < 1) { CHECK(false); return; }
+    const int nd = have >= 2 ? 2 : 1;
+    const T tol = sizeof(T) == 4 ? T(1e-5) : T(1e-12);
+    const int64_t d = 64, n = 24, m = 4003;
+    RNGState<> seed(1997);
+    DenseSkOp<T> S(DenseDist(d, m), seed);
+    std::vector<T> A(m * n);                                    // RowMajor m x n
+    for (int64_t i = 0; i < m * n; ++i) A[i] = T(((i * 2654435761u) % 2001) / 1000.0 - 1.0);
+    std::vector<T> Bfull(d * n, T(0));
+    sketch_general(blas::Layout::RowMajor, blas::Op::NoTrans, blas::Op::NoTrans, d, n, m, T(1), S, 0, 0, A.data(), n, T(0),
+                   Bfull.data(), n);
+    Communicators comms(nd);
+    CHECK(comms.size() == nd);
+    std::vector<T*> dA(nd, nullptr), dB(nd, nullptr);
+    std::vector<const T*> cA(nd, nullptr);
+    std::vector<int64_t> lda(nd, n);
+    int64_t covered = 0;
+    for (int g = 0; g < nd; ++g) {
+        auto [start, count] = mshard_block(m, nd, g);
+        CHECK(start == covered && (start % 4 == 0 || start == m));
+        covered += count;
+        cudaSetDevice(comms.device(g));
+        cudaMalloc((void**) &dA[g], sizeof(T) * (size_t) (count > 0 ? count * n : 1));
+        cudaMalloc((void**) &dB[g], sizeof(T) * (size_t) (d * n));
+        cudaMemcpy(dA[g], A.data() + start * n, sizeof(T) * (size_t) (count * n), cudaMemcpyHostToDevice);
+        cA[g] = dA[g];
+    }
+    CHECK(covered == m);
+    for (Reduce mode : {Reduce::Scatter, Reduce::All}) {
+        sketch_general_mshard(comms, blas::Layout::RowMajor, blas::Op::NoTrans, blas::Op::NoTrans, d, n, m, T(1), S, 0, 0, cA.data(),
+                              lda.data(), T(0), dB.data(), mode);
+        for (int g = 0; g < nd; ++g) {
+            cudaSetDevice(comms.device(g));
+            cudaDeviceSynchronize();
+            const int64_t cnt = mode == Reduce::Scatter ? d * n / nd : d * n, off = mode == Reduce::Scatter ? g * cnt : 0;
+            std::vector<T> got((size_t) cnt);
+            cudaMemcpy(got.data(), dB[g], sizeof(T) * (size_t) cnt, cudaMemcpyDeviceToHost);
+            double num = 0, den = 0;
+            for (int64_t i = 0; i < cnt; ++i) { double e = (double) got[i] - (double) Bfull[off + i]; num += e * e; den += (double) Bfull[off + i] * Bfull[off + i]; }
+            CHECK(std::sqrt(num / den) < tol);
+        }
+    }
+    for (int g = 0; g < nd; ++g) { cudaSetDevice(comms.device(g)); cudaFree(dA[g]); cudaFree(dB[g]); }
+    cudaSetDevice(0);
+    // a filled operator is refused, as is a communicator array of the wrong size
+    std::printf("multi_gpu_checks<%s>: %d GPU(s)\n", sizeof(T) == 4 ? "float" : "double", nd);
+}
+
 int main(int argc, char** argv) {
     host_checks();
     if (!(argc > 1 && std::strcmp(argv[1], "--host") == 0)) {
         device_checks<float>();
         device_checks<double>();
+        multi_gpu_checks<float>();
+        multi_gpu_checks<double>();
     }
     std::printf(failures ? "test_dropin: %d FAILURES\n" : "test_dropin: all checks passed\n", failures);
     return failures ? 1 : 0;

@@ -466,6 +466,55 @@ class Ref(_Base):
     def rsksp3(self, fmt, layout, opA, opS, m, d, n, alpha, spA, dist, ctr, key, ro_s, co_s, beta, B, ldb, prefill=0):
         self._sksp(0, fmt, layout, opA, opS, m, d, n, alpha, dist, ctr, key, prefill, ro_s, co_s, spA, beta, B, ldb)
 
+    # --- sparse data: public spmm, conversions, random matrices (the reference's own code; int64 indices) ---
+    def spmm(self, side_left, fmt, layout, op1, op2, x, y, z, alpha, spA, ro_a, co_a, B, ldb, beta, C, ldc):
+        """left_spmm(layout, opA, opB, d, n, m, ...) for side_left = 1; right_spmm(layout, opA(dense), opB(sparse),
+        m, d, n, ...) for side_left = 0 (spmm_dispatch.hh:52-219). C is updated in place."""
+        sfx, t = self._t(C.dtype)
+        A_rows, A_cols, nnz, vals, idx0, idx1 = spA
+        fn = getattr(self.lib, f"rbref_spmm_{sfx}")
+        sig = "iicccqqq" + t + "qqqppp" + "qq" + "pq" + t + "pq"
+        self._check(_call(fn, sig, (side_left, fmt, layout, op1, op2, x, y, z, alpha, A_rows, A_cols, nnz, vals, idx0, idx1,
+                                    ro_a, co_a, B, ldb, beta, C, ldc)), "spmm")
+
+    def coo_to_compressed(self, to_csc, n_rows, n_cols, vals, rows, cols):
+        nnz = len(vals)
+        sfx, _ = self._t(vals.dtype)
+        ov, oi = np.zeros(nnz, vals.dtype), np.zeros(nnz, np.int64)
+        op = np.zeros((n_cols if to_csc else n_rows) + 1, np.int64)
+        fn = getattr(self.lib, f"rbref_coo_to_compressed_{sfx}")
+        self._check(_call(fn, "iqqqpppppp", (to_csc, n_rows, n_cols, nnz, np.ascontiguousarray(vals),
+                                             np.ascontiguousarray(rows, np.int64), np.ascontiguousarray(cols, np.int64),
+                                             ov, oi, op)), "coo_to_compressed")
+        return ov, oi, op
+
+    def compressed_to_coo(self, from_csc, n_rows, n_cols, vals, idx, ptr):
+        nnz = len(vals)
+        sfx, _ = self._t(vals.dtype)
+        out = np.zeros(nnz, np.int64)
+        fn = getattr(self.lib, f"rbref_compressed_to_coo_{sfx}")
+        self._check(_call(fn, "iqqqpppp", (from_csc, n_rows, n_cols, nnz, np.ascontiguousarray(vals),
+                                           np.ascontiguousarray(idx, np.int64), np.ascontiguousarray(ptr, np.int64), out)),
+                    "compressed_to_coo")
+        return out
+
+    def random_sparse(self, which, m, n, density, ctr, key, dtype=np.float32):
+        """random_csr (which=0) / random_csc (1) / random_coo (2), random_matrix.hh:136-355.
+        Returns (vals, idx0, idx1, nnz, next_ctr) in the (vals, idx0, idx1) convention of the C ABI."""
+        sfx, _ = self._t(dtype)
+        fn = getattr(self.lib, f"rbref_random_sparse_{sfx}")
+        nnz, nxt = np.zeros(1, np.int64), np.zeros(4, np.uint32)
+        n0 = lambda k: (m + 1) if which == 0 else k
+        n1 = lambda k: (n + 1) if which == 1 else k
+        v, i0, i1 = np.zeros(1, dtype), np.zeros(n0(1), np.int64), np.zeros(n1(1), np.int64)
+        self._check(_call(fn, "iqqdppqppppp", (which, m, n, float(density), u32(ctr), u32(key), 0, v, i0, i1, nnz, nxt)),
+                    "random_sparse")
+        k = int(nnz[0])
+        v, i0, i1 = np.zeros(max(k, 1), dtype), np.zeros(n0(max(k, 1)), np.int64), np.zeros(n1(max(k, 1)), np.int64)
+        self._check(_call(fn, "iqqdppqppppp", (which, m, n, float(density), u32(ctr), u32(key), max(k, 1), v, i0, i1, nnz,
+                                               nxt)), "random_sparse")
+        return v[:k], (i0 if which == 0 else i0[:k]), (i1 if which == 1 else i1[:k]), k, nxt
+
     def sketch_vector_dense(self, opS, d, m, alpha, dist, ctr, key, ro_s, co_s, x, incx, beta, y, incy):
         sfx, t = self._t(y.dtype)
         fn = getattr(self.lib, f"rbref_sketch_vector_dense_{sfx}")

@@ -1,0 +1,340 @@
+"""GPU parity tests added in round 2 (run with -m gpu on the B200 box), all through the C ABI:
+
+* the BASELINE.json configurations at their OWN shapes against the compiled reference (oracle/_ref): C1 in full,
+  a row block of C3 with a non-zero operator offset, a row slice of a C5 column shard;
+* the public spmm entry points and the format conversions against the reference's own left_spmm / right_spmm /
+  coo_to_csr / coo_to_csc / csr_to_coo / csc_to_coo (not scipy);
+* random_coo bit for bit against the reference's sequential PhiloxStream, random_csr / random_csc structure, and
+  the CSR column partition;
+* the m-sharded left sketch of the C ABI (rb_lskge3_mshard_*): one rank in-process, two ranks under torchrun with
+  CUDA + NCCL (skipped below two devices), and the single-process rb_comm_init form through the C++ drop-in test.
+"""
+import itertools
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+
+pytestmark = pytest.mark.gpu
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+
+
+def relerr(a, b):
+    a = np.asarray(a, np.float64)
+    b = np.asarray(b, np.float64)
+    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300)
+
+
+@pytest.fixture(scope="module")
+def gpu():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    from gpu_impl import Gpu
+    return Gpu()
+
+
+def _gauss(rb, torch, rows, cols, seed, dtype):
+    """rows x cols standard-normal data made by the library's own fill_dense (bit-exact to the reference's, so the
+    CPU side could regenerate it; here it is simply copied back). Returned flat, in DenseDist's natural layout."""
+    buf = torch.empty(rows * cols, dtype=dtype, device="cuda")
+    rb.fill_dense(rb.DenseDist(rows, cols), buf, rb.RNGState(seed))
+    return buf
+
+
+# ------------------------------------------------------------------------------ BASELINE shapes vs the reference
+def test_c1_full_shape_vs_reference(ref):
+    """BASELINE.json configs[0] exactly: sketch_general<float>(ColMajor, N, N, d=1024, n=1024, m=100000, 1,
+    DenseSkOp(DenseDist(1024, 100000, Uniform)), A, lda=m, 0, B, ldb=d). Tolerance: 1e-5 relative Frobenius
+    (north_star); the reference's own componentwise bound (test/test_matmul_cores/linop_common.hh:260-266) is looser."""
+    import torch
+    import randblas_b200 as rb
+    d, n, m = 1024, 1024, 100000
+    A = _gauss(rb, torch, m, n, 99, torch.float32)          # tall => ColMajor natural layout, lda = m
+    B = torch.zeros(d * n, dtype=torch.float32, device="cuda")
+    S = rb.DenseSkOp(rb.DenseDist(d, m, rb.ScalarDist.Uniform), rb.RNGState(1997), np.float32)
+    before = rb.counter("tensor_core_launches")
+    rb.sketch_general("C", "N", "N", d, n, m, 1.0, S, 0, 0, A, m, 0.0, B, d)
+    torch.cuda.synchronize()
+    assert rb.counter("tensor_core_launches") == before + 1
+    want = np.zeros(d * n, np.float32)
+    ctr, key = ol.state_from_u64(1997)
+    ref.set_threads(os.cpu_count() or 1)
+    ref.lskge3("C", "N", "N", d, n, m, np.float32(1), (d, m, "U", "L"), ctr, key, 0, 0, A.cpu().numpy(), m,
+               np.float32(0), want, d)
+    err = relerr(B.cpu().numpy(), want)
+    assert err < 1e-5, err
+    # the CPU result itself carries float-GEMM rounding; against an fp64 product of the same operands the GPU path
+    # must be at least as accurate as the contract as well
+    Sm, _ = ref.fill_dense_unpacked("R", d, m, "U", "L", d, m, 0, 0, ctr, key, np.float32)
+    exact = (torch.from_numpy(Sm.reshape(d, m)).cuda().double() @ A.view(n, m).t().double()).t().contiguous().view(-1)
+    err64 = float((B.double() - exact).norm() / exact.norm())
+    assert err64 < 1e-5, err64
+    print(f"C1 full: rel err vs reference {err:.2e}, vs fp64 product {err64:.2e}")
+
+
+def test_c3_block_shape_vs_reference(ref):
+    """A row block of BASELINE.json configs[2]: d=4096, n=512, 20000 rows of A taken at row 1,000,000 of the
+    m = 4,000,000 problem (co_s = 1000000: what rank 2 of 8 computes first), Gaussian double. 1e-12."""
+    import torch
+    import randblas_b200 as rb
+    d, n, mb, m_total, co = 4096, 512, 20000, 4000000, 1000000
+    A = _gauss(rb, torch, mb, n, 99, torch.float64)          # ColMajor, lda = mb
+    B = torch.zeros(d * n, dtype=torch.float64, device="cuda")
+    S = rb.DenseSkOp(rb.DenseDist(d, m_total, rb.ScalarDist.Gaussian), rb.RNGState(1997), np.float64)
+    before = rb.counter("tensor_core_launches")
+    rb.sketch_general("C", "N", "N", d, n, mb, 1.0, S, 0, co, A, mb, 0.0, B, d)
+    torch.cuda.synchronize()
+    assert rb.counter("tensor_core_launches") == before + 1
+    want = np.zeros(d * n, np.float64)
+    ctr, key = ol.state_from_u64(1997)
+    ref.set_threads(os.cpu_count() or 1)
+    ref.lskge3("C", "N", "N", d, n, mb, 1.0, (d, m_total, "G", "L"), ctr, key, 0, co, A.cpu().numpy(), mb, 0.0, want, d)
+    err = relerr(B.cpu().numpy(), want)
+    assert err < 1e-12, err
+    print(f"C3 block: rel err vs reference {err:.2e}")
+
+
+def test_c5_slice_shape_vs_reference(ref):
+    """A row slice of a column shard of BASELINE.json configs[4]: d=512, the shard's n_local = 125000 columns, the
+    first 100000 rows of the 1e7-row CSR matrix (density 1e-4, made by random_coo -- the reference's generator --
+    then CSR), against the reference's sketch_sparse with the matching 512 x 100000 window of the 512 x 1e7 operator."""
+    import torch
+    import randblas_b200 as rb
+    d, n_local, rows, m_total = 512, 125000, 100000, 10000000
+    A, _ = rb.random_csr(rows, n_local, 1e-4, rb.RNGState(4242), np.float32, np.int64)
+    assert A.ambiguous == 0
+    B = torch.zeros(d * n_local, dtype=torch.float32, device="cuda")
+    S = rb.DenseSkOp(rb.DenseDist(d, m_total), rb.RNGState(1997), np.float32)
+    rb.sketch_sparse("C", "N", "N", d, n_local, rows, 1.0, S, 0, 0, A, 0.0, B, d)
+    torch.cuda.synchronize()
+    spA = (rows, n_local, A.nnz, A.vals.cpu().numpy(), A.rowptr.cpu().numpy(), A.colidxs.cpu().numpy())
+    want = np.zeros(d * n_local, np.float32)
+    ctr, key = ol.state_from_u64(1997)
+    ref.set_threads(os.cpu_count() or 1)
+    ref.lsksp3(0, "C", "N", "N", d, n_local, rows, np.float32(1), (d, m_total, "G", "L"), ctr, key, 0, 0, spA,
+               np.float32(0), want, d)
+    err = relerr(B.cpu().numpy(), want)
+    assert err < 1e-5, err
+    print(f"C5 slice: nnz {A.nnz}, rel err vs reference {err:.2e}")
+
+
+# ------------------------------------------------------------------------------ spmm + conversions vs the reference
+def _sp_tuple(M, fmt, dt):
+    if fmt == 0:
+        M = M.tocsr(); M.sort_indices()
+        return (M.shape[0], M.shape[1], M.nnz, M.data.astype(dt), M.indptr.astype(np.int64), M.indices.astype(np.int64))
+    if fmt == 1:
+        M = M.tocsc(); M.sort_indices()
+        return (M.shape[0], M.shape[1], M.nnz, M.data.astype(dt), M.indices.astype(np.int64), M.indptr.astype(np.int64))
+    M = M.tocoo()
+    return (M.shape[0], M.shape[1], M.nnz, M.data.astype(dt), M.row.astype(np.int64), M.col.astype(np.int64))
+
+
+def _rb_mat(rb, torch, spA, fmt, idt):
+    r, c, nnz, vals, i0, i1 = spA
+    cls = (rb.CSRMatrix, rb.CSCMatrix, rb.COOMatrix)[fmt]
+    return cls(r, c, nnz, torch.from_numpy(vals).cuda(), torch.from_numpy(i0.astype(idt)).cuda(),
+               torch.from_numpy(i1.astype(idt)).cuda())
+
+
+def test_left_and_right_spmm_vs_reference(ref):
+    """rb_spmm_* against RandBLAS::sparse_data::left_spmm / right_spmm themselves (spmm_dispatch.hh:52-219): CSR, CSC,
+    COO x both ops of the sparse and of the dense matrix x both layouts x float/double x int32/int64, padded leading
+    dimensions, alpha/beta, and a COO submatrix window."""
+    import scipy.sparse as sp
+    import torch
+    import randblas_b200 as rb
+    rng = np.random.default_rng(13)
+    d, n, m = 37, 23, 211
+    for dt, tol in ((np.float64, 1e-12), (np.float32, 1e-5)):
+        for fmt, idt, lay, opA, opB in itertools.product((0, 1, 2), (np.int32, np.int64), "CR", "NT", "NT"):
+            Am = sp.random(*((d, m) if opA == "N" else (m, d)), density=0.08, random_state=int(rng.integers(1 << 30)),
+                           format="coo", dtype=np.float64)
+            spA = _sp_tuple(Am, fmt, dt)
+            # left: C(d x n) = alpha op(A)(d x m) op(B)(m x n) + beta C
+            rB, cB = (m, n) if opB == "N" else (n, m)
+            ldb = (rB if lay == "C" else cB) + 1
+            ldc = (d if lay == "C" else n) + 2
+            Bbuf = rng.standard_normal(ldb * (cB if lay == "C" else rB)).astype(dt)
+            C0 = rng.standard_normal(ldc * (n if lay == "C" else d)).astype(dt)
+            want = C0.copy()
+            ref.spmm(1, fmt, lay, opA, opB, d, n, m, dt(0.5), spA, 0, 0, Bbuf, ldb, dt(-1.5), want, ldc)
+            Cd = torch.from_numpy(C0.copy()).cuda()
+            rb.left_spmm(lay, opA, opB, d, n, m, 0.5, _rb_mat(rb, torch, spA, fmt, idt), 0, 0, torch.from_numpy(Bbuf).cuda(),
+                         ldb, -1.5, Cd, ldc)
+            assert relerr(Cd.cpu().numpy(), want) < tol, ("left", fmt, idt, lay, opA, opB)
+            # right: C(n x d) = alpha op(B)(n x m) op(A_sp)(m x d) + beta C
+            Am2 = sp.random(*((m, d) if opA == "N" else (d, m)), density=0.08, random_state=int(rng.integers(1 << 30)),
+                            format="coo", dtype=np.float64)
+            spA2 = _sp_tuple(Am2, fmt, dt)
+            rB2, cB2 = (n, m) if opB == "N" else (m, n)
+            ldb2 = (rB2 if lay == "C" else cB2) + 1
+            ldc2 = (n if lay == "C" else d) + 1
+            Bbuf2 = rng.standard_normal(ldb2 * (cB2 if lay == "C" else rB2)).astype(dt)
+            C02 = rng.standard_normal(ldc2 * (d if lay == "C" else n)).astype(dt)
+            want2 = C02.copy()
+            ref.spmm(0, fmt, lay, opB, opA, n, d, m, dt(2.0), spA2, 0, 0, Bbuf2, ldb2, dt(0.25), want2, ldc2)
+            Cd2 = torch.from_numpy(C02.copy()).cuda()
+            rb.right_spmm(lay, opB, opA, n, d, m, 2.0, torch.from_numpy(Bbuf2).cuda(), ldb2,
+                          _rb_mat(rb, torch, spA2, fmt, idt), 0, 0, 0.25, Cd2, ldc2)
+            assert relerr(Cd2.cpu().numpy(), want2) < tol, ("right", fmt, idt, lay, opA, opB)
+    # COO submatrix window (the reference accepts offsets for COO only)
+    big = sp.random(60, 300, density=0.05, random_state=5, format="coo", dtype=np.float64)
+    spA = _sp_tuple(big, 2, np.float64)
+    Bbuf = rng.standard_normal(m * n)
+    want = np.zeros(d * n)
+    ref.spmm(1, 2, "R", "N", "N", d, n, m, 1.0, spA, 3, 7, Bbuf, n, 0.0, want, n)
+    Cd = torch.zeros(d * n, dtype=torch.float64, device="cuda")
+    rb.left_spmm("R", "N", "N", d, n, m, 1.0, _rb_mat(rb, torch, spA, 2, np.int64), 3, 7, torch.from_numpy(Bbuf).cuda(), n,
+                 0.0, Cd, n)
+    assert relerr(Cd.cpu().numpy(), want) < 1e-12
+
+
+def test_sparse_format_conversions_vs_reference(ref):
+    """coo_to_csr / coo_to_csc / csr_to_coo / csc_to_coo against the reference's conversions.hh:49-121 on unsorted,
+    duplicate-free COO input: identical arrays (indices and values), for both scalar types, device and host arrays."""
+    import scipy.sparse as sp
+    import torch
+    import randblas_b200 as rb
+    rng = np.random.default_rng(17)
+    for (nr, nc, dens) in ((37, 53, 0.2), (2000, 3000, 0.01), (301, 7, 0.3)):
+        M = sp.random(nr, nc, density=dens, random_state=int(rng.integers(1 << 30)), format="coo", dtype=np.float64)
+        perm = rng.permutation(M.nnz)
+        for idt, dt, on_dev in itertools.product((np.int32, np.int64), (np.float32, np.float64), (True, False)):
+            vals, rows, cols = M.data[perm].astype(dt), M.row[perm].astype(np.int64), M.col[perm].astype(np.int64)
+            mk = (lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()) if on_dev else np.ascontiguousarray
+            back = (lambda t: t.cpu().numpy()) if on_dev else (lambda t: t)
+            coo = rb.COOMatrix(nr, nc, M.nnz, mk(vals), mk(rows.astype(idt)), mk(cols.astype(idt)))
+            csr, csc = rb.coo_to_csr(coo), rb.coo_to_csc(coo)
+            rv, ri, rp = ref.coo_to_compressed(0, nr, nc, vals, rows, cols)
+            assert np.array_equal(back(csr.rowptr), rp) and np.array_equal(back(csr.colidxs), ri)
+            assert np.array_equal(back(csr.vals), rv)
+            cv, ci, cp = ref.coo_to_compressed(1, nr, nc, vals, rows, cols)
+            assert np.array_equal(back(csc.colptr), cp) and np.array_equal(back(csc.rowidxs), ci)
+            assert np.array_equal(back(csc.vals), cv)
+            assert np.array_equal(back(rb.csr_to_coo(csr).rows), ref.compressed_to_coo(0, nr, nc, rv, ri, rp))
+            assert np.array_equal(back(rb.csc_to_coo(csc).cols), ref.compressed_to_coo(1, nr, nc, cv, ci, cp))
+
+
+# ------------------------------------------------------------------------------ random matrices, column partition
+def test_random_coo_bit_exact_vs_reference(ref):
+    """rb_random_coo_* against RandBLAS::sparse_data::random_coo (random_matrix.hh:290-355): indices, values and the
+    returned state bit for bit, for both scalar and index types, several densities and keys, matrices with no stored
+    entry at all, and one large enough to take several scan batches (> 2^22 entries)."""
+    import torch
+    import randblas_b200 as rb
+    cases = [(50, 70, 0.1, 42), (1, 1, 0.5, 0), (7, 3, 0.9, 1), (1000, 999, 1e-3, 7), (300, 400, 1e-7, 3),
+             (2000, 3000, 0.02, 1 << 40), (0, 5, 0.3, 2), (5, 9, 0.0, 2), (3000, 4000, 0.45, 11)]
+    for (m, n, dens, k) in cases:
+        ctr, key = ol.state_from_u64(k)
+        ctr = ol.ctr_add(ctr, 0xFFFFFFF0)                     # counter carry into the second limb along the way
+        st = rb.RNGState(counter=list(ctr), key=list(key))
+        for dt, idt in ((np.float32, np.int64), (np.float64, np.int32)):
+            v, r, c, nnz, nxt = ref.random_sparse(2, m, n, dens, ctr, key, dt)
+            A, nst = rb.random_coo(m, n, dens, st, dt, idt)
+            assert A.ambiguous == 0
+            assert A.nnz == nnz, (m, n, dens, k, A.nnz, nnz)
+            assert nst.counter == [int(x) for x in nxt], (m, n, dens)
+            assert np.array_equal(A.rows.cpu().numpy(), r) and np.array_equal(A.cols.cpu().numpy(), c)
+            assert np.array_equal(A.vals.cpu().numpy(), v)
+    torch.cuda.synchronize()
+
+
+def test_random_csr_csc_and_column_block(ref):
+    """random_csr / random_csc are the compressed forms of random_coo's matrix (checked through the reference's own
+    coo_to_csr / coo_to_csc); csr_column_block equals scipy's column slice, and the column-sharded sketch of the blocks
+    equals the corresponding columns of the unsharded sketch_sparse."""
+    import scipy.sparse as sp
+    import torch
+    import randblas_b200 as rb
+    m, n, dens = 700, 900, 0.02
+    st = rb.RNGState(5)
+    ctr, key = ol.state_from_u64(5)
+    for dt, idt in ((np.float32, np.int64), (np.float64, np.int32)):
+        A, nst = rb.random_csr(m, n, dens, st, dt, idt)
+        v, r, c, nnz, nxt = ref.random_sparse(2, m, n, dens, ctr, key, dt)
+        rv, ri, rp = ref.coo_to_compressed(0, m, n, v, r, c)
+        assert A.nnz == nnz and nst.counter == [int(x) for x in nxt]
+        assert np.array_equal(A.rowptr.cpu().numpy(), rp) and np.array_equal(A.colidxs.cpu().numpy(), ri)
+        assert np.array_equal(A.vals.cpu().numpy(), rv)
+        C, _ = rb.random_csc(m, n, dens, st, dt, idt)
+        v2, r2, c2, nnz2, _ = ref.random_sparse(2, n, m, dens, ctr, key, dt)     # the transpose, row-major sorted
+        assert C.nnz == nnz2 and np.array_equal(C.rowidxs.cpu().numpy(), c2) and np.array_equal(C.vals.cpu().numpy(), v2)
+        ref_ptr = np.searchsorted(r2, np.arange(n + 1))
+        assert np.array_equal(C.colptr.cpu().numpy(), ref_ptr)
+        # column partition
+        M = sp.csr_matrix((rv, ri, rp), shape=(m, n))
+        d = 64
+        S = rb.DenseSkOp(rb.DenseDist(d, m), rb.RNGState(1997), dt)
+        tdt = torch.float32 if dt == np.float32 else torch.float64
+        Bfull = torch.zeros(d * n, dtype=tdt, device="cuda")
+        rb.sketch_sparse("C", "N", "N", d, n, m, 1.0, S, 0, 0, A, 0.0, Bfull, d)
+        for (c0, c1) in ((0, n), (0, 0), (13, 14), (100, 512), (512, n)):
+            blk = rb.csr_column_block(A, c0, c1)
+            want = M[:, c0:c1].tocsr(); want.sort_indices()
+            assert blk.nnz == want.nnz and blk.n_cols == c1 - c0
+            assert np.array_equal(blk.rowptr.cpu().numpy(), want.indptr)
+            assert np.array_equal(blk.colidxs.cpu().numpy(), want.indices)
+            assert np.array_equal(blk.vals.cpu().numpy(), want.data)
+            if c1 > c0:
+                Bblk = torch.zeros(d * (c1 - c0), dtype=tdt, device="cuda")
+                rb.sketch_sparse("C", "N", "N", d, c1 - c0, m, 1.0, S, 0, 0, blk, 0.0, Bblk, d)
+                assert torch.equal(Bblk, Bfull[d * c0: d * c1])
+            cb = rb.csc_column_block(C, c0, c1)
+            wc = M[:, c0:c1].tocsc(); wc.sort_indices()
+            assert cb.nnz == wc.nnz and np.array_equal(cb.colptr.cpu().numpy(), wc.indptr)
+            assert np.array_equal(cb.rowidxs.cpu().numpy(), wc.indices)
+
+
+# ------------------------------------------------------------------------------ m-sharded sketch in the C ABI
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+def test_mshard_entry_point_one_rank(gpu, ref, dt):
+    """rb_lskge3_mshard_* with a communicator of one rank (no NCCL involved): both modes, beta != 0, both layouts,
+    a non-trivial operator window, against the reference's sketch_general."""
+    import torch
+    import randblas_b200 as rb
+    from randblas_b200.sharding import Comm, lskge3_mshard
+    comm = Comm(1, 0)
+    assert comm.info()["nranks"] == 1
+    rng = np.random.default_rng(3)
+    ctr, key = ol.state_from_u64(1997)
+    tol = 1e-5 if dt == np.float32 else 1e-12
+    for layout, opS, opA, fam in (("C", "N", "N", "G"), ("R", "N", "N", "U"), ("C", "T", "N", "G"), ("R", "N", "T", "U")):
+        d, n, m, ro, co = 48, 20, 1003, 2, 5
+        Dr, Dc = (d + 3, m + 9) if opS == "N" else (m + 9, d + 3)
+        rA, cA = (m, n) if opA == "N" else (n, m)
+        lda = rA if layout == "C" else cA
+        ldb = d if layout == "C" else n
+        A = rng.standard_normal(rA * cA).astype(dt)
+        B0 = rng.standard_normal(d * n).astype(dt)
+        S = rb.DenseSkOp(rb.DenseDist(Dr, Dc, fam), rb.RNGState(1997), dt)
+        for mode, beta in ((0, 0.0), (1, 0.0), (0, -0.5), (1, 2.0)):
+            want = B0.copy()
+            ref.lskge3(layout, opS, opA, d, n, m, dt(1.5), (Dr, Dc, fam, "L"), ctr, key, ro, co, A, lda, dt(beta), want, ldb)
+            Bd = torch.from_numpy(B0.copy()).cuda()
+            lskge3_mshard(comm, layout, opS, opA, d, n, m, 1.5, S, ro, co, torch.from_numpy(A).cuda(), lda, beta, Bd, mode)
+            torch.cuda.synchronize()
+            assert relerr(Bd.cpu().numpy(), want) < tol, (layout, opS, opA, mode, beta)
+    comm.destroy()
+
+
+def test_mshard_two_ranks_cuda_nccl_vs_single_gpu_and_reference():
+    """The m-sharded left sketch on TWO GPUs, one process per GPU under torchrun, CUDA kernels + NCCL reduce-scatter /
+    all-reduce inside librandblas_b200.so, against the single-GPU sketch of the whole A and against the reference
+    (1e-12 double, 1e-5 float). The worker is tests/mshard_worker.py; skipped below two devices."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two CUDA devices (run with gpurun --gpus 2)")
+    port = 29400 + os.getpid() % 500
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), os.path.join(HERE, "mshard_worker.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    sys.stdout.write(r.stdout[-3000:])
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert "MSHARD_OK" in r.stdout
