@@ -270,6 +270,7 @@ def test_random_csr_csc_and_column_block(ref):
         assert np.array_equal(C.colptr.cpu().numpy(), ref_ptr)
         # column partition
         M = sp.csr_matrix((rv, ri, rp), shape=(m, n))
+        Mc = sp.csc_matrix((C.vals.cpu().numpy(), C.rowidxs.cpu().numpy(), C.colptr.cpu().numpy()), shape=(m, n))
         d = 64
         S = rb.DenseSkOp(rb.DenseDist(d, m), rb.RNGState(1997), dt)
         tdt = torch.float32 if dt == np.float32 else torch.float64
@@ -285,9 +286,10 @@ def test_random_csr_csc_and_column_block(ref):
             if c1 > c0:
                 Bblk = torch.zeros(d * (c1 - c0), dtype=tdt, device="cuda")
                 rb.sketch_sparse("C", "N", "N", d, c1 - c0, m, 1.0, S, 0, 0, blk, 0.0, Bblk, d)
-                assert torch.equal(Bblk, Bfull[d * c0: d * c1])
+                # same sums in a different order (the kernel reduces into B with floating-point atomics)
+                assert relerr(Bblk.cpu().numpy(), Bfull[d * c0: d * c1].cpu().numpy()) < (1e-5 if dt == np.float32 else 1e-12)
             cb = rb.csc_column_block(C, c0, c1)
-            wc = M[:, c0:c1].tocsc(); wc.sort_indices()
+            wc = Mc[:, c0:c1].tocsc(); wc.sort_indices()
             assert cb.nnz == wc.nnz and np.array_equal(cb.colptr.cpu().numpy(), wc.indptr)
             assert np.array_equal(cb.rowidxs.cpu().numpy(), wc.indices)
 
@@ -307,7 +309,7 @@ def test_mshard_entry_point_one_rank(gpu, ref, dt):
     tol = 1e-5 if dt == np.float32 else 1e-12
     for layout, opS, opA, fam in (("C", "N", "N", "G"), ("R", "N", "N", "U"), ("C", "T", "N", "G"), ("R", "N", "T", "U")):
         d, n, m, ro, co = 48, 20, 1003, 2, 5
-        Dr, Dc = (d + 3, m + 9) if opS == "N" else (m + 9, d + 3)
+        Dr, Dc = (d + 7, m + 9) if opS == "N" else (m + 9, d + 7)
         rA, cA = (m, n) if opA == "N" else (n, m)
         lda = rA if layout == "C" else cA
         ldb = d if layout == "C" else n
