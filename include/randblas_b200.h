@@ -316,7 +316,9 @@ int rb_lskge3_mshard_all_f64(int ndev, const rb_comm_t* comms, char layout, char
  * rb_set_option("dense_path", v): 0 = auto (tensor-core kernels where the shape allows), 1 = force the
  * generic SIMT kernel. Other switches select among kernels that compute the same result (kept for measurement):
  * "tc_cluster" (0 / 1 / 2: 2-CTA cluster mode of the float tensor-core kernel: never / where it pays / whenever
- * possible), "tc_splits", "dmma_uniform_warps", "saso_path", "saso_fill_path", "spdata_path" (DESIGN.md section 4).
+ * possible), "tc_splits", "tc_halves", "saso_path" (0 auto / 1 atomic kernel / 2 binned kernel), "saso_fill_path",
+ * "spdata_path" (1 = the deterministic column-owner kernel), "h2d_chunk_mb" (block size of the host-pointer sketch
+ * pipeline).
  * rb_get_counter("kernel_launches" | "tensor_core_launches" | "saso_owner_launches") counts kernels this library
  * launched. */
 int rb_set_option(const char* name, int64_t value);

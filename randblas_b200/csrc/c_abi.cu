@@ -18,7 +18,6 @@ namespace rb {
 static thread_local std::string g_err;
 static std::atomic<int64_t> g_launches{0};
 static std::atomic<int64_t> g_dense_path{0};
-static std::atomic<int64_t> g_dmma_uniform{0};       // 1: DMMA kernel in which every warp generates and multiplies (first design)
 static std::atomic<int64_t> g_saso_fill_path{0};   // 1: warp-per-vector SASO fill kernel (the 64-bit-index path)
 static std::atomic<int64_t> g_tc_launches{0};
 static std::atomic<int64_t> g_tc_splits{0};
@@ -26,7 +25,7 @@ static std::atomic<int64_t> g_tc_halves{1};      // generator warps split into t
 static std::atomic<int64_t> g_tc_cluster{1};     // 2-CTA clusters sharing the generated operator tile (skge3_f32_tc.cu)
 static std::atomic<int64_t> g_spdata_path{0};   // 0 auto (k-group kernel), 1 force the column-owner kernel (no atomics)
 static std::atomic<int64_t> g_h2d_chunk_mb{64};   // block size of the host-pointer sketch pipeline (MB of A per block)
-static std::atomic<int64_t> g_saso_path{0};     // 0 auto, 1 force the atomic kernel, 2 force the owner kernel
+static std::atomic<int64_t> g_saso_path{0};     // 0 auto, 1 force the atomic kernel, 2 force the binned kernel
 
 void set_error(const std::string& m) { g_err = m; }
 int fail(const std::string& m) { g_err = m; return RB_ERR_ARG; }
@@ -79,7 +78,6 @@ const double2* logf_table_device() {
 
 int64_t get_option(const char* name) {
     if (!std::strcmp(name, "dense_path")) return g_dense_path.load();
-    if (!std::strcmp(name, "dmma_uniform_warps")) return g_dmma_uniform.load();
     if (!std::strcmp(name, "saso_fill_path")) return g_saso_fill_path.load();
     if (!std::strcmp(name, "tc_splits")) return g_tc_splits.load();
     if (!std::strcmp(name, "tc_cluster")) return g_tc_cluster.load();
@@ -1102,7 +1100,6 @@ int64_t rb_get_option(const char* name) { return name ? rb::get_option(name) : 0
 int rb_set_option(const char* name, int64_t value) {
     RB_REQUIRE(name != nullptr);
     if (!std::strcmp(name, "dense_path")) { g_dense_path = value; return 0; }
-    if (!std::strcmp(name, "dmma_uniform_warps")) { g_dmma_uniform = value; return 0; }
     if (!std::strcmp(name, "saso_fill_path")) { g_saso_fill_path = value; return 0; }
     if (!std::strcmp(name, "tc_splits")) { g_tc_splits = value; return 0; }
     if (!std::strcmp(name, "tc_cluster")) { g_tc_cluster = value; return 0; }

@@ -90,179 +90,12 @@ __device__ __forceinline__ void cp_async16(void* dst, const void* src, int src_b
 
 // YMN: Y is contiguous along Q (left sketch of RowMajor data, right sketch of ColMajor data); the tile is staged as
 // [k][q] and the B fragments are read across rows.
-template <bool GAUSS, bool YMN, class TILE>
-__global__ void __launch_bounds__(D_THREADS, 1) skge3_dmma_kernel(const DmmaArgs a) {
-    constexpr int DM = TILE::DM, DN = TILE::DN, D_WN = TILE::D_WN, D_MI = TILE::D_MI, D_NI = TILE::D_NI, D_GR = TILE::D_GR,
-                  DLQ = TILE::DLQ;
-    __shared__ __align__(16) double2 logtab[GAUSS ? LOGF_TABLE_ENTRIES : 1];
-    extern __shared__ __align__(16) double dsm[];
-    double* Xs = dsm;                              // [D_STAGES][DM][DLD]
-    double* Ys = dsm + D_STAGES * DM * DLD;        // [D_STAGES][DN][DLD]
-    __shared__ __align__(8) unsigned long long bars[2 * D_STAGES];
-    const uint32_t bar_full = tma::smem_u32(bars), bar_empty = bar_full + 8 * D_STAGES;
-    if constexpr (GAUSS) load_logf_table(logtab, a.logtab);
-
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int wi = warp / D_WN, wj = warp % D_WN;  // 4 x 4 warps
-    const int g = lane >> 2, t4 = lane & 3;
-    const int64_t i0 = (int64_t) blockIdx.y * DM, j0 = (int64_t) blockIdx.x * DN;
-    const int split = blockIdx.z;
-    const int per = a.steps_total / a.splits, rem = a.steps_total % a.splits;
-    const int s_begin = split * per + min(split, rem);
-    const int nsteps = per + (split < rem ? 1 : 0);
-
-    // generator role: rows xr + (D_THREADS / D_CPR) rr, 4-wide chunk xc of the DK-deep step
-    const int xc = tid % D_CPR, xr = tid / D_CPR;
-    const uint64_t seed_lo = ((uint64_t) a.ctr.c1 << 32) | a.ctr.c0, seed_hi = ((uint64_t) a.ctr.c3 << 32) | a.ctr.c2;
-    uint64_t off[D_GR];
-#pragma unroll
-    for (int rr = 0; rr < D_GR; ++rr)
-        off[rr] = (uint64_t) ((a.v0 + i0 + xr + (D_THREADS / D_CPR) * rr) * a.R + a.ublk0 + xc) + (uint64_t) D_CPR * (uint64_t) s_begin;
-
-    auto gen_x = [&](int buf) {
-#pragma unroll
-        for (int rr = 0; rr < D_GR; ++rr) {
-            const uint64_t lo = seed_lo + off[rr];
-            const uint64_t hi = seed_hi + (lo < seed_lo ? 1ull : 0ull);
-            off[rr] += D_CPR;
-            const Ctr128 cc{(uint32_t) lo, (uint32_t) (lo >> 32), (uint32_t) hi, (uint32_t) (hi >> 32)};
-            float4 f = transform4<GAUSS>(philox4x32_10(cc, a.key), logtab);
-            if (a.kshift) {
-                const float4 h = transform4<GAUSS>(philox4x32_10(ctr_add(cc, 1), a.key), logtab);
-                if (a.kshift == 1) f = make_float4(f.y, f.z, f.w, h.x);
-                else if (a.kshift == 2) f = make_float4(f.z, f.w, h.x, h.y);
-                else f = make_float4(f.w, h.x, h.y, h.z);
-            }
-            double* dst = Xs + ((size_t) buf * DM + xr + (D_THREADS / D_CPR) * rr) * DLD + 4 * xc;
-            *reinterpret_cast<double2*>(dst) = make_double2(finish_sample<double, GAUSS>(f.x), finish_sample<double, GAUSS>(f.y));
-            *reinterpret_cast<double2*>(dst + 2) = make_double2(finish_sample<double, GAUSS>(f.z), finish_sample<double, GAUSS>(f.w));
-        }
-    };
-    // Y tile: 128 columns x 16 k = 1024 chunks of 2 doubles; thread handles chunks tid + D_THREADS q
-    auto load_y = [&](int buf, int step) {
-        const int64_t k0 = (int64_t) (s_begin + step) * DK;
-#pragma unroll
-        for (int q = 0; q < (DN * DK / 2) / D_THREADS; ++q) {
-            const int ch = tid + D_THREADS * q;
-            if constexpr (!YMN) {
-                const int jj = ch / (DK / 2), kc = (ch % (DK / 2)) * 2;
-                double* dst = Ys + ((size_t) buf * DN + jj) * DLD + kc;
-                const int64_t j = j0 + jj, k = k0 + kc;
-                if (j < a.Q && k + 1 < a.K) {
-                    cp_async16(dst, a.Y + j * a.ycs + k, 16);
-                } else {
-                    double y0 = 0.0, y1 = 0.0;
-                    if (j < a.Q && k < a.K) y0 = a.Y[j * a.ycs + k];
-                    dst[0] = y0; dst[1] = y1;
-                }
-            } else {
-                const int kk = ch / (DN / 2), jc = (ch % (DN / 2)) * 2;     // k-row of the tile, pair of columns
-                double* dst = Ys + (size_t) buf * DN * DLD + kk * DLQ + jc;
-                const int64_t j = j0 + jc, k = k0 + kk;
-                if (k < a.K && j + 1 < a.Q) {
-                    cp_async16(dst, a.Y + k * a.ycs + j, 16);
-                } else {
-                    double y0 = 0.0, y1 = 0.0;
-                    if (k < a.K && j < a.Q) y0 = a.Y[k * a.ycs + j];
-                    dst[0] = y0; dst[1] = y1;
-                }
-            }
-        }
-        // the stage's full barrier gets one more arrival when this thread's copies have landed
-        asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar_full + 8u * (uint32_t) buf) : "memory");
-    };
-
-    double acc[D_MI][D_NI][2];
-#pragma unroll
-    for (int mi = 0; mi < D_MI; ++mi)
-#pragma unroll
-        for (int ni = 0; ni < D_NI; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
-
-    if (tid == 0) {
-#pragma unroll
-        for (int i = 0; i < D_STAGES; ++i) {
-            tma::mbar_init(bar_full + 8u * i, 2 * D_THREADS);
-            tma::mbar_init(bar_empty + 8u * i, D_THREADS / 32);
-        }
-        tma::mbar_fence_init();
-    }
-    __syncthreads();                  // logtab, barriers
-    auto arrive = [&](uint32_t bar) {
-        asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(bar) : "memory");
-    };
-    // produce this thread's share of stage (step % D_STAGES): its Y copies and its 8 samples of the S tile
-    auto produce = [&](int step) {
-        const int buf = step % D_STAGES;
-        if (step >= D_STAGES) tma::mbar_wait(bar_empty + 8u * (uint32_t) buf, (uint32_t) ((step / D_STAGES - 1) & 1));
-        load_y(buf, step);
-        gen_x(buf);
-        arrive(bar_full + 8u * (uint32_t) buf);
-    };
-    auto consume = [&](int step) {
-        const int buf = step % D_STAGES;
-        tma::mbar_wait(bar_full + 8u * (uint32_t) buf, (uint32_t) ((step / D_STAGES) & 1));
-        const double* xb = Xs + ((size_t) buf * DM + wi * (D_MI * 8) + g) * DLD + t4;
-        const double* yb = YMN ? Ys + (size_t) buf * DN * DLD + t4 * DLQ + wj * (D_NI * 8) + g
-                               : Ys + ((size_t) buf * DN + wj * (D_NI * 8) + g) * DLD + t4;
-#pragma unroll
-        for (int k4 = 0; k4 < DK / 4; ++k4) {
-            double af[D_MI], bf[D_NI];
-#pragma unroll
-            for (int mi = 0; mi < D_MI; ++mi) af[mi] = xb[mi * 8 * DLD + k4 * 4];
-#pragma unroll
-            for (int ni = 0; ni < D_NI; ++ni) bf[ni] = YMN ? yb[k4 * 4 * DLQ + ni * 8] : yb[ni * 8 * DLD + k4 * 4];
-#pragma unroll
-            for (int mi = 0; mi < D_MI; ++mi)
-#pragma unroll
-                for (int ni = 0; ni < D_NI; ++ni) dmma(acc[mi][ni], af[mi], bf[ni]);
-        }
-        __syncwarp();
-        if (lane == 0) arrive(bar_empty + 8u * (uint32_t) buf);
-    };
-    // prologue: the first D_AHEAD stages; then step s consumes stage s and produces stage s + D_AHEAD, in opposite
-    // order for the two warps of a scheduler (warp w and w + 4). With two stages this still never stalls: the warps
-    // that produce first need the stage consumed in the PREVIOUS iteration, the warps that consume first need the
-    // stage completed in the previous iteration.
-    for (int s0 = 0; s0 < D_AHEAD && s0 < nsteps; ++s0) produce(s0);
-    if (((warp >> 2) & 1) == 0) {
-        for (int step = 0; step < nsteps; ++step) {
-            consume(step);
-            if (step + D_AHEAD < nsteps) produce(step + D_AHEAD);
-        }
-    } else {
-        for (int step = 0; step < nsteps; ++step) {
-            if (step + D_AHEAD < nsteps) produce(step + D_AHEAD);
-            consume(step);
-        }
-    }
-
-    // epilogue: c0 at (row g, col 2 t4), c1 at (row g, col 2 t4 + 1) of each 8 x 8 tile
-#pragma unroll
-    for (int mi = 0; mi < D_MI; ++mi) {
-        const int64_t i = i0 + wi * (D_MI * 8) + mi * 8 + g;
-#pragma unroll
-        for (int ni = 0; ni < D_NI; ++ni) {
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                const int64_t j = j0 + wj * (D_NI * 8) + ni * 8 + 2 * t4 + e;
-                if (a.W) {
-                    a.W[((int64_t) split * a.Q_pad + j) * a.P_pad + i] = acc[mi][ni][e];
-                } else if (i < a.P && j < a.Q) {
-                    double* cp = a.C + i * a.crs + j * a.ccs;
-                    double r = a.alpha * acc[mi][ni][e];
-                    if (a.beta != 0.0) r += a.beta * (*cp);
-                    *cp = r;
-                }
-            }
-        }
-    }
-}
-
-// ---- warp-specialised variant -------------------------------------------------------------------------------
+// ---- the kernel: warp-specialised ------------------------------------------------------------------------------
 // 12 warps: warps 0-3 (one per scheduler) only GENERATE the S tile of every stage; warps 4-11 (two per scheduler) issue
-// the DMMAs and, between two steps, the cp.async copies of the Y tile two steps ahead (8 per thread). A DMMA warp never leaves its DMMA stream (in the
-// kernel above every warp spends part of each step generating, and DMMAs issue in order), the producer warp of a
-// scheduler fills the issue slots between DMMAs. Register split with setmaxnreg: producers 72, DMMA warps 216.
+// the DMMAs and, between two steps, the cp.async copies of the Y tile two steps ahead (8 per thread). A DMMA warp never
+// leaves its DMMA stream, the producer warp of a scheduler fills the issue slots between DMMAs. Register split with
+// setmaxnreg: producers 72, DMMA warps 216. (A first design in which every warp generated and multiplied ran at 72.9-83.6 ms
+// on the C3 shard instead of 69.4)
 constexpr int WS_THREADS = 384, WS_PROD = 128;
 
 // XMAT: the operator is materialised (S.buff != nullptr, skge.hh:174-181): the producer warps copy its DM x 16 tiles
@@ -520,19 +353,7 @@ int launch_dense_dmma_f64(const DenseProblem<double>& p, cudaStream_t st) {
     const size_t smem = wide ? TileWide::smem : TileSquare::smem;
     const bool gauss = p.family == 'G';
     dim3 grid((unsigned) tiles_q, (unsigned) tiles_p, (unsigned) splits);
-    auto launch = [&](auto kern, DevOnce& attr_done) -> int {
-        if (attr_done.need()) {
-            if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem) != cudaSuccess) {
-                cudaGetLastError();
-                return -1;
-            }
-            attr_done.done();
-        }
-        kern<<<grid, D_THREADS, smem, st>>>(a);
-        return 0;
-    };
     static DevOnce attr_done[20];
-    const bool ws = get_option("dmma_uniform_warps") == 0;    // default: warp-specialised kernel
     auto launch_ws = [&](auto kern, DevOnce& done) -> int {
         if (done.need()) {
             if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem) != cudaSuccess) {
@@ -548,7 +369,7 @@ int launch_dense_dmma_f64(const DenseProblem<double>& p, cudaStream_t st) {
     if (xmat) {
         if (wide) lrc = y_mn ? launch_ws(skge3_dmma_ws_kernel<false, true, TileWide, true>, attr_done[19]) : launch_ws(skge3_dmma_ws_kernel<false, false, TileWide, true>, attr_done[18]);
         else lrc = y_mn ? launch_ws(skge3_dmma_ws_kernel<false, true, TileSquare, true>, attr_done[17]) : launch_ws(skge3_dmma_ws_kernel<false, false, TileSquare, true>, attr_done[16]);
-    } else if (ws) {
+    } else {
         if (wide) {
             if (gauss) lrc = y_mn ? launch_ws(skge3_dmma_ws_kernel<true, true, TileWide>, attr_done[15]) : launch_ws(skge3_dmma_ws_kernel<true, false, TileWide>, attr_done[14]);
             else lrc = y_mn ? launch_ws(skge3_dmma_ws_kernel<false, true, TileWide>, attr_done[13]) : launch_ws(skge3_dmma_ws_kernel<false, false, TileWide>, attr_done[12]);
@@ -556,12 +377,6 @@ int launch_dense_dmma_f64(const DenseProblem<double>& p, cudaStream_t st) {
             if (gauss) lrc = y_mn ? launch_ws(skge3_dmma_ws_kernel<true, true, TileSquare>, attr_done[11]) : launch_ws(skge3_dmma_ws_kernel<true, false, TileSquare>, attr_done[10]);
             else lrc = y_mn ? launch_ws(skge3_dmma_ws_kernel<false, true, TileSquare>, attr_done[9]) : launch_ws(skge3_dmma_ws_kernel<false, false, TileSquare>, attr_done[8]);
         }
-    } else if (wide) {
-        if (gauss) lrc = y_mn ? launch(skge3_dmma_kernel<true, true, TileWide>, attr_done[7]) : launch(skge3_dmma_kernel<true, false, TileWide>, attr_done[6]);
-        else lrc = y_mn ? launch(skge3_dmma_kernel<false, true, TileWide>, attr_done[5]) : launch(skge3_dmma_kernel<false, false, TileWide>, attr_done[4]);
-    } else {
-        if (gauss) lrc = y_mn ? launch(skge3_dmma_kernel<true, true, TileSquare>, attr_done[3]) : launch(skge3_dmma_kernel<true, false, TileSquare>, attr_done[2]);
-        else lrc = y_mn ? launch(skge3_dmma_kernel<false, true, TileSquare>, attr_done[1]) : launch(skge3_dmma_kernel<false, false, TileSquare>, attr_done[0]);
     }
     if (lrc) return -1;
     count_launch();

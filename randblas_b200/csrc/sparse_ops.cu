@@ -270,8 +270,6 @@ int launch_saso_apply(const SasoProblem<T>& p, cudaStream_t st) {
     if constexpr (sizeof(T) == 4) {
         rc = launch_saso_binned_f32(p, st);     // register-resident output, binned entry lists (saso_binned.cu)
         if (rc >= 0) return rc;
-        rc = launch_saso_owner_f32(p, st);      // first-generation owner kernel (saso_path = 3, or P > 8192)
-        if (rc >= 0) return rc;
     }
     // only minor-axis vectors that intersect the window are visited
     const int64_t w0 = p.major_is_rows ? p.co_s : p.ro_s;

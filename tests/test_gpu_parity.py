@@ -572,7 +572,7 @@ def test_sparse_operator_sketch_all_variants_vs_oracle(gpu, port, dt):
 
 
 def test_saso_owner_kernel_vs_oracle_and_vs_atomic_kernel(gpu, port):
-    """The register-resident SASO apply (saso_owner.cu) forced on shapes that cross tile boundaries: two row
+    """The register-resident SASO apply (saso_binned.cu) forced on shapes that cross tile boundaries: two row
     tiles of C (d > 1024), ragged column slices (n % 32 != 0), ragged last chunk of A, windows of the operator,
     every sub-warp group size of the entry generator, alpha/beta. Checked against the oracle, and at a larger
     shape against the atomic kernel (same operator, different summation order)."""
@@ -583,8 +583,8 @@ def test_saso_owner_kernel_vs_oracle_and_vs_atomic_kernel(gpu, port):
     dt = np.float32
     try:
         before = rb.counter("saso_owner_launches")
-        # saso_path 2 = binned kernel (saso_binned.cu, the default for large problems), 3 = first-generation owner kernel
-        for path, (d, n, m, vn, ro, co) in [(pp, sh) for pp in (2, 3) for sh in (
+        # saso_path 2 = force the binned kernel (saso_binned.cu, the default for large problems)
+        for path, (d, n, m, vn, ro, co) in [(pp, sh) for pp in (2,) for sh in (
                 (45, 29, 2111, 3, 2, 5), (1500, 64, 3000, 8, 0, 0), (1100, 100, 1537, 17, 7, 3),
                 (300, 36, 900, 32, 0, 1), (64, 32, 5000, 1, 1, 0), (2048, 40, 777, 5, 0, 0), (3000, 33, 1409, 2, 1, 1))]:
             rb.set_option("saso_path", path)
@@ -864,11 +864,9 @@ def test_dmma_double_sketch_q_contiguous_data_vs_oracle(gpu, port):
         port.lskge3("R", "N", "N", d, n, m, dt(alpha), (Dr, Dc, fam, "L"), ctr, key, ro, co, A, lda, dt(beta), B2, n + 1)
         assert relerr(B1, B2) < 1e-12, (("left RowMajor", d, n, m, ro, co, fam), relerr(B1, B2))
         assert np.array_equal(B1.reshape(d, n + 1)[:, n], B0.reshape(d, n + 1)[:, n])
-    # both CTA tiles (64 x 256 for n > 128, 128 x 128 otherwise) in both data orientations, for the warp-specialised
-    # kernel (default) and the first design (every warp generates and multiplies)
-    for uniform_warps, lay, (d, n, m, fam) in [(u, l, c) for u in (0, 1) for l in "CR"
+    # both CTA tiles (64 x 256 for n > 128, 128 x 128 otherwise) in both data orientations
+    for uniform_warps, lay, (d, n, m, fam) in [(u, l, c) for u in (0,) for l in "CR"
                                                for c in ((300, 100, 1200, "G"), (300, 260, 1200, "U"))]:
-        rb.set_option("dmma_uniform_warps", uniform_warps)
         lda = (m if lay == "C" else n) + 2
         A = rng.standard_normal((n if lay == "C" else m) * lda)
         ldb = (d if lay == "C" else n) + 1
@@ -879,7 +877,6 @@ def test_dmma_double_sketch_q_contiguous_data_vs_oracle(gpu, port):
         assert rb.counter("tensor_core_launches") == before + 1, (lay, d, n, m)
         port.lskge3(lay, "N", "N", d, n, m, dt(0.75), (d, m, fam, "L"), ctr, key, 0, 0, A, lda, dt(0.5), B2, ldb)
         assert relerr(B1, B2) < 1e-12, ((uniform_warps, lay, d, n, m, fam), relerr(B1, B2))
-    rb.set_option("dmma_uniform_warps", 0)
     for (m, d, n, Dr, Dc, ro, co, fam, alpha, beta) in [(2048, 128, 1024, 1024, 128, 0, 0, "G", 1.0, 0.0),
                                                          (1501, 100, 977, 1000, 120, 5, 3, "U", -0.5, 2.0)]:
         lda = m + (m % 2)
