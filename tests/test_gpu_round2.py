@@ -340,3 +340,56 @@ def test_mshard_two_ranks_cuda_nccl_vs_single_gpu_and_reference():
     sys.stdout.write(r.stdout[-3000:])
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "MSHARD_OK" in r.stdout
+
+
+# ------------------------------------------------------------------------------ example callers
+def _load_example(name):
+    import importlib.util
+    sys.path.insert(0, os.path.join(ROOT, "examples"))
+    spec = importlib.util.spec_from_file_location(name, os.path.join(ROOT, "examples", name + ".py"))
+    ex = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ex)
+    return ex
+
+
+def test_example_tls_sparse_skop_matches_reference_pipeline(ref):
+    """examples/tls_sparse_skop.py (the reference's examples/total-least-squares/tls_sparse_skop.cc) at a reduced size:
+    the sampled SASO operator equals the reference's arrays, the sketched data S*[A|b] equals the reference's
+    sketch_general for the same seeds (sampled and unsampled operator), and the sketched TLS solution is close to the
+    classical one."""
+    import torch
+    ex = _load_example("tls_sparse_skop")
+    m, n = 3000, 60
+    sk = 2 * (n + 1)
+    ctr, key = ol.state_from_u64(1997)
+    for sample_first in (True, False):
+        rel, SAB, S, AB = ex.main(m, n, verbose=False, sample_first=sample_first)
+        assert rel < 0.5
+        want = np.zeros(sk * (n + 1))
+        ref.lskges("C", "N", "N", sk, n + 1, m, 1.0, (sk, m, 8, "S"), ctr, key, 0, 0, AB.cpu().numpy(), m, 0.0, want, sk)
+        assert relerr(SAB.cpu().numpy(), want) < 1e-12
+        if sample_first:
+            v, r, c, nnz, _ = ref.fill_sparse(sk, m, 8, "S", ctr, key, np.float64, np.int64)
+            assert S.nnz == nnz and np.array_equal(S.rows.cpu().numpy(), r) and np.array_equal(S.cols.cpu().numpy(), c)
+            assert np.array_equal(S.vals.cpu().numpy(), v)
+    torch.cuda.synchronize()
+
+
+def test_example_sparse_low_rank_qb_recovers_planted_vectors():
+    """examples/svd_rank1_plus_noise.py (the reference's examples/sparse-low-rank-approx/svd_rank1_plus_noise.cc): the QB
+    factors reproduce the sparse matrix's action to the noise level and the leading singular triplet is the planted one."""
+    import scipy.sparse as sp
+    import torch
+    ex = _load_example("svd_rank1_plus_noise")
+    m, n, vec_nnz = 4000, 2500, 4
+    for p in (1, 2):
+        s0, cos_u, cos_v, A, Q, B = ex.main(m, n, vec_nnz, p=p, verbose=False)
+        assert abs(s0 - 100.0) < 1e-6 and cos_u > 1 - 1e-10 and cos_v > 1 - 1e-10
+        k = max(3, vec_nnz)
+        M = sp.coo_matrix((A.vals.cpu().numpy(), (A.rows.cpu().numpy(), A.cols.cpu().numpy())), shape=(m, n)).tocsr()
+        Qm, Bm = Q.view(k, m).t().cpu().numpy(), B.view(n, k).t().cpu().numpy()
+        assert np.linalg.norm(Qm.T @ Qm - np.eye(k)) < 1e-10
+        assert np.linalg.norm(Bm - Qm.T @ M) < 1e-10 * 100            # B = Q^T A through right_spmm
+        x = np.random.default_rng(0).standard_normal(n)
+        assert np.linalg.norm(M @ x - Qm @ (Bm @ x)) < 1e-3 * np.linalg.norm(M @ x)
+    torch.cuda.synchronize()
