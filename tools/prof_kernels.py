@@ -75,14 +75,8 @@ def main():
         S = rb.SparseSkOp(rb.SparseDist(d, m, k), rb.RNGState(1997), dtype=np.float32)
         f = lambda: rb.fill_sparse(S)
     elif what == "sksp":
-        d, m, n, per_row = 512, 1000000, 125000, 12.5
-        lens = torch.poisson(torch.full((m,), per_row, device="cuda")).to(torch.int64)
-        rowptr = torch.zeros(m + 1, dtype=torch.int64, device="cuda")
-        torch.cumsum(lens, 0, out=rowptr[1:])
-        nnz = int(rowptr[-1].item())
-        col = torch.randint(0, n, (nnz,), device="cuda", dtype=torch.int64)
-        vals = torch.randn(nnz, device="cuda", dtype=torch.float32)
-        A = rb.CSRMatrix(m, n, nnz, vals, rowptr, col)
+        d, m, n = 512, 1000000, 125000
+        A, _ = rb.random_csr(m, n, 1e-4, rb.RNGState(4242), np.float32, np.int64)      # a row slice of the C5 shard
         S = rb.DenseSkOp(rb.DenseDist(d, 10000000), rb.RNGState(1997), np.float32)
         B = torch.zeros(d * n, dtype=torch.float32, device="cuda")
         f = lambda: rb.sketch_sparse("C", "N", "N", d, n, m, 1.0, S, 0, 0, A, 0.0, B, d)
