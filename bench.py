@@ -796,9 +796,28 @@ def run_workload(wl, rb, torch, dist, rank, world, local, comm, steps, warmup, a
         if world > 1:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
         units, h2d, d2h = wl.e2e_units()
+        ceiling = None
+        if world > 1:
+            # what the host side allows when all ranks copy at once: a raw pinned-memory copy of the step's dominant
+            # transfer (same direction, up to 512 MB), all ranks concurrently -- the ceiling the e2e leg can reach
+            nb = int(min(max(h2d, d2h), 512 << 20))
+            hb = torch.empty(nb, dtype=torch.uint8, pin_memory=True)
+            db = torch.empty(nb, dtype=torch.uint8, device="cuda")
+            src, dst = (hb, db) if h2d >= d2h else (db, hb)
+            dst.copy_(src, non_blocking=True)
+            barrier()
+            tc0 = time.perf_counter()
+            for _ in range(3):
+                dst.copy_(src, non_blocking=True)
+            torch.cuda.synchronize()
+            tc = torch.tensor([(time.perf_counter() - tc0) / 3], dtype=torch.float64, device="cuda")
+            dist.all_reduce(tc, op=dist.ReduceOp.MAX)
+            ceiling = {"direction": "h2d" if h2d >= d2h else "d2h", "bytes": nb,
+                       "gbs_per_rank_all_ranks_concurrent": nb / 1e9 / float(tc.item())}
+            del hb, db
         e2e = {"value": units * world / float(te.item()), "unit": wl.unit, "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": d2h, "ms_per_step": float(te.item()) * 1e3, "steps": n_e2e,
-               "pcie_gbs_per_rank": (h2d + d2h) / 1e9 / float(te.item()),
+               "pcie_gbs_per_rank": (h2d + d2h) / 1e9 / float(te.item()), "raw_copy_ceiling": ceiling,
                "sample": wl.sample + (" (one such sample per rank)" if world > 1 else "")}
 
     cpu = None

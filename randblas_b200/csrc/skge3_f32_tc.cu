@@ -70,6 +70,8 @@ struct TcArgs {
     int64_t P, Q;
     int steps_total;   // ceil(K / 32)
     int y_mn;          // 1: Y is Q-contiguous; raw tiles are transposed by the generator warps
+    int x_t;           // 1: the operator's Philox blocks run along the ROWS of X (Axis::Short operators, transposed use of a
+                       //    Long one): a block is 4 consecutive rows of one column k; v0 then counts along k, ublk0 along i
     int splits;
     float alpha, beta;
     float* C;
@@ -458,6 +460,32 @@ __global__ void __launch_bounds__(TC_THREADS, 1) skge3_tc_kernel(const __grid_co
                 }
             } else {
             const bool my_turn = (CL == 1) || ((uint32_t) st == crank);
+            if (a.x_t) {
+                // Philox blocks along the rows of X: thread -> (column k of the step, 4-row block); element (i, k) is lane
+                // (u0 + i0 + i) & 3 of block (v0 + k) * R + (u0 + i0 + i) / 4 with u0 % 4 == 0 (checked by the launcher).
+                // The K-major swizzled tile is written with 4-byte stores: the 32 lanes of a warp hold 32 consecutive k
+                // of the same rows, i.e. 8 swizzled 16-byte chunks x 4 words = 32 different banks per store.
+                const int kl = gt & 31, rb0 = gt >> 5;
+#pragma unroll
+                for (int rr = 0; rr < XPT; ++rr) {
+                    const int rb = rb0 + (GEN_WARPS) * rr;
+                    const uint64_t o = (uint64_t) ((a.v0 + (int64_t) (s_begin + it) * BK + kl) * a.R + a.ublk0 + (i0 >> 2) + rb);
+                    const uint64_t lo = seed_lo + o;
+                    const uint64_t hi = seed_hi + (lo < seed_lo ? 1ull : 0ull);
+                    const Ctr128 cc{(uint32_t) lo, (uint32_t) (lo >> 32), (uint32_t) hi, (uint32_t) (hi >> 32)};
+                    const float4 f = transform4<GAUSS>(philox4x32_10(cc, a.key), logtab);
+                    const float fv[4] = {f.x, f.y, f.z, f.w};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int row = 4 * rb + j;
+                        float h, l;
+                        split_rn(finish_sample<float, GAUSS>(fv[j]), h, l);
+                        const uint32_t o4 = (uint32_t) row * 128u + (uint32_t) (((kl >> 2) ^ (row & 7)) << 4) + (uint32_t) (kl & 3) * 4u;
+                        *reinterpret_cast<float*>(stage + o4) = h;
+                        *reinterpret_cast<float*>(stage + X_BYTES + o4) = l;
+                    }
+                }
+            } else {
 #pragma unroll
             for (int rr = 0; rr < XPT; ++rr) {
                 const uint64_t lo = seed_lo + off[rr];
@@ -486,6 +514,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) skge3_tc_kernel(const __grid_co
                     st_cluster_v4(ra + X_BYTES, l);
                 }
             }
+            }   // !x_t
             }
             if (!a.y_mn) {
             mbar_wait(bar_full(st), ph);
@@ -599,7 +628,10 @@ int launch_dense_tc_f32(const DenseProblem<float>& p, cudaStream_t st) {
     const bool xmat = p.S_buff != nullptr;
     if (xmat && get_option("dense_path") == 4) return -1;     // experiment switch: materialised operators to the generic kernel
     if (!xmat && p.family == 'G' && !p.gen.logtab) return -1;
-    if (!(p.uk == 1 && p.vi == 1)) return -1;                 // Philox blocks must run along K
+    // Philox blocks along K (the default Axis::Long operators used as they are), or along the rows of X (Axis::Short
+    // operators and transposed uses: reference case table dense_skops.hh:187-199) when the window starts on a block
+    const bool x_t = (p.ui == 1 && p.vk == 1);
+    if (!(p.uk == 1 && p.vi == 1) && !(x_t && !xmat && (p.u0 & 3) == 0)) return -1;
     // Y K-contiguous, or Q-contiguous (left sketch of RowMajor data, right sketch of ColMajor data)
     const bool y_mn = (p.yrs != 1);
     if (y_mn && p.ycs != 1) return -1;
@@ -620,14 +652,14 @@ int launch_dense_tc_f32(const DenseProblem<float>& p, cudaStream_t st) {
 
     const int64_t tiles_p = (p.P + BM - 1) / BM, tiles_q = (p.Q + BN - 1) / BN;
     if (tiles_p > 65535 || tiles_q > 0x7fffffff) return -1;
-    const int kshift = (int) (p.u0 & 3);
+    const int kshift = x_t ? 0 : (int) (p.u0 & 3);
     const int64_t steps = (p.K + BK - 1) / BK;
     // Pairs of column tiles share the generated operator tile through a 2-CTA cluster. tc_cluster: 0 never; 1 (default)
     // where it was measured to pay -- Gaussian operators with K-contiguous data (1.83 -> 1.70 ms at d = n = 1024,
     // m = 1e5); 2 whenever the tile count is even. It does not pay elsewhere: distributed shared memory moves ~21 B/clk,
     // so shipping the 32 KB (hi, lo) tile costs as much as the MMAs of the step (Uniform: 1.06 -> 1.44 ms).
     const int64_t cl_opt = get_option("tc_cluster");
-    const bool cluster = !xmat && (tiles_q % 2 == 0) && (cl_opt == 2 || (cl_opt == 1 && p.family == 'G' && !y_mn));
+    const bool cluster = !xmat && !x_t && (tiles_q % 2 == 0) && (cl_opt == 2 || (cl_opt == 1 && p.family == 'G' && !y_mn));
     // Split K. Two constraints: (1) the tensor core adds into its fp32 accumulator with truncation, a bias that
     // grows linearly with the number of accumulated MMAs (measured: 4.6e-4 relative after 2048 K steps, 1.9e-6
     // after 8), so no partial sum stays in TMEM for more than MAX_CHAIN_STEPS steps; partial sums are added in
@@ -679,6 +711,7 @@ int launch_dense_tc_f32(const DenseProblem<float>& p, cudaStream_t st) {
     a.P = p.P; a.Q = p.Q;
     a.steps_total = (int) steps;
     a.y_mn = y_mn ? 1 : 0;
+    a.x_t = x_t ? 1 : 0;
     a.splits = splits;
     a.alpha = p.alpha; a.beta = p.beta;
     a.C = p.C; a.crs = p.crs; a.ccs = p.ccs;
@@ -691,7 +724,7 @@ int launch_dense_tc_f32(const DenseProblem<float>& p, cudaStream_t st) {
     static DevOnce attr_done[7];
     const bool gauss = p.family == 'G';
     // tc_halves: 1 (default) = the generator warps work on two K steps at a time where the kernel supports it
-    const bool halves = !xmat && !cluster && !y_mn && get_option("tc_halves") != 0;
+    const bool halves = !xmat && !cluster && !y_mn && !x_t && get_option("tc_halves") != 0;
     const int variant = xmat ? 2 : (cluster ? 3 : (halves ? 5 : 0)) + (gauss ? 1 : 0);
     auto set_attr = [&](auto kern) { return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM); };
     if (attr_done[variant].need()) {

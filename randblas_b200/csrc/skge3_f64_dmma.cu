@@ -64,6 +64,7 @@ struct DmmaArgs {
     const double2* logtab;
     int64_t R, v0, ublk0;
     int kshift;
+    int x_t;              // 1: Philox blocks run along the ROWS of X (Axis::Short operators, transposed uses): v0 counts along k
     int64_t P, Q, K;
     int steps_total, splits;
     double alpha, beta;
@@ -174,6 +175,25 @@ __global__ void __launch_bounds__(WS_THREADS, 1) skge3_dmma_ws_kernel(const Dmma
             const int buf = step % D_STAGES;
             if (step >= D_STAGES) tma::mbar_wait(bar_empty + 8u * (uint32_t) buf, (uint32_t) ((step / D_STAGES - 1) & 1));
             // S tile
+            if (!XMAT && a.x_t) {
+                // blocks along the rows of X: thread -> (column k of the step, 4-row block); element (i, k) is lane
+                // (u0 + i0 + i) & 3 of block (v0 + k) * R + (u0 + i0 + i) / 4, u0 % 4 == 0 (checked by the launcher)
+                const int kl = tid & (DK - 1), rb0 = tid / DK;
+#pragma unroll 2
+                for (int rr = 0; rr < P_GR; ++rr) {
+                    const int rb = rb0 + (WS_PROD / DK) * rr;
+                    const uint64_t o = (uint64_t) ((a.v0 + (int64_t) (s_begin + step) * DK + kl) * a.R + a.ublk0 + (i0 >> 2) + rb);
+                    const uint64_t lo = seed_lo + o;
+                    const uint64_t hi = seed_hi + (lo < seed_lo ? 1ull : 0ull);
+                    const Ctr128 cc{(uint32_t) lo, (uint32_t) (lo >> 32), (uint32_t) hi, (uint32_t) (hi >> 32)};
+                    const float4 f = transform4<GAUSS>(philox4x32_10(cc, a.key), logtab);
+                    double* dst = Xs + ((size_t) buf * DM + 4 * rb) * DLD + kl;
+                    dst[0] = finish_sample<double, GAUSS>(f.x);
+                    dst[DLD] = finish_sample<double, GAUSS>(f.y);
+                    dst[2 * DLD] = finish_sample<double, GAUSS>(f.z);
+                    dst[3 * DLD] = finish_sample<double, GAUSS>(f.w);
+                }
+            } else
 #pragma unroll 2
             for (int rr = 0; rr < P_GR; ++rr) {
                 const int row = xr + (WS_PROD / D_CPR) * rr;
@@ -298,9 +318,12 @@ __global__ void __launch_bounds__(256) splitk_reduce_f64_kernel(const double* __
 
 int launch_dense_dmma_f64(const DenseProblem<double>& p, cudaStream_t st) {
     const bool xmat = p.S_buff != nullptr;
-    if (xmat && (get_option("dense_path") == 4 || get_option("dmma_uniform_warps") != 0)) return -1;
+    if (xmat && get_option("dense_path") == 4) return -1;
     if (!xmat && p.family == 'G' && !p.gen.logtab) return -1;
-    if (!(p.uk == 1 && p.vi == 1)) return -1;                 // Philox blocks (rows of a materialised operator) must run along K
+    // Philox blocks (rows of a materialised operator) along K, or -- generated operators only -- along the rows of X
+    // (Axis::Short operators and transposed uses, dense_skops.hh:187-199) when the window starts on a block boundary
+    const bool x_t = (p.ui == 1 && p.vk == 1);
+    if (!(p.uk == 1 && p.vi == 1) && !(x_t && !xmat && (p.u0 & 3) == 0)) return -1;
     // Y K-contiguous, or Q-contiguous (left sketch of RowMajor data, right sketch of ColMajor data)
     const bool y_mn = (p.yrs != 1);
     if (y_mn && p.ycs != 1) return -1;
@@ -335,7 +358,8 @@ int launch_dense_dmma_f64(const DenseProblem<double>& p, cudaStream_t st) {
     DmmaArgs a;
     a.ctr = p.gen.ctr; a.key = p.gen.key; a.R = p.gen.R; a.logtab = p.gen.logtab;
     a.v0 = p.v0;
-    a.kshift = (int) (p.u0 & 3);
+    a.kshift = x_t ? 0 : (int) (p.u0 & 3);
+    a.x_t = x_t ? 1 : 0;
     a.ublk0 = p.u0 >> 2;
     a.P = p.P; a.Q = p.Q; a.K = p.K;
     a.steps_total = (int) steps; a.splits = splits;

@@ -393,3 +393,52 @@ def test_example_sparse_low_rank_qb_recovers_planted_vectors():
         x = np.random.default_rng(0).standard_normal(n)
         assert np.linalg.norm(M @ x - Qm @ (Bm @ x)) < 1e-3 * np.linalg.norm(M @ x)
     torch.cuda.synchronize()
+
+
+# ------------------------------------------------------------------------------ Axis::Short operators on tensor cores
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+def test_short_axis_operators_on_tensor_cores_vs_oracle(gpu, port, dt):
+    """Dense operators whose Philox blocks run along the ROWS of op(S) -- Axis::Short distributions and transposed uses
+    of tall Axis::Long ones (the reference's case table, dense_skops.hh:187-199) -- take the tcgen05 / DMMA kernels too
+    (round 1 sent them to the SIMT kernel). Ragged tiles in all three dimensions, both families, alpha/beta, windows that
+    start on a Philox block boundary (tensor cores) and one that does not (generic kernel), left and right sketches,
+    K- and Q-contiguous data; against the oracle, with the launch counter proving which kernel ran."""
+    import randblas_b200 as rb
+    rng = np.random.default_rng(21)
+    ctr, key = ol.state_from_u64(1997)
+    tol = 1e-5 if dt == np.float32 else 1e-12
+    # (layout, opS, d, n, m, D_rows, D_cols, axis, ro, co, family, alpha, beta, expect tensor cores)
+    cases = [("C", "N", 200, 300, 5003, 212, 6000, "S", 4, 6, "G", 0.5, -1.5, True),
+             ("C", "N", 130, 70, 2500, 140, 9000, "S", 8, 4001, "U", -2.0, 1.0, True),
+             ("R", "N", 256, 130, 1031, 256, 1031, "S", 0, 0, "U", 1.0, 0.0, True),
+             ("C", "T", 200, 90, 3000, 3100, 204, "S", 7, 0, "G", 1.0, 0.25, True),      # tall + Short, transposed use
+             ("C", "N", 200, 300, 5003, 212, 6000, "S", 3, 6, "G", 0.5, -1.5, False)]    # window off the block boundary
+    for (lay, opS, d, n, m, Dr, Dc, ax, ro, co, fam, alpha, beta, tc) in cases:
+        pad = 4 if dt == np.float32 else 2
+        inner = m if lay == "C" else n
+        lda = inner + (pad - inner % pad) % pad
+        A = rng.standard_normal((n if lay == "C" else m) * lda).astype(dt)
+        ldb = (d if lay == "C" else n) + 1
+        B0 = rng.standard_normal((n if lay == "C" else d) * ldb).astype(dt)
+        B1, B2 = B0.copy(), B0.copy()
+        before = rb.counter("tensor_core_launches")
+        gpu.lskge3(lay, opS, "N", d, n, m, dt(alpha), (Dr, Dc, fam, ax), ctr, key, ro, co, A, lda, dt(beta), B1, ldb)
+        ran_tc = rb.counter("tensor_core_launches") == before + 1
+        assert ran_tc == tc, (lay, opS, d, n, m, ax, ro, co, ran_tc)
+        port.lskge3(lay, opS, "N", d, n, m, dt(alpha), (Dr, Dc, fam, ax), ctr, key, ro, co, A, lda, dt(beta), B2, ldb)
+        assert relerr(B1, B2) < tol, ((lay, opS, d, n, m, ax, ro, co, fam), relerr(B1, B2))
+    # right sketch: B(m x d) = A(m x n) S(n x d) with a tall Axis::Short operator (RowMajor natural layout)
+    mm, dd, nn = 1500, 100, 977
+    for lay in "CR":
+        inner = mm if lay == "C" else nn
+        pad = 4 if dt == np.float32 else 2
+        lda = inner + (pad - inner % pad) % pad
+        A = rng.standard_normal((nn if lay == "C" else mm) * lda).astype(dt)
+        ldb = (mm if lay == "C" else dd) + 3
+        B0 = rng.standard_normal((dd if lay == "C" else mm) * ldb).astype(dt)
+        B1, B2 = B0.copy(), B0.copy()
+        before = rb.counter("tensor_core_launches")
+        gpu.rskge3(lay, "N", "T", mm, dd, nn, dt(-0.5), A, lda, (120, 1000, "G", "S"), ctr, key, 4, 8, dt(2.0), B1, ldb)
+        assert rb.counter("tensor_core_launches") == before + 1, ("right", lay)
+        port.rskge3(lay, "N", "T", mm, dd, nn, dt(-0.5), A, lda, (120, 1000, "G", "S"), ctr, key, 4, 8, dt(2.0), B2, ldb)
+        assert relerr(B1, B2) < tol, (("right", lay), relerr(B1, B2))

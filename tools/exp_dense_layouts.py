@@ -39,6 +39,18 @@ def main():
         St = rb.DenseSkOp(rb.DenseDist(m, d, rb.ScalarDist.Uniform), rb.RNGState(1997), dt)
         t = timeit(lambda: rb.sketch_general("C", "N", "N", n, d, m, 1.0, A, n, St, 0, 0, 0.0, B, n))
         print(f"{np.dtype(dt).name} right ColMajor A(n x m) * S(m x d) (Q-contiguous): {t:.3f} ms, {flops / t / 1e9:.1f} TFLOP/s", flush=True)
+        # Axis::Short operator: Philox blocks run along the rows of S (round 2: tensor cores; round 1: generic SIMT kernel)
+        Ss = rb.DenseSkOp(rb.DenseDist(d, m, rb.ScalarDist.Uniform, rb.Axis.Short), rb.RNGState(1997), dt)
+        before = rb.counter("tensor_core_launches")
+        t = timeit(lambda: rb.sketch_general("C", "N", "N", d, n, m, 1.0, Ss, 0, 0, A, m, 0.0, B, d))
+        print(f"{np.dtype(dt).name} left ColMajor, Axis::Short operator: {t:.3f} ms, {flops / t / 1e9:.1f} TFLOP/s "
+              f"(tensor-core launches {rb.counter('tensor_core_launches') - before})", flush=True)
+        Sg = rb.DenseSkOp(rb.DenseDist(d, m, rb.ScalarDist.Gaussian, rb.Axis.Short), rb.RNGState(1997), dt)
+        t = timeit(lambda: rb.sketch_general("C", "N", "N", d, n, m, 1.0, Sg, 0, 0, A, m, 0.0, B, d))
+        print(f"{np.dtype(dt).name} left ColMajor, Axis::Short Gaussian operator: {t:.3f} ms, {flops / t / 1e9:.1f} TFLOP/s", flush=True)
+        rb.set_option("dense_path", 1)
+        t = timeit(lambda: rb.sketch_general("C", "N", "N", d, n, m, 1.0, Ss, 0, 0, A, m, 0.0, B, d), reps=2)
+        print(f"{np.dtype(dt).name} left ColMajor, Axis::Short operator, generic SIMT kernel: {t:.3f} ms, {flops / t / 1e9:.1f} TFLOP/s", flush=True)
         rb.set_option("dense_path", 3 if dt == np.float32 else 1)
         t = timeit(lambda: rb.sketch_general("R", "N", "N", d, n, m, 1.0, S, 0, 0, A, n, 0.0, B, n), reps=2)
         print(f"{np.dtype(dt).name} left RowMajor, generic SIMT kernel: {t:.3f} ms, {flops / t / 1e9:.1f} TFLOP/s", flush=True)
