@@ -183,6 +183,24 @@ __device__ __forceinline__ void mma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 
+// ---- CTA pair (cta_group::2): the two SMs of a TPC execute ONE M = 256 MMA; each holds its 128 rows of X and of the
+// accumulator and HALF of the Y tile (128 of the 256 columns), so per SM and K step the tensor core reads half the Y
+// bytes, TMA writes half and the generators split half (shared-memory port: 176 KB per step instead of 272).
+constexpr uint32_t IDESC_TF32_PAIR = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t) (BN >> 3) << 17) | ((uint32_t) ((2 * BM) >> 4) << 24);
+__device__ __forceinline__ void mma_tf32_pair(uint32_t d_tmem, uint64_t da, uint64_t db, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(da), "l"(db), "r"(IDESC_TF32_PAIR), "r"(accumulate)
+        : "memory");
+}
+// commit of the pair's MMAs, arriving on the barrier at this offset in BOTH CTAs
+__device__ __forceinline__ void mma_commit_group2(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+                 "h"((uint16_t) 3)
+                 : "memory");
+}
+
 // the same commit, arriving on the barrier at this offset in both CTAs of a 2-CTA cluster
 __device__ __forceinline__ void mma_commit_pair(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
@@ -224,9 +242,18 @@ __device__ __forceinline__ float lo_trunc(float y) { return __fsub_rn(y, __uint_
 // Philox blocks per thread instead of two, and two step times to finish them), so tiles of two consecutive K steps are
 // being generated at the same time. The generators are latency-bound, not issue-bound (see the cluster note above);
 // this doubles the independent work in flight per scheduler. K-contiguous data, generated operator, no cluster.
-template <bool GAUSS, bool XMAT, int CL = 1, bool HALF = false>
+// PAIR: cta_group::2. The two CTAs of a cluster (1, 2, 1) own two consecutive ROW tiles of C and the same column tile;
+// CTA 0 (the leader) issues every MMA for both, each CTA generates its own X tile, loads and splits its half of Y,
+// and signals the leader's `ready` barrier; the leader's commits free the stages of both CTAs (multicast).
+template <bool GAUSS, bool XMAT, int CL = 1, bool HALF = false, bool PAIR = false>
 __global__ void __launch_bounds__(TC_THREADS, 1) skge3_tc_kernel(const __grid_constant__ CUtensorMap tmY,
                                                                  const __grid_constant__ CUtensorMap tmX, const TcArgs a) {
+    // stage geometry: a CTA of a pair holds half of the Y tile, which leaves room for a third stage in the same 192 KB
+    constexpr int NST = PAIR ? 3 : STAGES;
+    constexpr uint32_t YB = PAIR ? Y_BYTES / 2 : Y_BYTES;       // bytes of Y (and of Y_lo) per stage in this CTA
+    constexpr uint32_t SB = 2 * X_BYTES + 2 * YB;               // bytes per stage
+    static_assert(NST * SB <= RAW_OFFSET, "stages fit the dynamic shared memory the launcher asks for");
+    static_assert(!(PAIR && HALF), "the two-halves generator schedule is tied to two stages");
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(16) double2 logtab[GAUSS ? LOGF_TABLE_ENTRIES : 1];
     const uint32_t raw = smem_u32(smem_raw);
@@ -236,25 +263,33 @@ __global__ void __launch_bounds__(TC_THREADS, 1) skge3_tc_kernel(const __grid_co
 
     const uint32_t bar0 = base + BAR_OFFSET;
     auto bar_full = [&](int s) { return bar0 + 8u * s; };
-    auto bar_ready = [&](int s) { return bar0 + 8u * (STAGES + s); };
-    auto bar_empty = [&](int s) { return bar0 + 8u * (2 * STAGES + s); };
-    const uint32_t bar_accum = bar0 + 8u * (3 * STAGES);
-    const uint32_t bar_raw_full = bar0 + 8u * (3 * STAGES + 1), bar_raw_empty = bar0 + 8u * (3 * STAGES + 2);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + BAR_OFFSET + 8 * (3 * STAGES + 3));
+    auto bar_ready = [&](int s) { return bar0 + 8u * (NST + s); };
+    auto bar_empty = [&](int s) { return bar0 + 8u * (2 * NST + s); };
+    const uint32_t bar_accum = bar0 + 8u * (3 * NST);
+    const uint32_t bar_raw_full = bar0 + 8u * (3 * NST + 1), bar_raw_empty = bar0 + 8u * (3 * NST + 2);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + BAR_OFFSET + 8 * (3 * NST + 3));
 
     if constexpr (GAUSS) load_logf_table(logtab, a.logtab);
     if (warp == 0 && lane == 0) {
-        for (int s = 0; s < STAGES; ++s) {
+        for (int s = 0; s < NST; ++s) {
             mbar_init(bar_full(s), 1);
             // in a cluster the stage this CTA generates itself gets local arrivals only; the other one also the peer's
             uint32_t ready_count = HALF ? GEN_WARPS / 2 : GEN_WARPS;
+            if constexpr (PAIR) {
+                // leader: its generator warps + ONE arrival forwarded by the peer (its otherwise idle MMA warp waits on the
+                // peer's local barrier and signals here: a cluster-scope release per generator warp and step cost a
+                // membar each -- the top stall of the first version of this mode)
+                uint32_t rk;
+                asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rk));
+                if (rk == 0) ready_count += 1;
+            }
             if constexpr (CL > 1) {
                 uint32_t rk;
                 asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rk));
                 if ((uint32_t) s != rk) ready_count = 2 * GEN_WARPS;
             }
             mbar_init(bar_ready(s), ready_count);
-            mbar_init(bar_empty(s), CL);
+            mbar_init(bar_empty(s), PAIR ? 1 : CL);
         }
         mbar_init(bar_accum, 1);
         mbar_init(bar_raw_full, 1);
@@ -263,22 +298,31 @@ __global__ void __launch_bounds__(TC_THREADS, 1) skge3_tc_kernel(const __grid_co
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmY) : "memory");
         if constexpr (XMAT) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmX) : "memory");
     } else if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                     "r"(TMEM_COLS)
-                     : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if constexpr (PAIR) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                         "r"(TMEM_COLS)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                         "r"(TMEM_COLS)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     uint32_t crank = 0;
-    if constexpr (CL > 1) {
+    if constexpr (CL > 1 || PAIR) {
         asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
         cluster_sync();                 // the peer's barriers exist before anything arrives on them
     }
 
-    const int64_t i0 = (int64_t) blockIdx.y * BM, j0 = (int64_t) blockIdx.x * BN;
+    // the CTA pair of a cta_group::2 MMA is two CTAs adjacent in the cluster's (= the grid's) x dimension: in PAIR mode
+    // the grid is (row tiles, column tiles, splits) instead of (column tiles, row tiles, splits)
+    const int64_t i0 = (int64_t) (PAIR ? blockIdx.x : blockIdx.y) * BM, j0 = (int64_t) (PAIR ? blockIdx.y : blockIdx.x) * BN;
     const int split = blockIdx.z;
     const int per = a.steps_total / a.splits, rem = a.steps_total % a.splits;
     const int s_begin = split * per + min(split, rem);
@@ -288,16 +332,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) skge3_tc_kernel(const __grid_co
         if (lane == 0) {
             constexpr int PF = 6;
             if (!a.y_mn) {
-                for (int it = 0; it < min(PF, nsteps); ++it) tma_prefetch_2d(&tmY, (s_begin + it) * BK, (int) j0);
+                const int jy = (int) j0 + (PAIR ? (int) crank * (BN / 2) : 0);      // first column this CTA loads
+                for (int it = 0; it < min(PF, nsteps); ++it) tma_prefetch_2d(&tmY, (s_begin + it) * BK, jy);
                 for (int it = 0; it < nsteps; ++it) {
-                    const int st = it % STAGES;
-                    const uint32_t ph = (it / STAGES) & 1;
-                    if (it + PF < nsteps) tma_prefetch_2d(&tmY, (s_begin + it + PF) * BK, (int) j0);
+                    const int st = it % NST;
+                    const uint32_t ph = (it / NST) & 1;
+                    if (it + PF < nsteps) tma_prefetch_2d(&tmY, (s_begin + it + PF) * BK, jy);
                     mbar_wait(bar_empty(st), ph ^ 1);
+                    if constexpr (PAIR) {
+                        // this CTA's 128 columns of the tile (the tensor map's box is 32 k x 128 columns in this mode)
+                        mbar_arrive_expect_tx(bar_full(st), YB);
+                        tma_load_2d(base + st * SB + 2 * X_BYTES, &tmY, bar_full(st), (s_begin + it) * BK, jy);
+                        continue;
+                    }
                     mbar_arrive_expect_tx(bar_full(st), XMAT ? Y_BYTES + X_BYTES : Y_BYTES);
-                    tma_load_2d(base + st * STAGE_BYTES + 2 * X_BYTES, &tmY, bar_full(st), (s_begin + it) * BK, (int) j0);
+                    tma_load_2d(base + st * SB + 2 * X_BYTES, &tmY, bar_full(st), (s_begin + it) * BK, (int) j0);
                     if constexpr (XMAT)
-                        tma_load_2d(base + st * STAGE_BYTES, &tmX, bar_full(st), (int) a.xk0 + (s_begin + it) * BK,
+                        tma_load_2d(base + st * SB, &tmX, bar_full(st), (int) a.xk0 + (s_begin + it) * BK,
                                     (int) (a.xr0 + i0));
                 }
             } else {
@@ -307,10 +358,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) skge3_tc_kernel(const __grid_co
                     if (j + 2 * PF < 2 * nsteps) tma_prefetch_2d(&tmY, (int) j0, s_begin * BK + (j + 2 * PF) * RAW_K);
                     if constexpr (XMAT) {
                         if ((j & 1) == 0) {                      // the X tile of step j / 2 rides that stage's full barrier
-                            const int it = j >> 1, st = it % STAGES;
-                            mbar_wait(bar_empty(st), (uint32_t) (((it / STAGES) & 1) ^ 1));
+                            const int it = j >> 1, st = it % NST;
+                            mbar_wait(bar_empty(st), (uint32_t) (((it / NST) & 1) ^ 1));
                             mbar_arrive_expect_tx(bar_full(st), X_BYTES);
-                            tma_load_2d(base + st * STAGE_BYTES, &tmX, bar_full(st), (int) a.xk0 + (s_begin + it) * BK,
+                            tma_load_2d(base + st * SB, &tmX, bar_full(st), (int) a.xk0 + (s_begin + it) * BK,
                                         (int) (a.xr0 + i0));
                         }
                     }
@@ -321,16 +372,50 @@ __global__ void __launch_bounds__(TC_THREADS, 1) skge3_tc_kernel(const __grid_co
             }
         }
     } else if (warp == 1) {
+        if constexpr (PAIR) {
+            if (lane == 0 && crank == 0) {
+                for (int it = 0; it < nsteps; ++it) {
+                    const int st = it % NST;
+                    const uint32_t ph = (it / NST) & 1;
+                    // both CTAs' generator warps arrive here after their X tile, their half of Y (TMA, observed through
+                    // their own full barrier) and its low part are in place
+                    mbar_wait_cluster(bar_ready(st), ph);
+                    mbar_wait(bar_full(st), ph);
+                    fence_proxy_async();
+                    tc_fence_after();
+                    const uint32_t xh = base + st * SB, xl = xh + X_BYTES, yh = xl + X_BYTES, yl = yh + YB;
+#pragma unroll
+                    for (int kk = 0; kk < BK / 8; ++kk) {
+                        const uint64_t dxh = smem_desc_sw128(xh + kk * 32), dxl = smem_desc_sw128(xl + kk * 32);
+                        const uint64_t dyh = smem_desc_sw128(yh + kk * 32), dyl = smem_desc_sw128(yl + kk * 32);
+                        const uint32_t acc = (it > 0 || kk > 0) ? 1u : 0u;
+                        mma_tf32_pair(tmem_base + BN, dxl, dyh, acc);
+                        mma_tf32_pair(tmem_base + BN, dxh, dyl, 1u);
+                        mma_tf32_pair(tmem_base, dxh, dyh, acc);
+                    }
+                    mma_commit_group2(bar_empty(st));
+                }
+                mma_commit_group2(bar_accum);
+            } else if (lane == 0) {
+                // peer CTA: forward "my tiles of step it are ready" to the leader with one cluster-scope release
+                const uint32_t leader_ready0 = map_to_cta(bar_ready(0), 0u);
+                for (int it = 0; it < nsteps; ++it) {
+                    const int st = it % NST;
+                    mbar_wait(bar_ready(st), (uint32_t) ((it / NST) & 1));
+                    mbar_arrive_remote(leader_ready0 + 8u * (uint32_t) st);
+                }
+            }
+        } else
         if (lane == 0) {
             for (int it = 0; it < nsteps; ++it) {
-                const int st = it % STAGES;
-                const uint32_t ph = (it / STAGES) & 1;
+                const int st = it % NST;
+                const uint32_t ph = (it / NST) & 1;
                 if constexpr (CL > 1) mbar_wait_cluster(bar_ready(st), ph);
                 else mbar_wait(bar_ready(st), ph);
                 if (XMAT || !a.y_mn) mbar_wait(bar_full(st), ph);
                 if constexpr (CL > 1) fence_proxy_async();     // the peer's generic-proxy stores into this CTA's tiles
                 tc_fence_after();
-                const uint32_t xh = base + st * STAGE_BYTES, xl = xh + X_BYTES, yh = xl + X_BYTES, yl = yh + Y_BYTES;
+                const uint32_t xh = base + st * SB, xl = xh + X_BYTES, yh = xl + X_BYTES, yl = yh + YB;
 #pragma unroll
                 for (int kk = 0; kk < BK / 8; ++kk) {
                     const uint64_t dxh = smem_desc_sw128(xh + kk * 32), dxl = smem_desc_sw128(xl + kk * 32);
@@ -359,7 +444,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) skge3_tc_kernel(const __grid_co
             for (int rr = 0; rr < HB; ++rr)
                 hoff[rr] = (uint64_t) ((a.v0 + i0 + hr + (HT / 8) * rr) * a.R + a.ublk0 + hc) + 8ull * (uint64_t) (s_begin + half);
             const uint32_t hxoff = (uint32_t) hr * 128u + (uint32_t) ((hc ^ (hr & 7)) << 4);
-            uint8_t* stage = smem + half * STAGE_BYTES;        // stage == half, always
+            uint8_t* stage = smem + half * SB;        // stage == half, always
             for (int it = half; it < nsteps; it += 2) {
                 const uint32_t ph = (uint32_t) ((it >> 1) & 1);
                 mbar_wait(bar_empty(half), ph ^ 1);
@@ -386,9 +471,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) skge3_tc_kernel(const __grid_co
                 }
                 mbar_wait(bar_full(half), ph);
                 const uint8_t* ysrc = stage + 2 * X_BYTES;
-                uint8_t* ydst = stage + 2 * X_BYTES + Y_BYTES;
+                uint8_t* ydst = stage + 2 * X_BYTES + YB;
 #pragma unroll
-                for (int q = 0; q < (int) (Y_BYTES / 16) / HT; ++q) {
+                for (int q = 0; q < (int) (YB / 16) / HT; ++q) {
                     const uint32_t o = (uint32_t) (ht + HT * q) * 16u;
                     const float4 y = *reinterpret_cast<const float4*>(ysrc + o);
                     float4 l;
@@ -415,16 +500,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) skge3_tc_kernel(const __grid_co
             off[rr] = (uint64_t) ((a.v0 + i0 + rbase + ROWS_PER_PASS * rr) * a.R + a.ublk0 + c) + 8ull * (uint64_t) s_begin;
         const uint32_t xoff = (uint32_t) rbase * 128u + (uint32_t) ((c ^ (r0 & 7)) << 4);
         for (int it = 0; it < nsteps; ++it) {
-            const int st = it % STAGES;
-            const uint32_t ph = (it / STAGES) & 1;
-            uint8_t* stage = smem + st * STAGE_BYTES;
+            const int st = it % NST;
+            const uint32_t ph = (it / NST) & 1;
+            uint8_t* stage = smem + st * SB;
             mbar_wait(bar_empty(st), ph ^ 1);
             if (a.y_mn) {
                 // transpose the raw Q-contiguous tile into the K-major swizzled Y (the tensor core truncates it to TF32
                 // itself) and Y_lo tiles of this stage, then hand the raw buffer back to the TMA producer
                 const uint8_t* rawt = smem + RAW_OFFSET;
                 uint8_t* yh = stage + 2 * X_BYTES;
-                uint8_t* yl = yh + Y_BYTES;
+                uint8_t* yl = yh + YB;
 #pragma unroll
                 for (int half = 0; half < BK / RAW_K; ++half) {
                     mbar_wait(bar_raw_full, (uint32_t) half);          // raw tile 2 it + half: parity = half
@@ -509,7 +594,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) skge3_tc_kernel(const __grid_co
                 *reinterpret_cast<float4*>(stage + xoff + rr * (ROWS_PER_PASS * 128)) = h;
                 *reinterpret_cast<float4*>(stage + X_BYTES + xoff + rr * (ROWS_PER_PASS * 128)) = l;
                 if constexpr (CL > 1) {
-                    const uint32_t ra = map_to_cta(base + (uint32_t) st * STAGE_BYTES + xoff + rr * (ROWS_PER_PASS * 128), crank ^ 1u);
+                    const uint32_t ra = map_to_cta(base + (uint32_t) st * SB + xoff + rr * (ROWS_PER_PASS * 128), crank ^ 1u);
                     st_cluster_v4(ra, h);
                     st_cluster_v4(ra + X_BYTES, l);
                 }
@@ -519,9 +604,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) skge3_tc_kernel(const __grid_co
             if (!a.y_mn) {
             mbar_wait(bar_full(st), ph);
             const uint8_t* ysrc = stage + 2 * X_BYTES;
-            uint8_t* ydst = stage + 2 * X_BYTES + Y_BYTES;
+            uint8_t* ydst = stage + 2 * X_BYTES + YB;
 #pragma unroll
-            for (int q = 0; q < (int) (Y_BYTES / 16) / (32 * GEN_WARPS); ++q) {
+            for (int q = 0; q < (int) (YB / 16) / (32 * GEN_WARPS); ++q) {
                 const uint32_t o = (uint32_t) (gt + 32 * GEN_WARPS * q) * 16u;
                 const float4 y = *reinterpret_cast<const float4*>(ysrc + o);
                 float4 l;
@@ -529,6 +614,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) skge3_tc_kernel(const __grid_co
                 *reinterpret_cast<float4*>(ydst + o) = l;
             }
             }
+            // PAIR: the tiles were written into THIS CTA's shared memory (the pair's tensor cores read them through the async
+            // proxy), so the shared::cta fence is enough; the all-state-space fence of the CL = 2 mode costs a full membar
             if constexpr (CL > 1) fence_proxy_async_all();
             else fence_proxy_async();
             __syncwarp();
@@ -576,10 +663,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) skge3_tc_kernel(const __grid_co
     }
     tc_fence_before();
     __syncthreads();
-    if constexpr (CL > 1) cluster_sync();   // no CTA leaves while its peer can still arrive on its barriers
+    if constexpr (CL > 1 || PAIR) cluster_sync();   // no CTA leaves while its peer can still arrive on its barriers
     if (warp == 1) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+        if constexpr (PAIR)
+            asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+        else
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
     }
 }
 
@@ -659,7 +749,14 @@ int launch_dense_tc_f32(const DenseProblem<float>& p, cudaStream_t st) {
     // m = 1e5); 2 whenever the tile count is even. It does not pay elsewhere: distributed shared memory moves ~21 B/clk,
     // so shipping the 32 KB (hi, lo) tile costs as much as the MMAs of the step (Uniform: 1.06 -> 1.44 ms).
     const int64_t cl_opt = get_option("tc_cluster");
-    const bool cluster = !xmat && !x_t && (tiles_q % 2 == 0) && (cl_opt == 2 || (cl_opt == 1 && p.family == 'G' && !y_mn));
+    // CTA pairs (cta_group::2, "tc_pair", default on): two consecutive row tiles share the Y tile. Generated operator,
+    // K-contiguous data, an even number of row tiles.
+    const int64_t pair_opt = get_option("tc_pair");
+    // tc_pair: 0 never, 1 (default) where it was measured to pay -- Uniform operators (C1: 1.05 -> 0.98 ms; Gaussian operators
+    // are bound by the generator warps and lose the two-halves / shared-tile schedules: 1.79 -> 1.94 ms), 2 whenever possible
+    const bool pair = !xmat && !y_mn && (tiles_p % 2 == 0) && tiles_q <= 65535 && cl_opt != 2 &&
+                      (pair_opt == 2 || (pair_opt == 1 && p.family == 'U'));
+    const bool cluster = !pair && !xmat && !x_t && (tiles_q % 2 == 0) && (cl_opt == 2 || (cl_opt == 1 && p.family == 'G' && !y_mn));
     // Split K. Two constraints: (1) the tensor core adds into its fp32 accumulator with truncation, a bias that
     // grows linearly with the number of accumulated MMAs (measured: 4.6e-4 relative after 2048 K steps, 1.9e-6
     // after 8), so no partial sum stays in TMEM for more than MAX_CHAIN_STEPS steps; partial sums are added in
@@ -683,7 +780,7 @@ int launch_dense_tc_f32(const DenseProblem<float>& p, cudaStream_t st) {
     CUtensorMap tm;
     const cuuint64_t gdim[2] = {(cuuint64_t) (y_mn ? p.Q : p.K), (cuuint64_t) (y_mn ? p.K : p.Q)};
     const cuuint64_t gstr[1] = {(cuuint64_t) (y_mn ? p.yrs : p.ycs) * 4ull};
-    const cuuint32_t box[2] = {(cuuint32_t) (y_mn ? BN : BK), (cuuint32_t) (y_mn ? RAW_K : BN)};
+    const cuuint32_t box[2] = {(cuuint32_t) (y_mn ? BN : BK), (cuuint32_t) (y_mn ? RAW_K : (pair ? BN / 2 : BN))};
     const cuuint32_t estr[2] = {1, 1};
     CUresult cr = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(p.Y), gdim, gstr, box, estr,
                       CU_TENSOR_MAP_INTERLEAVE_NONE, y_mn ? CU_TENSOR_MAP_SWIZZLE_NONE : CU_TENSOR_MAP_SWIZZLE_128B,
@@ -721,11 +818,11 @@ int launch_dense_tc_f32(const DenseProblem<float>& p, cudaStream_t st) {
         a.W = (float*) workspace(6, (size_t) splits * a.P_pad * a.Q_pad * sizeof(float), st);
         if (!a.W) return fail_cuda(cudaErrorMemoryAllocation, "split-K workspace");
     }
-    static DevOnce attr_done[7];
+    static DevOnce attr_done[9];
     const bool gauss = p.family == 'G';
     // tc_halves: 1 (default) = the generator warps work on two K steps at a time where the kernel supports it
-    const bool halves = !xmat && !cluster && !y_mn && !x_t && get_option("tc_halves") != 0;
-    const int variant = xmat ? 2 : (cluster ? 3 : (halves ? 5 : 0)) + (gauss ? 1 : 0);
+    const bool halves = !xmat && !cluster && !pair && !y_mn && !x_t && get_option("tc_halves") != 0;
+    const int variant = xmat ? 2 : (pair ? 7 : (cluster ? 3 : (halves ? 5 : 0))) + (gauss ? 1 : 0);
     auto set_attr = [&](auto kern) { return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM); };
     if (attr_done[variant].need()) {
         cudaError_t e;
@@ -736,12 +833,27 @@ int launch_dense_tc_f32(const DenseProblem<float>& p, cudaStream_t st) {
             case 3: e = set_attr(skge3_tc_kernel<false, false, 2, false>); break;
             case 4: e = set_attr(skge3_tc_kernel<true, false, 2, false>); break;
             case 5: e = set_attr(skge3_tc_kernel<false, false, 1, true>); break;
-            default: e = set_attr(skge3_tc_kernel<true, false, 1, true>); break;
+            case 6: e = set_attr(skge3_tc_kernel<true, false, 1, true>); break;
+            case 7: e = set_attr(skge3_tc_kernel<false, false, 1, false, true>); break;
+            default: e = set_attr(skge3_tc_kernel<true, false, 1, false, true>); break;
         }
         if (e != cudaSuccess) { cudaGetLastError(); return -1; }
         attr_done[variant].done();
     }
     dim3 grid((unsigned) tiles_q, (unsigned) tiles_p, (unsigned) splits);
+    if (pair) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned) tiles_p, (unsigned) tiles_q, (unsigned) splits);
+        cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = TC_SMEM; cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        cudaError_t e;
+        e = gauss ? cudaLaunchKernelEx(&cfg, skge3_tc_kernel<true, false, 1, false, true>, tm, tmx, a)
+                  : cudaLaunchKernelEx(&cfg, skge3_tc_kernel<false, false, 1, false, true>, tm, tmx, a);
+        if (e != cudaSuccess) return fail_cuda(e, "CTA-pair launch of the tensor-core sketch kernel");
+    } else
     if (xmat) skge3_tc_kernel<false, true, 1, false><<<grid, TC_THREADS, TC_SMEM, st>>>(tm, tmx, a);
     else if (halves) {
         if (gauss) skge3_tc_kernel<true, false, 1, true><<<grid, TC_THREADS, TC_SMEM, st>>>(tm, tmx, a);

@@ -21,6 +21,9 @@ def main():
     what = sys.argv[1]
     reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
     torch.cuda.set_device(0)
+    for kv in os.environ.get("RB_OPTIONS", "").split(","):      # e.g. RB_OPTIONS=tc_pair=0
+        if "=" in kv:
+            rb.set_option(kv.split("=")[0], int(kv.split("=")[1]))
     if what == "fill_gauss_f64":
         rows, cols = 256, 1000000
         D = rb.DenseDist(8192, cols, rb.ScalarDist.Gaussian, rb.Axis.Long)
