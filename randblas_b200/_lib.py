@@ -6,7 +6,8 @@ import ctypes
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "librandblas_b200.so")
+# RANDBLAS_B200_LIB: an alternative build of the same library (kernel experiments); the default is the in-tree build
+LIB_PATH = os.environ.get("RANDBLAS_B200_LIB") or os.path.join(HERE, "librandblas_b200.so")
 
 _lib = None
 
