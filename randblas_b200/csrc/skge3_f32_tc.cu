@@ -341,8 +341,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) skge3_tc_kernel(const __grid_co
                     mbar_wait(bar_empty(st), ph ^ 1);
                     if constexpr (PAIR) {
                         // this CTA's 128 columns of the tile (the tensor map's box is 32 k x 128 columns in this mode)
-                        mbar_arrive_expect_tx(bar_full(st), YB);
+                        mbar_arrive_expect_tx(bar_full(st), XMAT ? YB + X_BYTES : YB);
                         tma_load_2d(base + st * SB + 2 * X_BYTES, &tmY, bar_full(st), (s_begin + it) * BK, jy);
+                        if constexpr (XMAT)         // this CTA's own 128 rows of the materialised operator
+                            tma_load_2d(base + st * SB, &tmX, bar_full(st), (int) a.xk0 + (s_begin + it) * BK, (int) (a.xr0 + i0));
                         continue;
                     }
                     mbar_arrive_expect_tx(bar_full(st), XMAT ? Y_BYTES + X_BYTES : Y_BYTES);
@@ -713,6 +715,38 @@ EncodeTiledFn encode_tiled() {
 
 }  // namespace
 
+// Gaussian operators with several column tiles: every column tile of C regenerates the same 128 x 32 operator tile, and
+// the Box-Muller generator (not the tensor core) bounds the fused kernel (d = n = 1024, m = 1e5: 1.70 ms against 0.97 ms for
+// Uniform). With two or more column tiles it is cheaper to generate each K panel of op(S) ONCE into a scratch buffer with the fill
+// kernel and run the materialised-operator (XMAT) instantiation on it: same operand values and, for a single panel, the
+// same split-K as the fused kernel. The panel (<= 512 MB of scratch) is written and re-read immediately and never becomes a
+// caller-visible S. "tc_materialise": 0 never, 1 (default) auto, 2 always.
+static int dense_tc_f32_via_panel(const DenseProblem<float>& p, bool x_t, cudaStream_t st) {
+    int64_t kp = ((int64_t) 512 << 20) / 4 / (p.P > 0 ? p.P : 1);
+    kp = (kp / 1280) * 1280;                        // whole 40-step chains of 32
+    if (kp < 1280) kp = 1280;
+    if (kp > p.K) kp = (p.K + 3) / 4 * 4;
+    const int64_t ld = kp;
+    float* panel = (float*) workspace(5, (size_t) p.P * (size_t) ld * sizeof(float), st);
+    if (!panel) return fail_cuda(cudaErrorMemoryAllocation, "operator panel workspace");
+    for (int64_t k0 = 0; k0 < p.K; k0 += kp) {
+        const int64_t kc = (p.K - k0 < kp) ? p.K - k0 : kp;
+        int rc;
+        if (!x_t) rc = launch_fill_dense<float>(p.gen, p.family, p.v0, p.P, p.u0 + k0, kc, panel, ld, 1, st);
+        else rc = launch_fill_dense<float>(p.gen, p.family, p.v0 + k0, kc, p.u0, p.P, panel, 1, ld, st);
+        if (rc) return rc;
+        DenseProblem<float> q = p;
+        q.S_buff = panel; q.S_ld = ld;
+        q.v0 = 0; q.u0 = 0; q.vi = 1; q.ui = 0; q.vk = 0; q.uk = 1;
+        q.K = kc;
+        q.Y = p.Y + k0 * p.yrs;
+        q.beta = (k0 == 0) ? p.beta : 1.0f;
+        rc = launch_dense_tc_f32(q, st);
+        if (rc) return rc < 0 ? fail("operator panel: the tensor-core kernel refused its own panel") : rc;
+    }
+    return 0;
+}
+
 int launch_dense_tc_f32(const DenseProblem<float>& p, cudaStream_t st) {
     // shapes / layouts this kernel takes; everything else goes to the generic kernel
     const bool xmat = p.S_buff != nullptr;
@@ -742,6 +776,11 @@ int launch_dense_tc_f32(const DenseProblem<float>& p, cudaStream_t st) {
 
     const int64_t tiles_p = (p.P + BM - 1) / BM, tiles_q = (p.Q + BN - 1) / BN;
     if (tiles_p > 65535 || tiles_q > 0x7fffffff) return -1;
+    {
+        const int64_t mat_opt = get_option("tc_materialise");
+        if (!xmat && p.family == 'G' && (mat_opt == 2 || (mat_opt == 1 && tiles_q >= 2)) && p.K >= 64)
+            return dense_tc_f32_via_panel(p, x_t, st);
+    }
     const int kshift = x_t ? 0 : (int) (p.u0 & 3);
     const int64_t steps = (p.K + BK - 1) / BK;
     // Pairs of column tiles share the generated operator tile through a 2-CTA cluster. tc_cluster: 0 never; 1 (default)
@@ -754,8 +793,8 @@ int launch_dense_tc_f32(const DenseProblem<float>& p, cudaStream_t st) {
     const int64_t pair_opt = get_option("tc_pair");
     // tc_pair: 0 never, 1 (default) where it was measured to pay -- Uniform operators (C1: 1.05 -> 0.98 ms; Gaussian operators
     // are bound by the generator warps and lose the two-halves / shared-tile schedules: 1.79 -> 1.94 ms), 2 whenever possible
-    const bool pair = !xmat && !y_mn && (tiles_p % 2 == 0) && tiles_q <= 65535 && cl_opt != 2 &&
-                      (pair_opt == 2 || (pair_opt == 1 && p.family == 'U'));
+    const bool pair = !y_mn && (tiles_p % 2 == 0) && tiles_q <= 65535 && cl_opt != 2 &&
+                      (pair_opt == 2 || (pair_opt == 1 && (xmat || p.family == 'U')));
     const bool cluster = !pair && !xmat && !x_t && (tiles_q % 2 == 0) && (cl_opt == 2 || (cl_opt == 1 && p.family == 'G' && !y_mn));
     // Split K. Two constraints: (1) the tensor core adds into its fp32 accumulator with truncation, a bias that
     // grows linearly with the number of accumulated MMAs (measured: 4.6e-4 relative after 2048 K steps, 1.9e-6
@@ -818,11 +857,11 @@ int launch_dense_tc_f32(const DenseProblem<float>& p, cudaStream_t st) {
         a.W = (float*) workspace(6, (size_t) splits * a.P_pad * a.Q_pad * sizeof(float), st);
         if (!a.W) return fail_cuda(cudaErrorMemoryAllocation, "split-K workspace");
     }
-    static DevOnce attr_done[9];
+    static DevOnce attr_done[10];
     const bool gauss = p.family == 'G';
     // tc_halves: 1 (default) = the generator warps work on two K steps at a time where the kernel supports it
     const bool halves = !xmat && !cluster && !pair && !y_mn && !x_t && get_option("tc_halves") != 0;
-    const int variant = xmat ? 2 : (pair ? 7 : (cluster ? 3 : (halves ? 5 : 0))) + (gauss ? 1 : 0);
+    const int variant = xmat ? (pair ? 9 : 2) : (pair ? 7 : (cluster ? 3 : (halves ? 5 : 0))) + (gauss ? 1 : 0);
     auto set_attr = [&](auto kern) { return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM); };
     if (attr_done[variant].need()) {
         cudaError_t e;
@@ -835,7 +874,8 @@ int launch_dense_tc_f32(const DenseProblem<float>& p, cudaStream_t st) {
             case 5: e = set_attr(skge3_tc_kernel<false, false, 1, true>); break;
             case 6: e = set_attr(skge3_tc_kernel<true, false, 1, true>); break;
             case 7: e = set_attr(skge3_tc_kernel<false, false, 1, false, true>); break;
-            default: e = set_attr(skge3_tc_kernel<true, false, 1, false, true>); break;
+            case 8: e = set_attr(skge3_tc_kernel<true, false, 1, false, true>); break;
+            default: e = set_attr(skge3_tc_kernel<false, true, 1, false, true>); break;
         }
         if (e != cudaSuccess) { cudaGetLastError(); return -1; }
         attr_done[variant].done();
@@ -850,8 +890,9 @@ int launch_dense_tc_f32(const DenseProblem<float>& p, cudaStream_t st) {
         at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
         cfg.attrs = at; cfg.numAttrs = 1;
         cudaError_t e;
-        e = gauss ? cudaLaunchKernelEx(&cfg, skge3_tc_kernel<true, false, 1, false, true>, tm, tmx, a)
-                  : cudaLaunchKernelEx(&cfg, skge3_tc_kernel<false, false, 1, false, true>, tm, tmx, a);
+        if (xmat) e = cudaLaunchKernelEx(&cfg, skge3_tc_kernel<false, true, 1, false, true>, tm, tmx, a);
+        else e = gauss ? cudaLaunchKernelEx(&cfg, skge3_tc_kernel<true, false, 1, false, true>, tm, tmx, a)
+                       : cudaLaunchKernelEx(&cfg, skge3_tc_kernel<false, false, 1, false, true>, tm, tmx, a);
         if (e != cudaSuccess) return fail_cuda(e, "CTA-pair launch of the tensor-core sketch kernel");
     } else
     if (xmat) skge3_tc_kernel<false, true, 1, false><<<grid, TC_THREADS, TC_SMEM, st>>>(tm, tmx, a);
