@@ -316,6 +316,36 @@ __global__ void __launch_bounds__(256) splitk_reduce_f64_kernel(const double* __
 
 }  // namespace
 
+// Gaussian operators: the producer warps' Box-Muller work shares issue slots with the DMMA stream (fused 0.84 of cuBLAS
+// DGEMM against 0.89 with a materialised operator). "dmma_materialise" = 1 generates each K panel of op(S) once into a
+// scratch buffer (<= 512 MB) with the fill kernel and runs the materialised-operator instantiation on it; same operand
+// values, panel sums added in order (beta = 1 after the first panel). 0 (default) = fused, see DESIGN.md for the measurement.
+static int dense_dmma_f64_via_panel(const DenseProblem<double>& p, bool x_t, cudaStream_t st) {
+    int64_t kp = ((int64_t) 512 << 20) / 8 / (p.P > 0 ? p.P : 1);
+    kp = (kp / 1024) * 1024;
+    if (kp < 1024) kp = 1024;
+    if (kp > p.K) kp = (p.K + 1) / 2 * 2;
+    const int64_t ld = kp;
+    double* panel = (double*) workspace(5, (size_t) p.P * (size_t) ld * sizeof(double), st);
+    if (!panel) return fail_cuda(cudaErrorMemoryAllocation, "operator panel workspace");
+    for (int64_t k0 = 0; k0 < p.K; k0 += kp) {
+        const int64_t kc = (p.K - k0 < kp) ? p.K - k0 : kp;
+        int rc;
+        if (!x_t) rc = launch_fill_dense<double>(p.gen, p.family, p.v0, p.P, p.u0 + k0, kc, panel, ld, 1, st);
+        else rc = launch_fill_dense<double>(p.gen, p.family, p.v0 + k0, kc, p.u0, p.P, panel, 1, ld, st);
+        if (rc) return rc;
+        DenseProblem<double> q = p;
+        q.S_buff = panel; q.S_ld = ld;
+        q.v0 = 0; q.u0 = 0; q.vi = 1; q.ui = 0; q.vk = 0; q.uk = 1;
+        q.K = kc;
+        q.Y = p.Y + k0 * p.yrs;
+        q.beta = (k0 == 0) ? p.beta : 1.0;
+        rc = launch_dense_dmma_f64(q, st);
+        if (rc) return rc < 0 ? fail("operator panel: the DMMA kernel refused its own panel") : rc;
+    }
+    return 0;
+}
+
 int launch_dense_dmma_f64(const DenseProblem<double>& p, cudaStream_t st) {
     const bool xmat = p.S_buff != nullptr;
     if (xmat && get_option("dense_path") == 4) return -1;
@@ -337,6 +367,8 @@ int launch_dense_dmma_f64(const DenseProblem<double>& p, cudaStream_t st) {
     if (tiles_p > 65535 || tiles_q > 0x7fffffff) return -1;
     const int64_t steps = (p.K + DK - 1) / DK;
     if (steps > 0x7fffffff) return -1;
+    if (!xmat && p.family == 'G' && get_option("dmma_materialise") != 0 && p.K >= 1024)
+        return dense_dmma_f64_via_panel(p, x_t, st);
     const int64_t tiles = tiles_p * tiles_q;
     const int sms = sm_count();
     // split K only to fill the SMs: pick the split count (<= 16) with the best wave efficiency
