@@ -354,10 +354,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) skge3_tc_kernel(const __grid_co
                                     (int) (a.xr0 + i0));
                 }
             } else {
-                // tensor map (Q, K), box 256 q x RAW_K k, no swizzle: one raw tile in flight
-                for (int j = 0; j < min(2 * PF, 2 * nsteps); ++j) tma_prefetch_2d(&tmY, (int) j0, s_begin * BK + j * RAW_K);
+                // tensor map (Q, K), box 256 q (128 for a CTA of a pair) x RAW_K k, no swizzle: one raw tile in flight
+                const int jy = (int) j0 + (PAIR ? (int) crank * (BN / 2) : 0);
+                constexpr uint32_t RAWB = PAIR ? RAW_BYTES / 2 : RAW_BYTES;
+                for (int j = 0; j < min(2 * PF, 2 * nsteps); ++j) tma_prefetch_2d(&tmY, jy, s_begin * BK + j * RAW_K);
                 for (int j = 0; j < 2 * nsteps; ++j) {          // raw tile j = half (j & 1) of step j / 2
-                    if (j + 2 * PF < 2 * nsteps) tma_prefetch_2d(&tmY, (int) j0, s_begin * BK + (j + 2 * PF) * RAW_K);
+                    if (j + 2 * PF < 2 * nsteps) tma_prefetch_2d(&tmY, jy, s_begin * BK + (j + 2 * PF) * RAW_K);
                     if constexpr (XMAT) {
                         if ((j & 1) == 0) {                      // the X tile of step j / 2 rides that stage's full barrier
                             const int it = j >> 1, st = it % NST;
@@ -368,8 +370,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) skge3_tc_kernel(const __grid_co
                         }
                     }
                     mbar_wait(bar_raw_empty, (uint32_t) ((j & 1) ^ 1));
-                    mbar_arrive_expect_tx(bar_raw_full, RAW_BYTES);
-                    tma_load_2d(base + RAW_OFFSET, &tmY, bar_raw_full, (int) j0, s_begin * BK + j * RAW_K);
+                    mbar_arrive_expect_tx(bar_raw_full, RAWB);
+                    tma_load_2d(base + RAW_OFFSET, &tmY, bar_raw_full, jy, s_begin * BK + j * RAW_K);
                 }
             }
         }
@@ -382,7 +384,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) skge3_tc_kernel(const __grid_co
                     // both CTAs' generator warps arrive here after their X tile, their half of Y (TMA, observed through
                     // their own full barrier) and its low part are in place
                     mbar_wait_cluster(bar_ready(st), ph);
-                    mbar_wait(bar_full(st), ph);
+                    if (XMAT || !a.y_mn) mbar_wait(bar_full(st), ph);
                     fence_proxy_async();
                     tc_fence_after();
                     const uint32_t xh = base + st * SB, xl = xh + X_BYTES, yh = xl + X_BYTES, yl = yh + YB;
@@ -516,12 +518,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) skge3_tc_kernel(const __grid_co
                 for (int half = 0; half < BK / RAW_K; ++half) {
                     mbar_wait(bar_raw_full, (uint32_t) half);          // raw tile 2 it + half: parity = half
 #pragma unroll
-                    for (int q4 = 0; q4 < (BN * RAW_K / 4) / (32 * GEN_WARPS); ++q4) {
+                    constexpr int BNL = PAIR ? BN / 2 : BN;               // columns of the tile held by this CTA
+                    for (int q4 = 0; q4 < (BNL * RAW_K / 4) / (32 * GEN_WARPS); ++q4) {
                         const int ch = gt + 32 * GEN_WARPS * q4;
-                        const int qq = ch & (BN - 1), kl = ch / BN;        // column of the tile, 4-deep k chunk of this half
-                        const float* src = reinterpret_cast<const float*>(rawt) + (4 * kl) * BN + qq;
+                        const int qq = ch & (BNL - 1), kl = ch / BNL;      // column of the tile, 4-deep k chunk of this half
+                        const float* src = reinterpret_cast<const float*>(rawt) + (4 * kl) * BNL + qq;
                         float4 y;
-                        y.x = src[0]; y.y = src[BN]; y.z = src[2 * BN]; y.w = src[3 * BN];
+                        y.x = src[0]; y.y = src[BNL]; y.z = src[2 * BNL]; y.w = src[3 * BNL];
                         float4 l;
                         l.x = lo_trunc(y.x); l.y = lo_trunc(y.y); l.z = lo_trunc(y.z); l.w = lo_trunc(y.w);
                         const int kc = kl + half * (RAW_K / 4);
@@ -793,7 +796,7 @@ int launch_dense_tc_f32(const DenseProblem<float>& p, cudaStream_t st) {
     const int64_t pair_opt = get_option("tc_pair");
     // tc_pair: 0 never, 1 (default) where it was measured to pay -- Uniform operators (C1: 1.05 -> 0.98 ms; Gaussian operators
     // are bound by the generator warps and lose the two-halves / shared-tile schedules: 1.79 -> 1.94 ms), 2 whenever possible
-    const bool pair = !y_mn && (tiles_p % 2 == 0) && tiles_q <= 65535 && cl_opt != 2 &&
+    const bool pair = (tiles_p % 2 == 0) && tiles_q <= 65535 && cl_opt != 2 &&
                       (pair_opt == 2 || (pair_opt == 1 && (xmat || p.family == 'U')));
     const bool cluster = !pair && !xmat && !x_t && (tiles_q % 2 == 0) && (cl_opt == 2 || (cl_opt == 1 && p.family == 'G' && !y_mn));
     // Split K. Two constraints: (1) the tensor core adds into its fp32 accumulator with truncation, a bias that
@@ -819,7 +822,7 @@ int launch_dense_tc_f32(const DenseProblem<float>& p, cudaStream_t st) {
     CUtensorMap tm;
     const cuuint64_t gdim[2] = {(cuuint64_t) (y_mn ? p.Q : p.K), (cuuint64_t) (y_mn ? p.K : p.Q)};
     const cuuint64_t gstr[1] = {(cuuint64_t) (y_mn ? p.yrs : p.ycs) * 4ull};
-    const cuuint32_t box[2] = {(cuuint32_t) (y_mn ? BN : BK), (cuuint32_t) (y_mn ? RAW_K : (pair ? BN / 2 : BN))};
+    const cuuint32_t box[2] = {(cuuint32_t) (y_mn ? (pair ? BN / 2 : BN) : BK), (cuuint32_t) (y_mn ? RAW_K : (pair ? BN / 2 : BN))};
     const cuuint32_t estr[2] = {1, 1};
     CUresult cr = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(p.Y), gdim, gstr, box, estr,
                       CU_TENSOR_MAP_INTERLEAVE_NONE, y_mn ? CU_TENSOR_MAP_SWIZZLE_NONE : CU_TENSOR_MAP_SWIZZLE_128B,
