@@ -796,7 +796,8 @@ int launch_dense_tc_f32(const DenseProblem<float>& p, cudaStream_t st) {
     const int64_t pair_opt = get_option("tc_pair");
     // tc_pair: 0 never, 1 (default) where it was measured to pay -- Uniform operators (C1: 1.05 -> 0.98 ms; Gaussian operators
     // are bound by the generator warps and lose the two-halves / shared-tile schedules: 1.79 -> 1.94 ms), 2 whenever possible
-    const bool pair = (tiles_p % 2 == 0) && tiles_q <= 65535 && cl_opt != 2 &&
+    static thread_local bool pair_refused = false;     // a refused cluster launch (e.g. a partitioned GPU) falls back once and for all
+    const bool pair = !pair_refused && (tiles_p % 2 == 0) && tiles_q <= 65535 && cl_opt != 2 &&
                       (pair_opt == 2 || (pair_opt == 1 && (xmat || p.family == 'U')));
     const bool cluster = !pair && !xmat && !x_t && (tiles_q % 2 == 0) && (cl_opt == 2 || (cl_opt == 1 && p.family == 'G' && !y_mn));
     // Split K. Two constraints: (1) the tensor core adds into its fp32 accumulator with truncation, a bias that
@@ -896,7 +897,11 @@ int launch_dense_tc_f32(const DenseProblem<float>& p, cudaStream_t st) {
         if (xmat) e = cudaLaunchKernelEx(&cfg, skge3_tc_kernel<false, true, 1, false, true>, tm, tmx, a);
         else e = gauss ? cudaLaunchKernelEx(&cfg, skge3_tc_kernel<true, false, 1, false, true>, tm, tmx, a)
                        : cudaLaunchKernelEx(&cfg, skge3_tc_kernel<false, false, 1, false, true>, tm, tmx, a);
-        if (e != cudaSuccess) return fail_cuda(e, "CTA-pair launch of the tensor-core sketch kernel");
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            pair_refused = true;
+            return launch_dense_tc_f32(p, st);          // same problem, single-CTA kernels
+        }
     } else
     if (xmat) skge3_tc_kernel<false, true, 1, false><<<grid, TC_THREADS, TC_SMEM, st>>>(tm, tmx, a);
     else if (halves) {
