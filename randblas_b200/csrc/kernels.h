@@ -88,7 +88,8 @@ template <typename T>
 int launch_saso_apply(const SasoProblem<T>& p, cudaStream_t st);
 // fast path (saso_binned.cu): one-time binning pre-pass + decoupled TMA pipeline. 0 = done, -1 = shape/layout not taken
 // (the caller uses the atomic kernel), >0 error. C already beta-scaled.
-int launch_saso_binned_f32(const SasoProblem<float>& p, cudaStream_t st);
+template <typename T>
+int launch_saso_binned(const SasoProblem<T>& p, cudaStream_t st);
 
 // generic COO x dense: C(P x Q) += alpha * X * Y with X given by triplets inside a window
 template <typename T>

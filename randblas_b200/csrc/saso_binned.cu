@@ -32,7 +32,8 @@ namespace rb {
 namespace {
 
 constexpr int BN_THREADS = 1024;
-constexpr int BN_W = 32;                        // columns of C per CTA = one 128-byte row of Y per 8-lane group
+constexpr int BN_W = 32;                        // 4-byte words per row slice: a CTA owns 128 bytes of every row of C, i.e.
+                                                // 32 float or 16 double columns (one 128-byte row of Y per 8-lane group)
 constexpr int BN_RPG = 8;                       // rows of C per 8-lane group
 constexpr int BN_PT = (BN_THREADS / 8) * BN_RPG;   // 1024 rows of C per CTA
 constexpr int BN_KMAX = 704;                    // rows of Y per chunk
@@ -191,6 +192,7 @@ __global__ void __launch_bounds__(BIN_THREADS) saso_bin_kernel(const BinArgs a) 
     }
 }
 
+template <typename T>
 struct BinnedArgs {
     const uint32_t* sorted;
     const uint16_t* offs16;
@@ -199,14 +201,38 @@ struct BinnedArgs {
     int Ppad;
     int G;               // CTAs that share one tile of C (they split the chunks)
     int64_t P, Q;
-    float alpha;
-    float* C;
+    T alpha;
+    T* C;
     int64_t crs;
     int c_vec4;          // rows of C are 16-byte aligned
 };
 
+// 16 bytes of a Y row and of the accumulators of one row of C: 4 floats or 2 doubles per lane
+template <typename T> struct Vec16;
+template <> struct Vec16<float> {
+    static constexpr int N = 4;
+    float v[4];
+    __device__ __forceinline__ void load(uint32_t addr) {
+        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "r"(addr));
+    }
+};
+template <> struct Vec16<double> {
+    static constexpr int N = 2;
+    double v[2];
+    __device__ __forceinline__ void load(uint32_t addr) {
+        asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(v[0]), "=d"(v[1]) : "r"(addr));
+    }
+};
+// +-1 as T from the sign bit of a list word
+__device__ __forceinline__ double word_sign_f64(uint32_t p) {
+    return __hiloint2double((int) ((p & 0x80000000u) | 0x3ff00000u), 0);
+}
+
+template <typename T>
 __global__ void __launch_bounds__(BN_THREADS, 1) saso_binned_kernel(const __grid_constant__ CUtensorMap tmY,
-                                                                    const BinnedArgs a) {
+                                                                    const BinnedArgs<T> a) {
+    constexpr int CW = BN_W * 4 / (int) sizeof(T);     // columns of C per CTA
+    constexpr int VN = Vec16<T>::N;                    // columns per lane
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = tma::smem_u32(smem_raw);
     const uint32_t sbase = (raw + 127u) & ~127u;
@@ -217,7 +243,7 @@ __global__ void __launch_bounds__(BN_THREADS, 1) saso_binned_kernel(const __grid
 
     const int tid = threadIdx.x, lane = tid & 31;
     const int gi = tid >> 3, l8 = tid & 7;
-    const int col0 = (int) blockIdx.x * BN_W;
+    const int col0 = (int) blockIdx.x * CW;
     const int64_t row0 = (int64_t) blockIdx.y * BN_PT;
     const int g = (int) blockIdx.z;
     const int nbox = a.Kc / BN_BOXR;
@@ -244,14 +270,16 @@ __global__ void __launch_bounds__(BN_THREADS, 1) saso_binned_kernel(const __grid
         const uint32_t dst = sbase + (uint32_t) b * BN_STAGE;
         tma::mbar_arrive_expect_tx(bar, ybytes + lbytes + BN_OBYTES);
         for (int x = 0; x < nbox; ++x)
-            tma::load_2d(dst + (uint32_t) x * (BN_BOXR * BN_W * 4), &tmY, bar, col0, c * a.Kc + x * BN_BOXR);
+            tma::load_2d(dst + (uint32_t) x * (BN_BOXR * BN_W * 4), &tmY, bar, col0, c * a.Kc + x * BN_BOXR);   // 64 rows x 128 bytes
         if (lbytes) bulk_g2s(dst + BN_OFF_LIST, a.sorted + (int64_t) c * BN_ENT_CAP + lo4, lbytes, bar);
         bulk_g2s(dst + BN_OFF_OFFS, go, BN_OBYTES, bar);
     };
 
-    float acc[BN_RPG][4];
+    T acc[BN_RPG][VN];
 #pragma unroll
-    for (int q = 0; q < BN_RPG; ++q) acc[q][0] = acc[q][1] = acc[q][2] = acc[q][3] = 0.f;
+    for (int q = 0; q < BN_RPG; ++q)
+#pragma unroll
+        for (int e = 0; e < VN; ++e) acc[q][e] = (T) 0;
 
     if (tid == 0) {
         if (g < a.nchunks) issue(g, 0);
@@ -292,12 +320,17 @@ __global__ void __launch_bounds__(BN_THREADS, 1) saso_binned_kernel(const __grid
 #pragma unroll 1
             for (; pa < pe; pa += 4) {
                 const uint32_t pn = lds32(pa + 4);
-                const float4 y = lds128(ybase + (p << 1));
-                const float sg = word_sign(p);
-                acc[q][0] = fmaf(y.x, sg, acc[q][0]);
-                acc[q][1] = fmaf(y.y, sg, acc[q][1]);
-                acc[q][2] = fmaf(y.z, sg, acc[q][2]);
-                acc[q][3] = fmaf(y.w, sg, acc[q][3]);
+                Vec16<T> y;
+                y.load(ybase + (p << 1));
+                if constexpr (sizeof(T) == 4) {
+                    const float sg = word_sign(p);
+#pragma unroll
+                    for (int e = 0; e < VN; ++e) acc[q][e] = fmaf(y.v[e], sg, acc[q][e]);
+                } else {
+                    const double sg = word_sign_f64(p);
+#pragma unroll
+                    for (int e = 0; e < VN; ++e) acc[q][e] = fma(y.v[e], sg, acc[q][e]);
+                }
                 p = pn;
             }
         }
@@ -314,20 +347,26 @@ __global__ void __launch_bounds__(BN_THREADS, 1) saso_binned_kernel(const __grid
     }
 
     // ---- add the tile into C (beta was applied beforehand; G CTAs share the tile) ----
-    const int64_t col = (int64_t) col0 + l8 * 4;
+    const int64_t col = (int64_t) col0 + l8 * VN;
 #pragma unroll
     for (int q = 0; q < BN_RPG; ++q) {
         const int64_t row = row0 + (int64_t) gi * BN_RPG + q;
         if (row >= a.P || col >= a.Q) continue;
-        float* cp = a.C + row * a.crs + col;
-        const float v0 = a.alpha * acc[q][0], v1 = a.alpha * acc[q][1], v2 = a.alpha * acc[q][2], v3 = a.alpha * acc[q][3];
-        if (a.c_vec4 && col + 3 < a.Q) {
-            asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(cp), "f"(v0), "f"(v1), "f"(v2), "f"(v3) : "memory");
+        T* cp = a.C + row * a.crs + col;
+        if constexpr (sizeof(T) == 4) {
+            const float v0 = a.alpha * acc[q][0], v1 = a.alpha * acc[q][1], v2 = a.alpha * acc[q][2], v3 = a.alpha * acc[q][3];
+            if (a.c_vec4 && col + 3 < a.Q) {
+                asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(cp), "f"(v0), "f"(v1), "f"(v2), "f"(v3) : "memory");
+            } else {
+                atomicAdd(cp, v0);
+                if (col + 1 < a.Q) atomicAdd(cp + 1, v1);
+                if (col + 2 < a.Q) atomicAdd(cp + 2, v2);
+                if (col + 3 < a.Q) atomicAdd(cp + 3, v3);
+            }
         } else {
-            atomicAdd(cp, v0);
-            if (col + 1 < a.Q) atomicAdd(cp + 1, v1);
-            if (col + 2 < a.Q) atomicAdd(cp + 2, v2);
-            if (col + 3 < a.Q) atomicAdd(cp + 3, v3);
+            // (red has no vector form for f64: ptxas "Vector qualifier is not allowed")
+            atomicAdd(cp, a.alpha * acc[q][0]);
+            if (col + 1 < a.Q) atomicAdd(cp + 1, a.alpha * acc[q][1]);
         }
     }
 }
@@ -353,13 +392,15 @@ int launch_bin(const BinArgs& a, size_t smem, cudaStream_t st) {
 
 // Returns 0 if the product was computed, -1 if this path does not take the problem (caller falls back), >0 on error.
 // C must have been beta-scaled by the caller.
-int launch_saso_binned_f32(const SasoProblem<float>& p, cudaStream_t st) {
+template <typename T>
+int launch_saso_binned(const SasoProblem<T>& p, cudaStream_t st) {
+    constexpr int CW = BN_W * 4 / (int) sizeof(T);     // columns of C per CTA
     const int64_t path = get_option("saso_path");
     if (path == 1) return -1;                                 // 1 = force the atomic kernel
     const bool scatter = p.major_is_rows ? !p.x_is_transposed : p.x_is_transposed;   // short axis <-> rows of C
     if (!scatter) return -1;
     if (p.ycs != 1 || p.ccs != 1) return -1;
-    if ((reinterpret_cast<uintptr_t>(p.Y) & 15) != 0 || (p.yrs & 3) != 0) return -1;   // TMA alignment rules
+    if ((reinterpret_cast<uintptr_t>(p.Y) & 15) != 0 || ((p.yrs * (int64_t) sizeof(T)) & 15) != 0) return -1;   // TMA alignment rules
     if (p.vec_nnz > 32 || p.dim_major >= 0x7fffffffLL || p.P > BN_PMAX) return -1;
     if (p.Q > 0x7fffffffLL || p.yrs > 0x3fffffffLL) return -1;
     const int64_t w0 = p.major_is_rows ? p.co_s : p.ro_s;      // first column of X in operator coordinates
@@ -371,7 +412,7 @@ int launch_saso_binned_f32(const SasoProblem<float>& p, cudaStream_t st) {
     {
         static DevOnce attr_done;
         if (attr_done.need()) {
-            if (cudaFuncSetAttribute(saso_binned_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BN_SMEM) != cudaSuccess) {
+            if (cudaFuncSetAttribute(saso_binned_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, BN_SMEM) != cudaSuccess) {
                 cudaGetLastError();
                 return -1;
             }
@@ -381,7 +422,7 @@ int launch_saso_binned_f32(const SasoProblem<float>& p, cudaStream_t st) {
     const int k = (int) p.vec_nnz;
     int Kc = (BN_ENT / k) / BN_BOXR * BN_BOXR;
     if (Kc > BN_KMAX) Kc = BN_KMAX;
-    const int64_t ns = (p.Q + BN_W - 1) / BN_W, np = (p.P + BN_PT - 1) / BN_PT;
+    const int64_t ns = (p.Q + CW - 1) / CW, np = (p.P + BN_PT - 1) / BN_PT;
     if (ns > 0x7fffffffLL || np > 65535) return -1;
     const int Prows = (int) np * BN_PT, Ppad = Prows + 8;
     const size_t bin_smem = ((size_t) Prows + 32 + 2 * BN_ENT) * 4;
@@ -415,15 +456,16 @@ int launch_saso_binned_f32(const SasoProblem<float>& p, cudaStream_t st) {
 
         CUtensorMap tm;
         const cuuint64_t gdim[2] = {(cuuint64_t) p.Q, (cuuint64_t) nv};
-        const cuuint64_t gstr[1] = {(cuuint64_t) p.yrs * 4ull};
-        const cuuint32_t box[2] = {BN_W, BN_BOXR};
+        const cuuint64_t gstr[1] = {(cuuint64_t) p.yrs * sizeof(T)};
+        const cuuint32_t box[2] = {(cuuint32_t) CW, BN_BOXR};
         const cuuint32_t estr[2] = {1, 1};
-        CUresult cr = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(p.Y + v0 * p.yrs), gdim, gstr, box,
+        CUresult cr = enc(&tm, sizeof(T) == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2,
+                          const_cast<T*>(p.Y + v0 * p.yrs), gdim, gstr, box,
                           estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                           CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (cr != CUDA_SUCCESS) return v0 == 0 ? -1 : fail("cuTensorMapEncodeTiled failed for the SASO apply");
 
-        BinnedArgs a;
+        BinnedArgs<T> a;
         a.sorted = sorted; a.offs16 = offs16; a.nchunks = (int) nchunks; a.Kc = Kc; a.Ppad = Ppad;
         int64_t G = sms / (ns * np);
         if (G < 1) G = 1;
@@ -433,14 +475,17 @@ int launch_saso_binned_f32(const SasoProblem<float>& p, cudaStream_t st) {
         a.P = p.P; a.Q = p.Q;
         a.alpha = p.alpha;
         a.C = p.C; a.crs = p.crs;
-        a.c_vec4 = ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0 && (p.crs & 3) == 0) ? 1 : 0;
+        a.c_vec4 = ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0 && ((p.crs * (int64_t) sizeof(T)) & 15) == 0) ? 1 : 0;
         dim3 grid((unsigned) ns, (unsigned) np, (unsigned) G);
-        saso_binned_kernel<<<grid, BN_THREADS, BN_SMEM, st>>>(tm, a);
+        saso_binned_kernel<T><<<grid, BN_THREADS, BN_SMEM, st>>>(tm, a);
         count_launch();
         count_owner_launch();
         RB_CUDA(cudaGetLastError());
     }
     return 0;
 }
+
+template int launch_saso_binned<float>(const SasoProblem<float>&, cudaStream_t);
+template int launch_saso_binned<double>(const SasoProblem<double>&, cudaStream_t);
 
 }  // namespace rb

@@ -267,10 +267,8 @@ int launch_saso_apply(const SasoProblem<T>& p, cudaStream_t st) {
     int rc = launch_scale<T>(p.P, p.Q, p.beta, p.C, p.crs, p.ccs, st);
     if (rc) return rc;
     if (p.K <= 0 || p.alpha == (T) 0) return 0;
-    if constexpr (sizeof(T) == 4) {
-        rc = launch_saso_binned_f32(p, st);     // register-resident output, binned entry lists (saso_binned.cu)
-        if (rc >= 0) return rc;
-    }
+    rc = launch_saso_binned<T>(p, st);          // register-resident output, binned entry lists (saso_binned.cu)
+    if (rc >= 0) return rc;
     // only minor-axis vectors that intersect the window are visited
     const int64_t w0 = p.major_is_rows ? p.co_s : p.ro_s;
     const int64_t wn = p.major_is_rows ? p.cs : p.rs;

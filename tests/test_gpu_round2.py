@@ -442,3 +442,47 @@ def test_short_axis_operators_on_tensor_cores_vs_oracle(gpu, port, dt):
         assert rb.counter("tensor_core_launches") == before + 1, ("right", lay)
         port.rskge3(lay, "N", "T", mm, dd, nn, dt(-0.5), A, lda, (120, 1000, "G", "S"), ctr, key, 4, 8, dt(2.0), B2, ldb)
         assert relerr(B1, B2) < tol, (("right", lay), relerr(B1, B2))
+
+
+# ------------------------------------------------------------------------------ SASO apply, double
+def test_saso_binned_kernel_double_vs_oracle(gpu, port):
+    """The register-tile SASO apply (saso_binned.cu) instantiated for double (16 columns of C per CTA = the same 128 bytes
+    per row slice as 32 float columns): forced on shapes that cross tile boundaries -- two row tiles (d > 1024), ragged
+    column slices (n % 16 != 0), ragged last chunk, operator windows, every sub-warp group size, alpha/beta -- against
+    the oracle at 1e-12, and at a C4-like slice against an fp64 product of the sampled operator."""
+    import torch
+    import randblas_b200 as rb
+    rng = np.random.default_rng(5)
+    ctr, key = ol.state_from_u64(1997)
+    dt = np.float64
+    try:
+        rb.set_option("saso_path", 2)
+        before = rb.counter("saso_owner_launches")
+        for (d, n, m, vn, ro, co) in ((45, 29, 2111, 3, 2, 5), (1500, 34, 3000, 8, 0, 0), (1100, 50, 1537, 17, 7, 3),
+                                      (300, 36, 900, 32, 0, 1), (64, 16, 5000, 1, 1, 0), (2048, 20, 777, 5, 0, 0)):
+            for opS in "NT":
+                Dr, Dc = (d + ro + 3, m + co + 6) if opS == "N" else (m + ro + 6, d + co + 3)
+                lda = n + (n % 2)                                # 16-byte aligned rows for TMA
+                A = rng.standard_normal(m * lda)
+                ldb = n + 1
+                B0 = rng.standard_normal(d * ldb)
+                for alpha, beta in ((1.0, 0.0), (0.5, -1.5)):
+                    B1, B2 = B0.copy(), B0.copy()
+                    gpu.lskges("R", opS, "N", d, n, m, dt(alpha), (Dr, Dc, vn, "S"), ctr, key, ro, co, A, lda, dt(beta), B1, ldb)
+                    port.lskges("R", opS, "N", d, n, m, dt(alpha), (Dr, Dc, vn, "S"), ctr, key, ro, co, A, lda, dt(beta), B2, ldb)
+                    assert relerr(B1, B2) < 1e-12, ((d, n, m, vn, opS, alpha), relerr(B1, B2))
+        assert rb.counter("saso_owner_launches") > before, "the binned kernel did not run for double"
+        rb.set_option("saso_path", 0)
+        d, n, m, vn = 2048, 128, 100000, 8
+        S = rb.SparseSkOp(rb.SparseDist(d, m, vn), rb.RNGState(1997), dtype=dt)
+        A = torch.randn(m * n, dtype=torch.float64, device="cuda")
+        Bo = torch.full((d * n,), 7.0, dtype=torch.float64, device="cuda")
+        before = rb.counter("saso_owner_launches")
+        rb.sketch_general("R", "N", "N", d, n, m, 1.0, S, 0, 0, A, n, 0.0, Bo, n)
+        assert rb.counter("saso_owner_launches") == before + 1
+        rb.fill_sparse(S)
+        Sd = torch.sparse_coo_tensor(torch.stack([S.rows, S.cols]), S.vals, (d, m))
+        want = torch.sparse.mm(Sd, A.view(m, n)).view(-1)
+        assert float(torch.linalg.norm(Bo - want) / torch.linalg.norm(want)) < 1e-12
+    finally:
+        rb.set_option("saso_path", 0)
