@@ -340,6 +340,23 @@ class C2FillDense(Workload):
                 "kernel": "fill_dense_tiled_kernel<double, GAUSS>", "peak_source": pk["source"],
                 "algorithmic_bytes_per_launch": self.rows * self.cols * 8}
 
+    def extra(self, pk):
+        """The same kernel and buffer with the Uniform family: the HBM write path without the Box-Muller arithmetic."""
+        torch, rb = self.torch, self.rb
+        Du = rb.DenseDist(self.rows * self.world, self.cols, rb.ScalarDist.Uniform, rb.Axis.Long)
+        rb.fill_dense_unpacked("R", Du, self.rows, self.cols, self.ro, 0, self.buf, self.seed)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(5):
+            rb.fill_dense_unpacked("R", Du, self.rows, self.cols, self.ro, 0, self.buf, self.seed)
+        b.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b) / 5
+        gbs = self.rows * self.cols * 8 / 1e9 / (ms / 1e3)
+        return {"uniform_family": {"ms": ms, "Gsamples_per_s": self.rows * self.cols / 1e9 / (ms / 1e3), "achieved_GBs": gbs,
+                                   "frac_hbm": gbs / pk["hbm_gbs"], "kernel": "fill_dense_tiled_kernel<double, UNIFORM>"}}
+
     def verify(self, dist):
         """a 64 x 5000 corner of this rank's rows against the CPU checker (2 float ulp allowed, 0 expected)"""
         if self.rank != 0:

@@ -35,13 +35,16 @@ def main():
     worst = {}
     # (dtype, family, d, n, m, layout, tolerance): small ragged shapes (generic + tensor-core paths), then a block of
     # BASELINE.json configs[2] (d=4096, n=512) with 20000 rows per rank
-    cases = [(np.float64, "G", 256, 96, 20006, "C", 1e-12), (np.float32, "U", 128, 64, 9001, "R", 1e-5),
+    # the first case leaves the last rank(s) WITHOUT rows (m < 4 * world): their partial is zero, the collective still runs
+    cases = [(np.float64, "G", 8, 6 * world, 3, "C", 1e-12),
+             (np.float64, "G", 256, 96, 20006, "C", 1e-12), (np.float32, "U", 128, 64, 9001, "R", 1e-5),
              (np.float32, "G", 256, 256, 16384, "C", 1e-5), (np.float64, "G", 4096, 512, 20000 * world, "C", 1e-12)]
     for (dt, fam, d, n, m, layout, tol) in cases:
         tdt = torch.float32 if dt == np.float32 else torch.float64
-        # the full A, identical on every rank: the library's own generator with a fixed seed
+        # the full A (logical m x n), identical on every rank: the library's own generator with a fixed seed, written in
+        # ColMajor order whatever the distribution's natural layout is
         Afull = torch.empty(m * n, dtype=tdt, device="cuda")
-        rb.fill_dense(rb.DenseDist(m, n), Afull, rb.RNGState(99))            # tall: ColMajor, lda = m
+        rb.fill_dense_unpacked("C", rb.DenseDist(m, n), m, n, 0, 0, Afull, rb.RNGState(99))     # ColMajor, lda = m
         A2 = Afull.view(n, m).t()                                            # logical m x n
         start, count = block(m, rank, world, 4)
         if layout == "C":
