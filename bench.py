@@ -233,7 +233,11 @@ class C3DenseSketchF64(Workload):
         sustained = measured_gemm_tflops(self.torch, self.torch.float64, n=6144, reps=3, sustained_s=1.5)
         # the step is one ~0.5 s (N=1) launch timed back to back: the sustained DGEMM rate is the matching denominator
         peak = sustained if kernel_ms > 100.0 else burst
-        return {"bound": "tensor", "achieved": tf, "peak": peak, "unit": "TFLOP/s", "frac": tf / peak, "traffic": None,
+        return {"bound": "tensor", "achieved": tf, "peak": peak, "unit": "TFLOP/s", "frac": tf / peak,
+                "traffic": self.count * self.n * 8 * (137.445888 + 102.572032) / 134.217728,
+                "traffic_source": "ncu --set full on a 32768-row block (profiles/r02_ncu_summary.txt, dense_f64): dram read "
+                                  "137.4 MB + write 102.6 MB for a 134.2 MB block of A (the writes are the 8 split-K partial "
+                                  "tiles of that launch, a per-launch constant: the scaling by rows overstates them)",
                 "kernel": "skge3_dmma_ws_kernel (mma.sync m8n8k4 f64, warp-specialised) + splitk_reduce_f64_kernel",
                 "peak_source": "measured in this run: cuBLAS DGEMM 6144^3, " + ("back to back for 1.5 s (sustained)"
                                if kernel_ms > 100.0 else "best single launch (burst)") + "; nominal B200 FP64: 40 TFLOP/s",
@@ -335,8 +339,8 @@ class C2FillDense(Workload):
         gbs = self.rows * self.cols * 8 / 1e9 / (kernel_ms / 1e3)
         return {"bound": "hbm", "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gbs / pk["hbm_gbs"],
                 "traffic": self.rows * self.cols * 8 * (1.989540 + 0.000055) / 2.048,
-                "traffic_source": "ncu --set full on a 256 x 1e6 slice of this launch: dram write 1.990 GB + read 0.0001 GB "
-                                  "for 2.048 GB algorithmic, scaled by rows (profiles/)",
+                "traffic_source": "ncu --set full on a 256 x 1e6 slice of this launch (profiles/r02_ncu_summary.txt, "
+                                  "fill_gauss_f64): dram write 1.989 GB + read 0.0001 GB for 2.048 GB algorithmic, scaled by rows",
                 "kernel": "fill_dense_tiled_kernel<double, GAUSS>", "peak_source": pk["source"],
                 "algorithmic_bytes_per_launch": self.rows * self.cols * 8}
 
@@ -426,8 +430,12 @@ class C1DenseSketchF32(Workload):
         tf = 2.0 * self.d * self.m * self.n / 1e12 / (kernel_ms / 1e3)
         tf32 = measured_gemm_tflops(self.torch, self.torch.float32)
         peak = tf32 / 3.0                              # 3xTF32 issues 3 MMAs per fp32 product
-        return {"bound": "tensor", "achieved": tf, "peak": peak, "unit": "TFLOP/s", "frac": tf / peak, "traffic": None,
-                "kernel": "skge3_tc_kernel (tcgen05 3xTF32) + splitk_reduce_kernel",
+        return {"bound": "tensor", "achieved": tf, "peak": peak, "unit": "TFLOP/s", "frac": tf / peak,
+                "traffic": (409.712384 + 307.432192 + 348.154368 + 6.877696) * 1e6,
+                "traffic_source": "ncu --set full of this launch (profiles/r02_ncu_summary.txt, dense_f32): main kernel dram read "
+                                  "409.7 MB (A once) + write 307.4 MB (83 split-K partial tiles), reduce kernel read 348.2 MB + "
+                                  "write 6.9 MB",
+                "kernel": "skge3_tc_kernel<PAIR> (tcgen05 cta_group::2, 3xTF32) + splitk_reduce_kernel",
                 "peak_source": f"measured in this run: cuBLAS TF32 GEMM 8192^3 = {tf32:.1f} TFLOP/s, / 3 "
                                f"(MEASURED_PEAKS bf16 {pk['bf16_tflops']:.0f} / 2 / 3 = {pk['bf16_tflops'] / 6:.1f})",
                 "frac_of_measured_bf16_over_6": tf / (pk["bf16_tflops"] / 6.0),
@@ -500,8 +508,8 @@ class C4SasoApply(Workload):
         gbs = self.m * self.n * 4 / 1e9 / (kernel_ms / 1e3)
         return {"bound": "hbm", "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gbs / pk["hbm_gbs"],
                 "traffic": self.m * self.n * 4 * (1.064040 + 0.006197) / 1.024,
-                "traffic_source": "ncu --set full on the first 1e6 rows of A: dram read 1.064 GB + write 0.006 GB for "
-                                  "1.024 GB algorithmic, scaled by rows (profiles/)",
+                "traffic_source": "ncu --set full on the first 1e6 rows of A (profiles/r02_ncu_summary.txt, saso_apply): dram "
+                                  "read 1.064 GB + write 0.004 GB for 1.024 GB algorithmic, scaled by rows",
                 "kernel": "saso_bin_kernel<8> + saso_binned_kernel (saso_binned.cu)",
                 "peak_source": pk["source"],
                 "algorithmic_bytes_per_launch": self.m * self.n * 4}
@@ -611,7 +619,11 @@ class C5SketchSparse(Workload):
     def roofline(self, kernel_ms, pk):
         gbs = (self.bytes_A() + self.d * self.n_local * 4) / 1e9 / (kernel_ms / 1e3)
         return {"bound": "hbm", "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gbs / pk["hbm_gbs"],
-                "traffic": None, "kernel": "spdata_kgroup_kernel<float> (+ zero-fill of B)", "peak_source": pk["source"],
+                "traffic": self.nnz * (4.384612e9 + 7.600831e9) / 12.5e6,
+                "traffic_source": "ncu --set full on the first 1e6 rows (1.25e7 nonzeros; profiles/r02_ncu_summary.txt, sksp): dram "
+                                  "read 4.38 GB + write 7.60 GB, scaled by nonzeros -- B (256 MB) exceeds the L2, so "
+                                  "reductions into non-resident lines spill to DRAM",
+                "kernel": "spdata_kgroup_kernel<float> (+ zero-fill of B)", "peak_source": pk["source"],
                 "algorithmic_bytes_per_launch": self.bytes_A() + self.d * self.n_local * 4,
                 "nnz": self.nnz,
                 "l2_reduction_rate_G_red_v4_per_s": self.nnz * (self.d / 4) / 1e9 / (kernel_ms / 1e3),
