@@ -32,6 +32,12 @@ struct CSRMatrix {
               IndexBase index_base = IndexBase::Zero)
         : n_rows(n_rows), n_cols(n_cols), own_memory(false), nnz(nnz), index_base(index_base), vals(vals), rowptr(rowptr),
           colidxs(colidxs) {}
+    // move constructor (csr_matrix.hh:170-176): the source gives up its arrays
+    CSRMatrix(CSRMatrix<T, sint_t>&& o)
+        : n_rows(o.n_rows), n_cols(o.n_cols), own_memory(o.own_memory), nnz(o.nnz), index_base(o.index_base), vals(o.vals),
+          rowptr(o.rowptr), colidxs(o.colidxs) {
+        o.vals = nullptr; o.rowptr = nullptr; o.colidxs = nullptr; o.nnz = 0;
+    }
     ~CSRMatrix() {
         if (own_memory) { delete[] vals; delete[] rowptr; delete[] colidxs; }
     }
@@ -64,6 +70,11 @@ struct CSCMatrix {
               IndexBase index_base = IndexBase::Zero)
         : n_rows(n_rows), n_cols(n_cols), own_memory(false), nnz(nnz), index_base(index_base), vals(vals),
           rowidxs(rowidxs), colptr(colptr) {}
+    CSCMatrix(CSCMatrix<T, sint_t>&& o)                                           // csc_matrix.hh:169-175
+        : n_rows(o.n_rows), n_cols(o.n_cols), own_memory(o.own_memory), nnz(o.nnz), index_base(o.index_base), vals(o.vals),
+          rowidxs(o.rowidxs), colptr(o.colptr) {
+        o.vals = nullptr; o.rowidxs = nullptr; o.colptr = nullptr; o.nnz = 0;
+    }
     ~CSCMatrix() {
         if (own_memory) { delete[] vals; delete[] rowidxs; delete[] colptr; }
     }
@@ -100,6 +111,11 @@ struct COOMatrix {
         : n_rows(n_rows), n_cols(n_cols), own_memory(false), nnz(nnz), index_base(index_base), vals(vals), rows(rows),
           cols(cols), sort(NonzeroSort::None) {
         (void) compute_sort_type;
+    }
+    COOMatrix(COOMatrix<T, sint_t>&& o)                                           // coo_matrix.hh:195-202
+        : n_rows(o.n_rows), n_cols(o.n_cols), own_memory(o.own_memory), nnz(o.nnz), index_base(o.index_base), vals(o.vals),
+          rows(o.rows), cols(o.cols), sort(o.sort) {
+        o.vals = nullptr; o.rows = nullptr; o.cols = nullptr; o.nnz = 0;
     }
     ~COOMatrix() {
         if (own_memory) { delete[] vals; delete[] rows; delete[] cols; }

@@ -185,11 +185,39 @@ int random_coo_t(int64_t m, int64_t n, double density, Ctr128 ctr, PhiloxKey key
 
 }  // namespace
 
+static bool is_host_ptr(const void* p) {
+    if (!p) return false;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return true; }
+    return !(a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged);
+}
+
 template <typename T>
 static int random_coo_impl(int64_t m, int64_t n, double density, const uint32_t* ctr, const uint32_t* key, int64_t capacity,
                            T* vals, void* rows, void* cols, int idx_bytes, int64_t* nnz, uint32_t* next_ctr,
                            int64_t* ambiguous, void* stream) {
     cudaStream_t st = (cudaStream_t) stream;
+    if (capacity > 0 && vals && rows && cols && (is_host_ptr(vals) || is_host_ptr(rows) || is_host_ptr(cols))) {
+        // host destination (a caller of the CPU reference): generate into device scratch, copy the stored entries back
+        RB_REQUIRE(is_host_ptr(vals) && is_host_ptr(rows) && is_host_ptr(cols));
+        T* dv = nullptr; void* dr = nullptr; void* dc = nullptr;
+        RB_CUDA(cudaMallocAsync(&dv, (size_t) capacity * sizeof(T), st));
+        if (cudaMallocAsync(&dr, (size_t) capacity * idx_bytes, st) != cudaSuccess ||
+            cudaMallocAsync(&dc, (size_t) capacity * idx_bytes, st) != cudaSuccess) {
+            cudaGetLastError(); cudaFreeAsync(dv, st); if (dr) cudaFreeAsync(dr, st);
+            return fail_cuda(cudaErrorMemoryAllocation, "random_coo staging");
+        }
+        int rc = random_coo_impl<T>(m, n, density, ctr, key, capacity, dv, dr, dc, idx_bytes, nnz, next_ctr, ambiguous, stream);
+        if (!rc && *nnz > 0) {
+            const size_t k = (size_t) (*nnz < capacity ? *nnz : capacity);
+            cudaMemcpyAsync(vals, dv, k * sizeof(T), cudaMemcpyDeviceToHost, st);
+            cudaMemcpyAsync(rows, dr, k * idx_bytes, cudaMemcpyDeviceToHost, st);
+            cudaMemcpyAsync(cols, dc, k * idx_bytes, cudaMemcpyDeviceToHost, st);
+        }
+        cudaFreeAsync(dv, st); cudaFreeAsync(dr, st); cudaFreeAsync(dc, st);
+        if (cudaStreamSynchronize(st) != cudaSuccess && !rc) rc = fail_cuda(cudaGetLastError(), "random_coo copy back");
+        return rc;
+    }
     RB_REQUIRE(density >= 0.0 && density <= 1.0);            // random_matrix.hh:297
     RB_REQUIRE(m >= 0 && n >= 0 && capacity >= 0);
     RB_REQUIRE(ctr != nullptr && key != nullptr && nnz != nullptr);

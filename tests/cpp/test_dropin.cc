@@ -13,6 +13,7 @@
 #include <vector>
 #include <cuda_runtime_api.h>   // device buffers of the multi-GPU check only
 #include "RandBLAS.hh"
+#include "RandBLAS/sparse_data/random_matrix.hh"   // as in the reference: not part of the aggregate header
 
 using namespace RandBLAS;
 static int failures = 0;
@@ -346,11 +347,60 @@ static void multi_gpu_checks() {
     std::printf("multi_gpu_checks<%s>: %d GPU(s)\n", sizeof(T) == 4 ? "float" : "double", nd);
 }
 
+// --- random sparse matrices (RandBLAS/sparse_data/random_matrix.hh:136-355), written like the reference's
+// test_datastructures/test_spmats/test_random_matrix.cc: shapes, density, sortedness, determinism, state chaining
+static void random_matrix_checks() {
+    using namespace RandBLAS::sparse_data;
+    const int64_t m = 300, n = 500;
+    const double dens = 0.02;
+    RNGState<> st(42);
+    auto [A, next] = random_coo<double>(m, n, dens, st);
+    CHECK(A.n_rows == m && A.n_cols == n && A.nnz > 0 && A.sort == NonzeroSort::CSR);
+    CHECK(std::fabs((double) A.nnz - m * n * dens) < 6.0 * std::sqrt(m * n * dens));
+    bool ok = true;
+    for (int64_t e = 0; e < A.nnz; ++e) {
+        ok = ok && A.rows[e] >= 0 && A.rows[e] < m && A.cols[e] >= 0 && A.cols[e] < n;
+        if (e > 0) ok = ok && (A.rows[e] * n + A.cols[e] > A.rows[e - 1] * n + A.cols[e - 1]);     // strictly row-major sorted
+    }
+    CHECK(ok);
+    CHECK(next.counter.v[0] == (uint32_t) (A.nnz / 2 + 1) && next.key == st.key);      // the stream stops in block nnz / 2
+    auto [A2, next2] = random_coo<double>(m, n, dens, st);                               // same state, same matrix
+    ok = A2.nnz == A.nnz && next2 == next;
+    for (int64_t e = 0; e < A.nnz && ok; ++e) ok = A.rows[e] == A2.rows[e] && A.cols[e] == A2.cols[e] && A.vals[e] == A2.vals[e];
+    CHECK(ok);
+    auto [Af, nextf] = random_coo<float, int>(m, n, dens, st);                           // float values are the double ones rounded
+    ok = Af.nnz == A.nnz && nextf == next;
+    for (int64_t e = 0; e < A.nnz && ok; ++e) ok = Af.rows[e] == (int) A.rows[e] && Af.vals[e] == (float) A.vals[e];
+    CHECK(ok);
+    auto [R, nr] = random_csr<double>(m, n, dens, st);
+    ok = R.nnz == A.nnz && R.rowptr[0] == 0 && R.rowptr[m] == A.nnz && nr == next;
+    for (int64_t i = 0; i < m && ok; ++i)
+        for (int64_t e = R.rowptr[i]; e < R.rowptr[i + 1] && ok; ++e) ok = A.rows[e] == i && R.colidxs[e] == A.cols[e];
+    CHECK(ok);
+    auto [C, nc] = random_csc<double>(m, n, dens, st);
+    ok = C.n_rows == m && C.n_cols == n && C.colptr[0] == 0 && C.colptr[n] == C.nnz;
+    for (int64_t j = 0; j < n && ok; ++j)
+        for (int64_t e = C.colptr[j]; e + 1 < C.colptr[j + 1] && ok; ++e) ok = C.rowidxs[e] < C.rowidxs[e + 1];
+    CHECK(ok);
+    auto [E, ne] = random_coo<double>(m, n, 0.0, st);                                    // density 0: nothing drawn
+    CHECK(E.nnz == 0 && ne == st);
+    CHECK(throws_error([&] { random_coo<double>(m, n, 1.5, st); }));
+    // a sketch of the random matrix through sketch_sparse, as the reference's examples do
+    const int64_t d = 16;
+    DenseSkOp<double> S(DenseDist(d, m), RNGState<>(7));
+    std::vector<double> B(d * n, 0.0);
+    sketch_sparse(blas::Layout::ColMajor, blas::Op::NoTrans, blas::Op::NoTrans, d, n, m, 1.0, S, 0, 0, R, 0.0, B.data(), d);
+    double nrm = 0;
+    for (auto v : B) nrm += v * v;
+    CHECK(nrm > 0);
+}
+
 int main(int argc, char** argv) {
     host_checks();
     if (!(argc > 1 && std::strcmp(argv[1], "--host") == 0)) {
         device_checks<float>();
         device_checks<double>();
+        random_matrix_checks();
         multi_gpu_checks<float>();
         multi_gpu_checks<double>();
     }

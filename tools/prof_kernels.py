@@ -51,9 +51,15 @@ def main():
         A = torch.randn(m * n, dtype=torch.float32, device="cuda")
         B = torch.zeros(d * n, dtype=torch.float32, device="cuda")
         f = lambda: rb.sketch_general("C", "N", "N", d, n, m, 1.0, S, 0, 0, A, m, 0.0, B, d)
+    elif what == "dense_f32_qmajor":
+        # right sketch of ColMajor data (the range-finder call A * S): Q-contiguous data tiles
+        d, m, n = 1024, 100000, 1024
+        St = rb.DenseSkOp(rb.DenseDist(m, d, rb.ScalarDist.Uniform), rb.RNGState(1997), np.float32)
+        A = torch.randn(m * n, dtype=torch.float32, device="cuda")
+        B = torch.zeros(d * n, dtype=torch.float32, device="cuda")
+        f = lambda: rb.sketch_general("C", "N", "N", n, d, m, 1.0, A, n, St, 0, 0, 0.0, B, n)
     elif what == "dense_f32_gauss":
         d, m, n = 1024, 100000, 1024
-        rb.set_option("tc_cluster", 0)
         S = rb.DenseSkOp(rb.DenseDist(d, m, rb.ScalarDist.Gaussian), rb.RNGState(1997), np.float32)
         A = torch.randn(m * n, dtype=torch.float32, device="cuda")
         B = torch.zeros(d * n, dtype=torch.float32, device="cuda")
