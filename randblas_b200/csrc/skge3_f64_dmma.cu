@@ -97,7 +97,17 @@ __device__ __forceinline__ void cp_async16(void* dst, const void* src, int src_b
 // leaves its DMMA stream, the producer warp of a scheduler fills the issue slots between DMMAs. Register split with
 // setmaxnreg: producers 72, DMMA warps 216. (A first design in which every warp generated and multiplied ran at 72.9-83.6 ms
 // on the C3 shard instead of 69.4)
-constexpr int WS_THREADS = 384, WS_PROD = 128;
+#ifndef RB_DMMA_PROD_WARPS
+#define RB_DMMA_PROD_WARPS 4      // producer warps per CTA: one per scheduler (8 measured: no better)
+#endif
+#if RB_DMMA_PROD_WARPS == 8
+#define RB_DMMA_REGS_PROD "64"    // 512 threads start at 128 registers; 256 x 64 + 256 x 192 = the whole file
+#define RB_DMMA_REGS_MMA "192"
+#else
+#define RB_DMMA_REGS_PROD "72"
+#define RB_DMMA_REGS_MMA "216"
+#endif
+constexpr int WS_PROD = 32 * RB_DMMA_PROD_WARPS, WS_THREADS = 256 + WS_PROD;
 
 // XMAT: the operator is materialised (S.buff != nullptr, skge.hh:174-181): the producer warps copy its DM x 16 tiles
 // from global memory instead of generating them (plain loads, three stages ahead of the DMMA warps).
@@ -133,11 +143,29 @@ __global__ void __launch_bounds__(WS_THREADS, 1) skge3_dmma_ws_kernel(const Dmma
         asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(bar) : "memory");
     };
 
-    // Y tile of one step: DN x DK doubles = DN * DK / 2 16-byte copies, issued by the DMMA warps (256 threads)
-    auto load_y = [&](int buf, int step, int t) {
+    // Y tile of one step: DN x DK doubles = DN * DK / 2 16-byte copies, issued by the DMMA warps (256 threads). Thread t
+    // copies chunks t, t + 256, ...: consecutive chunks of a thread are a fixed number of tile rows apart, so inside the
+    // matrix (full tile, full K step -- all but the edge tiles and the last step) a copy is one pointer addition and one
+    // LDGSTS; the bounds-checked form below costs ~25 instructions per copy and made the stage boundary 22% of a DMMA
+    // warp's time (ncu source view, round 2).
+    constexpr int Y_CPT = (DN * DK / 2) / (WS_THREADS - WS_PROD);                       // copies per thread and step
+    constexpr int Y_RPQ = (WS_THREADS - WS_PROD) / (YMN ? DN / 2 : DK / 2);             // tile rows between two copies of a thread
+    const int yt = (int) threadIdx.x - WS_PROD;
+    const int y_r0 = yt / (YMN ? DN / 2 : DK / 2), y_c0 = (yt % (YMN ? DN / 2 : DK / 2)) * 2;
+    const bool tile_full = j0 + DN <= a.Q;
+    const double* y_first = YMN ? a.Y + ((int64_t) s_begin * DK + y_r0) * a.ycs + j0 + y_c0
+                                : a.Y + (j0 + y_r0) * a.ycs + (int64_t) s_begin * DK + y_c0;
+    const int64_t y_step = YMN ? DK * a.ycs : DK, y_q = Y_RPQ * a.ycs;
+    const int y_dst0 = y_r0 * (YMN ? DLQ : DLD) + y_c0;
+    auto y_is_fast = [&](int step) { return tile_full && (int64_t) (s_begin + step + 1) * DK <= a.K; };
+    auto y_arrive = [&](int buf) {
+        asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar_full + 8u * (uint32_t) buf) : "memory");
+    };
+    // bounds-checked copies of one step (edge tiles, the last K step, the prologue when it is ragged)
+    auto load_y_checked = [&](int buf, int step, int t) {
         const int64_t k0 = (int64_t) (s_begin + step) * DK;
-#pragma unroll
-        for (int q = 0; q < (DN * DK / 2) / (WS_THREADS - WS_PROD); ++q) {
+#pragma unroll 1
+        for (int q = 0; q < Y_CPT; ++q) {
             const int ch = t + (WS_THREADS - WS_PROD) * q;
             if constexpr (!YMN) {
                 const int jj = ch / (DK / 2), kc = (ch % (DK / 2)) * 2;
@@ -163,12 +191,25 @@ __global__ void __launch_bounds__(WS_THREADS, 1) skge3_dmma_ws_kernel(const Dmma
                 }
             }
         }
-        asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar_full + 8u * (uint32_t) buf) : "memory");
+    };
+    auto load_y = [&](int buf, int step, int t) {
+        if (y_is_fast(step)) {
+            const double* src = y_first + (int64_t) step * y_step;
+            double* dst = Ys + (size_t) buf * DN * DLD + y_dst0;
+#pragma unroll
+            for (int q = 0; q < Y_CPT; ++q) {
+                cp_async16(dst + q * (Y_RPQ * (YMN ? DLQ : DLD)), src, 16);
+                src += y_q;
+            }
+        } else {
+            load_y_checked(buf, step, t);
+        }
+        y_arrive(buf);
     };
 
     if (warp < WS_PROD / 32) {
         // ---------------- producers ----------------
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 " RB_DMMA_REGS_PROD ";");
         const int xc = tid % D_CPR, xr = tid / D_CPR;
         const uint64_t seed_lo = ((uint64_t) a.ctr.c1 << 32) | a.ctr.c0, seed_hi = ((uint64_t) a.ctr.c3 << 32) | a.ctr.c2;
         for (int step = 0; step < nsteps; ++step) {
@@ -237,7 +278,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) skge3_dmma_ws_kernel(const Dmma
         return;
     }
     // ---------------- DMMA warps ----------------
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 " RB_DMMA_REGS_MMA ";");
     const int cw = warp - WS_PROD / 32;
     const int wi = cw / D_WN, wj = cw % D_WN;
     const int g = lane >> 2, t4 = lane & 3;
@@ -247,34 +288,55 @@ __global__ void __launch_bounds__(WS_THREADS, 1) skge3_dmma_ws_kernel(const Dmma
 #pragma unroll
         for (int ni = 0; ni < D_NI; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
     const int ct = tid - WS_PROD;
-    for (int s0 = 0; s0 < D_AHEAD && s0 < nsteps; ++s0) load_y(s0, s0, ct);
-    for (int step = 0; step < nsteps; ++step) {
-        const int buf = step % D_STAGES;
-        tma::mbar_wait(bar_full + 8u * (uint32_t) buf, (uint32_t) ((step / D_STAGES) & 1));
-        const double* xb = Xs + ((size_t) buf * DM + wi * (D_MI * 8) + g) * DLD + t4;
-        const double* yb = YMN ? Ys + (size_t) buf * DN * DLD + t4 * DLQ + wj * (D_NI * 8) + g
-                               : Ys + ((size_t) buf * DN + wj * (D_NI * 8) + g) * DLD + t4;
+    // One stage = two halves of DK / 8 DMMA groups. The copies of the Y tile two steps ahead go out DURING the second half,
+    // one after every few rows of DMMAs (the stage they refill was left by every DMMA warp one iteration ago, so the wait
+    // in front of them does not stall): issued at the stage boundary they were time in which neither DMMA warp of a
+    // scheduler fed the pipe. What remains at the boundary: one arrive, one wait, the first fragment loads.
+    auto half_stage = [&](int buf, int h, auto&& after_row) {
+        const double* xb = Xs + ((size_t) buf * DM + wi * (D_MI * 8) + g) * DLD + t4 + h * (DK / 2);
+        const double* yb = YMN ? Ys + (size_t) buf * DN * DLD + (t4 + h * (DK / 2)) * DLQ + wj * (D_NI * 8) + g
+                               : Ys + ((size_t) buf * DN + wj * (D_NI * 8) + g) * DLD + t4 + h * (DK / 2);
 #pragma unroll
-        for (int k4 = 0; k4 < DK / 4; ++k4) {
+        for (int k4 = 0; k4 < DK / 8; ++k4) {
             double af[D_MI], bf[D_NI];
 #pragma unroll
             for (int mi = 0; mi < D_MI; ++mi) af[mi] = xb[mi * 8 * DLD + k4 * 4];
 #pragma unroll
             for (int ni = 0; ni < D_NI; ++ni) bf[ni] = YMN ? yb[k4 * 4 * DLQ + ni * 8] : yb[ni * 8 * DLD + k4 * 4];
 #pragma unroll
-            for (int mi = 0; mi < D_MI; ++mi)
+            for (int mi = 0; mi < D_MI; ++mi) {
 #pragma unroll
                 for (int ni = 0; ni < D_NI; ++ni) dmma(acc[mi][ni], af[mi], bf[ni]);
+                after_row(k4 * D_MI + mi);
+            }
+        }
+    };
+    constexpr int ROWS_HALF = (DK / 8) * D_MI;               // DMMA rows (D_NI DMMAs each) per half stage
+    static_assert(ROWS_HALF % Y_CPT == 0, "copies spread evenly over the second half of a stage");
+    for (int s0 = 0; s0 < D_AHEAD && s0 < nsteps; ++s0) load_y(s0, s0, ct);
+    for (int step = 0; step < nsteps; ++step) {
+        const int buf = step % D_STAGES;
+        tma::mbar_wait(bar_full + 8u * (uint32_t) buf, (uint32_t) ((step / D_STAGES) & 1));
+        half_stage(buf, 0, [](int) {});
+        const int nstep = step + D_AHEAD, nb = nstep % D_STAGES;
+        const bool refill = nstep < nsteps;
+        if (refill && nstep >= D_STAGES) tma::mbar_wait(bar_empty + 8u * (uint32_t) nb, (uint32_t) ((nstep / D_STAGES - 1) & 1));
+        if (refill && y_is_fast(nstep)) {
+            const double* src = y_first + (int64_t) nstep * y_step;
+            double* dst = Ys + (size_t) nb * DN * DLD + y_dst0;
+            half_stage(buf, 1, [&](int row) {
+                if (row % (ROWS_HALF / Y_CPT) == 0) {
+                    cp_async16(dst + (row / (ROWS_HALF / Y_CPT)) * (Y_RPQ * (YMN ? DLQ : DLD)), src, 16);
+                    src += y_q;
+                }
+            });
+            y_arrive(nb);
+        } else {
+            if (refill) load_y(nb, nstep, ct);
+            half_stage(buf, 1, [](int) {});
         }
         __syncwarp();
         if (lane == 0) arrive(bar_empty + 8u * (uint32_t) buf);
-        // Y tile of step + D_AHEAD into the stage every DMMA warp left one iteration ago
-        const int nstep = step + D_AHEAD;
-        if (nstep < nsteps) {
-            const int nb = nstep % D_STAGES;
-            if (nstep >= D_STAGES) tma::mbar_wait(bar_empty + 8u * (uint32_t) nb, (uint32_t) ((nstep / D_STAGES - 1) & 1));
-            load_y(nb, nstep, ct);
-        }
     }
 #pragma unroll
     for (int mi = 0; mi < D_MI; ++mi) {
@@ -316,12 +378,17 @@ __global__ void __launch_bounds__(256) splitk_reduce_f64_kernel(const double* __
 
 }  // namespace
 
-// Gaussian operators: the producer warps' Box-Muller work shares issue slots with the DMMA stream (fused 0.84 of cuBLAS
-// DGEMM against 0.89 with a materialised operator). "dmma_materialise" = 1 generates each K panel of op(S) once into a
-// scratch buffer (<= 512 MB) with the fill kernel and runs the materialised-operator instantiation on it; same operand
-// values, panel sums added in order (beta = 1 after the first panel). 0 (default) = fused, see DESIGN.md for the measurement.
+// Gaussian operators: the producer warps' Box-Muller arithmetic needs the FP64 pipe for its DFMAs, and a DMMA stream starves
+// them (tools/micro/dmma_dfma.cu: one dependent DFMA of another warp gets through every ~270 cycles while DMMAs issue back
+// to back), so the fused kernel is producer-bound: 70-75 ms on the C3 shard against 65 with a Uniform operator.
+// "dmma_materialise" = 1 (default) generates each K panel of op(S) once into scratch memory ("dmma_panel_mb", default 2 GB)
+// with the fill kernel -- no DMMA in flight, full rate -- and runs the materialised-operator instantiation on it: 64.5 ms.
+// Same operand values; panel sums are added in order (beta = 1 after the first panel), 1e-14 from the fused result.
+// 0 = fused. Short problems (K < 4096) stay fused.
 static int dense_dmma_f64_via_panel(const DenseProblem<double>& p, bool x_t, cudaStream_t st) {
-    int64_t kp = ((int64_t) 512 << 20) / 8 / (p.P > 0 ? p.P : 1);
+    int64_t mb = get_option("dmma_panel_mb");
+    if (mb < 16) mb = 16;
+    int64_t kp = (mb << 20) / 8 / (p.P > 0 ? p.P : 1);
     kp = (kp / 1024) * 1024;
     if (kp < 1024) kp = 1024;
     if (kp > p.K) kp = (p.K + 1) / 2 * 2;
@@ -367,7 +434,7 @@ int launch_dense_dmma_f64(const DenseProblem<double>& p, cudaStream_t st) {
     if (tiles_p > 65535 || tiles_q > 0x7fffffff) return -1;
     const int64_t steps = (p.K + DK - 1) / DK;
     if (steps > 0x7fffffff) return -1;
-    if (!xmat && p.family == 'G' && get_option("dmma_materialise") != 0 && p.K >= 1024)
+    if (!xmat && p.family == 'G' && get_option("dmma_materialise") != 0 && p.K >= 4096)
         return dense_dmma_f64_via_panel(p, x_t, st);
     const int64_t tiles = tiles_p * tiles_q;
     const int sms = sm_count();

@@ -70,6 +70,12 @@ def main():
         A = torch.randn(m * n, dtype=torch.float64, device="cuda")
         B = torch.zeros(d * n, dtype=torch.float64, device="cuda")
         f = lambda: rb.sketch_general("C", "N", "N", d, n, m, 1.0, S, 0, 0, A, m, 0.0, B, d)
+    elif what == "cublas_dgemm":
+        # the library kernel the C3 roofline is quoted against, at the profiled C3 slice's shape
+        d, m, n = 4096, 32768, 512
+        X = torch.randn(d, m, dtype=torch.float64, device="cuda")
+        Y = torch.randn(m, n, dtype=torch.float64, device="cuda")
+        f = lambda: torch.mm(X, Y)
     elif what in ("dense_f32_mat", "dense_f64_mat"):
         # materialised operator (S.buff filled): the XMAT instantiations of the tensor-core kernels
         dt, tdt = (np.float32, torch.float32) if what == "dense_f32_mat" else (np.float64, torch.float64)
