@@ -7,8 +7,8 @@ ONE JSON line on stdout (rank 0). The default run measures ALL FIVE configuratio
 keys (value, ms_per_step, roofline, e2e, cpu_baseline, clocks ...) are those of the HEADLINE configuration
 
     c3: sketch_general<double>, Gaussian, d=4096, n=512, m=4,000,000 -- the WHOLE problem, strong-scaled:
-        rank g of N holds rows block(m, g, N) of A (N=1: all 16.4 GB), regenerates its columns of S inside the fused
-        kernel, and the d x n partial products are summed by the NCCL reduce-scatter of rb_lskge3_mshard_f64
+        rank g of N holds rows block(m, g, N) of A (N=1: all 16.4 GB), regenerates its columns of S on the device
+        (never from the host; per K panel into scratch), and the d x n partial products are summed by the NCCL reduce-scatter of rb_lskge3_mshard_f64
         INSIDE the timed region; the result is verified after it (against torch.distributed's own all-reduce of
         independently computed partials, and against the compiled reference on a row block).
 
@@ -190,10 +190,11 @@ class Workload:
 
 class C3DenseSketchF64(Workload):
     """sketch_general<double> Gaussian d=4096 n=512 m=4,000,000, the whole problem: rank g holds rows
-    block(m, g, world) of A (ColMajor, lda = its row count) and calls rb_lskge3_mshard_f64 (fused generate+DMMA
-    kernel, then the NCCL reduce-scatter of the 16.8 MB partials inside the library)."""
+    block(m, g, world) of A (ColMajor, lda = its row count) and calls rb_lskge3_mshard_f64 (per 2 GB K panel of the
+    operator: fill kernel into scratch + DMMA kernel; then the NCCL reduce-scatter of the 16.8 MB partials inside the
+    library)."""
     key = "c3"
-    name = ("c3: sketch_general double Gaussian d=4096 m=4000000 n=512 ColMajor, S unfilled (fused), m-sharded over the "
+    name = ("c3: sketch_general double Gaussian d=4096 m=4000000 n=512 ColMajor, S unfilled (generated on the fly), m-sharded over the "
             "ranks with the NCCL reduce-scatter inside the timed region (N=1: the whole 16.4 GB A on one GPU)")
     metric = "sketch_general GB/s of A"
     unit = "GB/s"
@@ -234,11 +235,15 @@ class C3DenseSketchF64(Workload):
         # the step is one ~0.5 s (N=1) launch timed back to back: the sustained DGEMM rate is the matching denominator
         peak = sustained if kernel_ms > 100.0 else burst
         return {"bound": "tensor", "achieved": tf, "peak": peak, "unit": "TFLOP/s", "frac": tf / peak,
-                "traffic": self.count * self.n * 8 * (137.445888 + 102.572032) / 134.217728,
-                "traffic_source": "ncu --set full on a 32768-row block (profiles/r02_ncu_summary.txt, dense_f64): dram read "
-                                  "137.4 MB + write 102.6 MB for a 134.2 MB block of A (the writes are the 8 split-K partial "
-                                  "tiles of that launch, a per-launch constant: the scaling by rows overstates them)",
-                "kernel": "skge3_dmma_ws_kernel (mma.sync m8n8k4 f64, warp-specialised) + splitk_reduce_f64_kernel",
+                "traffic": self.count * self.n * 8 * (1017.2 + 1308.4 + 121.1 + 134.2 + 9.2) / 134.217728,
+                "traffic_source": "ncu --set full on a 32768-row block (profiles/r02_ncu_summary.txt, dense_f64), per 134.2 MB of "
+                                  "A: the fill kernel writes the 1.07 GB operator panel (1017 MB reached DRAM), the DMMA kernel "
+                                  "reads 1308 MB (panel + A) and writes 121 MB (split-K partials), the reduce reads 134 MB. The "
+                                  "panel is scratch (d/n = 8x the bytes of A at this shape): 0.65 TB/s of DRAM traffic against "
+                                  "a tensor-bound kernel; the fused kernel (dmma_materialise=0) moves 240 MB for the same block "
+                                  "and is 13% slower",
+                "kernel": "skge3_dmma_ws_kernel<materialised operator> (mma.sync m8n8k4 f64, warp-specialised) after "
+                          "fill_dense_tiled_kernel per K panel, + splitk_reduce_f64_kernel",
                 "peak_source": "measured in this run: cuBLAS DGEMM 6144^3, " + ("back to back for 1.5 s (sustained)"
                                if kernel_ms > 100.0 else "best single launch (burst)") + "; nominal B200 FP64: 40 TFLOP/s",
                 "peak_burst": burst, "peak_sustained": sustained, "frac_of_burst": tf / burst,
