@@ -318,9 +318,10 @@ int rb_lskge3_mshard_all_f64(int ndev, const rb_comm_t* comms, char layout, char
  * "tc_cluster" (0 / 1 / 2: 2-CTA cluster mode of the float tensor-core kernel: never / where it pays / whenever
  * possible), "tc_splits", "tc_halves", "saso_path" (0 auto / 1 atomic kernel / 2 binned kernel), "saso_fill_path",
  * "spdata_path" (1 = the deterministic column-owner kernel), "h2d_chunk_mb" (block size of the host-pointer sketch
- * pipeline), "tc_pair" (CTA pairs, cta_group::2: 0 never / 1 where it pays / 2 whenever possible), "tc_materialise"
+ * pipeline; the first two blocks are a quarter and a half of it), "tc_pair" (CTA pairs, cta_group::2: 0 never / 1 where it pays / 2 whenever possible), "tc_materialise"
  * (Gaussian float operators generated once per K panel: 0 never / 1 with >= 2 column tiles / 2 always),
- * "dmma_materialise" (the same for double, off by default).
+ * "dmma_materialise" (the same for double: 1 = Gaussian operators with K >= 4096, the default; 0 = fused kernel),
+ * "dmma_panel_mb" (size of that panel, default 2048).
  * rb_get_counter("kernel_launches" | "tensor_core_launches" | "saso_owner_launches") counts kernels this library
  * launched. */
 int rb_set_option(const char* name, int64_t value);

@@ -362,7 +362,7 @@ static int skge3_impl(bool left, char layout, char opS, char opA, int64_t d, int
     // contraction dimension (the reference's own blocked form, skge.hh:174-181: block k0 uses the operator window
     // shifted by k0 and accumulates with beta = 1), so the host->device copy of block i+1 overlaps the kernel of block i.
     const bool chunked = A != nullptr && S_buff == nullptr && !on_device(A) && Ktot > 0 &&
-                         (size_t) rows_A * (size_t) cols_A * sizeof(T) >= (g_h2d_chunk_mb.load() << 20) * 2ull;
+                         (size_t) rows_A * (size_t) cols_A * sizeof(T) >= ((size_t) g_h2d_chunk_mb.load() << 20) / 2;
     int rc = 0;
     if (!chunked) { rc = sA.open(A, sizeof(T), A_outer, A_inner, lda, true, false, st); if (rc) return rc; }
     rc = sB.open(B, sizeof(T), B_outer, B_inner, ldb, beta != (T) 0, true, st);
@@ -418,10 +418,18 @@ static int skge3_impl(bool left, char layout, char opS, char opA, int64_t d, int
         T* stage[2] = {(T*) workspace(8, stage_bytes, st), (T*) workspace(9, stage_bytes, st)};
         CopyPipe* pipe = copy_pipe();
         if (!stage[0] || !stage[1] || !pipe) rc = fail_cuda(cudaErrorMemoryAllocation, "sketch staging");
+        // the first two blocks are a quarter and a half of the block size: the first kernel starts after a short copy
+        auto block_len = [&](int i) {
+            int64_t k = (i == 0) ? kc_max / 4 : (i == 1) ? kc_max / 2 : kc_max;
+            k = (k / 1024) * 1024;
+            return k < 1024 ? (kc_max < 1024 ? kc_max : (int64_t) 1024) : k;
+        };
         int it = 0;
-        for (int64_t k0 = 0; k0 < Ktot && rc == 0; k0 += kc_max, ++it) {
+        int64_t kc = 0;
+        for (int64_t k0 = 0; k0 < Ktot && rc == 0; k0 += kc, ++it) {
             const int b = it & 1;
-            const int64_t kc = (Ktot - k0 < kc_max) ? Ktot - k0 : kc_max;
+            kc = block_len(it);
+            if (Ktot - k0 < kc) kc = Ktot - k0;
             if (it >= 2) cudaStreamWaitEvent(pipe->st, pipe->gen_done[b], 0);      // kernel it-2 has released the buffer
             cudaError_t e;
             if (k_inner) e = cudaMemcpy2DAsync(stage[b], (size_t) ld_stage * sizeof(T), A + k0, (size_t) lda * sizeof(T),
