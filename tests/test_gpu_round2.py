@@ -444,6 +444,44 @@ def test_short_axis_operators_on_tensor_cores_vs_oracle(gpu, port, dt):
         assert relerr(B1, B2) < tol, (("right", lay), relerr(B1, B2))
 
 
+def test_double_gaussian_operator_through_panels_vs_fused_and_oracle(gpu, port):
+    """Double Gaussian operators with K >= 4096 are generated per K panel into scratch memory and multiplied by the
+    materialised-operator DMMA kernel (dmma_materialise = 1, the default). With a 16 MB panel the cases below take four to
+    five panels (the last one ragged); the result must agree with the fused kernel (dmma_materialise = 0) and with the
+    oracle to 1e-12, for operators with blocks along K and along the rows (Axis::Short), both data layouts, alpha/beta."""
+    import randblas_b200 as rb
+    rng = np.random.default_rng(5)
+    ctr, key = ol.state_from_u64(77)
+    # (layout, d, n, m, D_rows, D_cols, axis, ro, co, alpha, beta)
+    cases = [("C", 300, 260, 20006, 310, 30000, "L", 3, 1001, 1.0, 0.0),
+             ("R", 300, 130, 24001, 300, 24001, "L", 0, 0, -0.5, 2.0),
+             ("C", 264, 200, 22222, 280, 25000, "S", 8, 5, 2.0, -1.0)]
+    try:
+        for (lay, d, n, m, Dr, Dc, ax, ro, co, alpha, beta) in cases:
+            inner = m if lay == "C" else n
+            lda = inner + inner % 2
+            A = rng.standard_normal((n if lay == "C" else m) * lda)
+            ldb = (d if lay == "C" else n) + 1
+            B0 = rng.standard_normal((n if lay == "C" else d) * ldb)
+            out = {}
+            for mat, mb in ((1, 16), (0, 16)):
+                rb.set_option("dmma_materialise", mat)
+                rb.set_option("dmma_panel_mb", mb)
+                B = B0.copy()
+                before = rb.counter("tensor_core_launches")
+                gpu.lskge3(lay, "N", "N", d, n, m, alpha, (Dr, Dc, "G", ax), ctr, key, ro, co, A, lda, beta, B, ldb)
+                launches = rb.counter("tensor_core_launches") - before
+                assert launches == (1 if mat == 0 else -(-m // ((16 << 20) // 8 // d // 1024 * 1024))), (lay, ax, mat, launches)
+                out[mat] = B
+            want = B0.copy()
+            port.lskge3(lay, "N", "N", d, n, m, alpha, (Dr, Dc, "G", ax), ctr, key, ro, co, A, lda, beta, want, ldb)
+            assert relerr(out[1], out[0]) < 1e-13, ((lay, ax), relerr(out[1], out[0]))
+            assert relerr(out[1], want) < 1e-12, ((lay, ax), relerr(out[1], want))
+    finally:
+        rb.set_option("dmma_materialise", 1)
+        rb.set_option("dmma_panel_mb", 2048)
+
+
 # ------------------------------------------------------------------------------ SASO apply, double
 def test_saso_binned_kernel_double_vs_oracle(gpu, port):
     """The register-tile SASO apply (saso_binned.cu) instantiated for double (16 columns of C per CTA = the same 128 bytes
