@@ -247,6 +247,9 @@ class C3DenseSketchF64(Workload):
                 "peak_source": "measured in this run: cuBLAS DGEMM 6144^3, " + ("back to back for 1.5 s (sustained)"
                                if kernel_ms > 100.0 else "best single launch (burst)") + "; nominal B200 FP64: 40 TFLOP/s",
                 "peak_burst": burst, "peak_sustained": sustained, "frac_of_burst": tf / burst,
+                "launch_duration": "the whole step: per 2 GB operator panel one fill, one DMMA and one split-K reduce launch "
+                                   "(ncu launch list profiles/r02_ncu_launches_bench.csv: DMMA kernel 93.5% of the step, panel "
+                                   "fill 6.2%, reduce 0.3%), so `achieved` charges the fill and the reduce to the DMMA kernel",
                 "algorithmic_flops_per_launch": 2.0 * self.d * self.count * self.n,
                 "hbm_gbs_of_A": self.count * self.n * 8 / 1e9 / (kernel_ms / 1e3)}
 

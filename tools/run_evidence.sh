@@ -4,7 +4,7 @@
 mkdir -p gpurun_out
 python -m pytest tests -m gpu -q 2>&1 | tail -30 > gpurun_out/r2_tests_gpu_full.log
 tail -5 gpurun_out/r2_tests_gpu_full.log
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/r2_ncu_launches_bench.csv \
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv --log-file gpurun_out/r2_ncu_launches_bench.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu --no-e2e > gpurun_out/r2_bench_under_ncu.log 2>&1
 tail -c 300 gpurun_out/r2_bench_under_ncu.log
 for t in "$@"; do
