@@ -482,6 +482,49 @@ def test_double_gaussian_operator_through_panels_vs_fused_and_oracle(gpu, port):
         rb.set_option("dmma_panel_mb", 2048)
 
 
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+def test_reference_componentwise_bound_dense_and_sparse_operators(gpu, port, dt):
+    """The reference's own acceptance test (test/test_matmul_cores/linop_common.hh:198-268): the sketch must equal
+    alpha * op(S_sub) * op(A) + beta * B0, computed from the MATERIALISED operator, within the componentwise bound
+    E = (|alpha| * k * 2 eps) * |S| |A| + |beta| * eps * |B0| (`:260-266`), element by element. Shapes of
+    test_lskge3.cc / test_lskges.cc (tiny: generic kernels) and shapes that reach the tensor-core and binned kernels."""
+    eps = float(np.finfo(dt).eps)
+    rng = np.random.default_rng(3)
+    ctr, key = ol.state_from_u64(0)
+
+    def check(B, S, Aop, alpha, beta, B0, k, what):
+        want = alpha * (S.astype(np.float64) @ Aop.astype(np.float64)) + beta * B0.astype(np.float64)
+        E = (abs(alpha) * k * 2 * eps) * (np.abs(S).astype(np.float64) @ np.abs(Aop).astype(np.float64)) \
+            + abs(beta) * eps * np.abs(B0).astype(np.float64)
+        bad = np.abs(B.astype(np.float64) - want) > E
+        assert not bad.any(), (what, int(bad.sum()), float(np.abs(B - want).max()), float(E.min()))
+
+    # dense operators: (d, n, m, D_rows, D_cols, family, ro, co, alpha, beta)
+    for (d, n, m, Dr, Dc, fam, ro, co, alpha, beta) in [(30, 10, 200, 30, 200, "G", 0, 0, 1.0, 0.0),
+                                                        (3, 5, 10, 8, 12, "U", 3, 1, 1.0, 0.0),
+                                                        (12, 19, 201, 12, 201, "G", 0, 0, 0.5, -1.0),
+                                                        (256, 300, 5000, 260, 6000, "U", 4, 8, 2.0, 0.25),
+                                                        (200, 260, 8200, 200, 8200, "G", 0, 0, 1.0, 1.0)]:
+        A = rng.standard_normal((m, n)).astype(dt)                          # logical m x n, stored ColMajor below
+        B0 = rng.standard_normal((d, n)).astype(dt)
+        Sfull, _ = port.fill_dense_unpacked("R", Dr, Dc, fam, "L", d, m, ro, co, ctr, key, dt)
+        S = Sfull.reshape(d, m)
+        Bc = np.asfortranarray(B0).ravel(order="F").copy()
+        gpu.lskge3("C", "N", "N", d, n, m, dt(alpha), (Dr, Dc, fam, "L"), ctr, key, ro, co,
+                   np.asfortranarray(A).ravel(order="F"), m, dt(beta), Bc, d)
+        check(Bc.reshape(n, d).T, S, A, alpha, beta, B0, m, ("dense", d, n, m, fam))
+    # SASO operators (test_lskges.cc shapes and a binned-kernel shape): vec_nnz 4 / 8
+    for (d, n, m, k, alpha, beta) in [(7, 5, 20, 3, 1.0, 0.0), (12, 19, 201, 4, -1.5, 0.5), (2048, 64, 30000, 8, 1.0, 0.0)]:
+        A = rng.standard_normal((m, n)).astype(dt)
+        B0 = rng.standard_normal((d, n)).astype(dt)
+        vals, rows, cols, nnz, _ = port.fill_sparse(d, m, k, "S", ctr, key, dt)
+        S = np.zeros((d, m), np.float64)
+        np.add.at(S, (rows[:nnz], cols[:nnz]), vals[:nnz].astype(np.float64))
+        Br = B0.ravel().copy()
+        gpu.lskges("R", "N", "N", d, n, m, dt(alpha), (d, m, k, "S"), ctr, key, 0, 0, A.ravel(), n, dt(beta), Br, n)
+        check(Br.reshape(d, n), S, A, alpha, beta, B0, m, ("saso", d, n, m, k))
+
+
 # ------------------------------------------------------------------------------ SASO apply, double
 def test_saso_binned_kernel_double_vs_oracle(gpu, port):
     """The register-tile SASO apply (saso_binned.cu) instantiated for double (16 columns of C per CTA = the same 128 bytes
