@@ -10,6 +10,7 @@
 #include <utility>
 #include <vector>
 #include "dense_skops.hh"
+#include "sparse_skops.hh"
 
 namespace RandBLAS::multi_gpu {
 
@@ -78,6 +79,26 @@ inline int call_all(int nd, const rb_comm_t* c, char l, char oS, char oA, int64_
                     const double* const* A, const int64_t* lda, double beta, double* const* B, int mode, void* const* st) {
     return rb_lskge3_mshard_all_f64(nd, c, l, oS, oA, d, n, m, alpha, Dr, Dc, fam, ax, ctr, key, ro, co, A, lda, beta, B, mode, st);
 }
+inline int call_saso(rb_comm_t c, char l, char oS, char oA, int64_t d, int64_t n, int64_t m, float alpha, int64_t Dr, int64_t Dc,
+                     int64_t k, const uint32_t* ctr, const uint32_t* key, int64_t ro, int64_t co, const float* A, int64_t lda,
+                     float beta, float* B, int mode, void* st) {
+    return rb_lskges_mshard_f32(c, l, oS, oA, d, n, m, alpha, Dr, Dc, k, ctr, key, ro, co, A, lda, beta, B, mode, st);
+}
+inline int call_saso(rb_comm_t c, char l, char oS, char oA, int64_t d, int64_t n, int64_t m, double alpha, int64_t Dr, int64_t Dc,
+                     int64_t k, const uint32_t* ctr, const uint32_t* key, int64_t ro, int64_t co, const double* A, int64_t lda,
+                     double beta, double* B, int mode, void* st) {
+    return rb_lskges_mshard_f64(c, l, oS, oA, d, n, m, alpha, Dr, Dc, k, ctr, key, ro, co, A, lda, beta, B, mode, st);
+}
+inline int call_saso_all(int nd, const rb_comm_t* c, char l, char oS, char oA, int64_t d, int64_t n, int64_t m, float alpha,
+                         int64_t Dr, int64_t Dc, int64_t k, const uint32_t* ctr, const uint32_t* key, int64_t ro, int64_t co,
+                         const float* const* A, const int64_t* lda, float beta, float* const* B, int mode, void* const* st) {
+    return rb_lskges_mshard_all_f32(nd, c, l, oS, oA, d, n, m, alpha, Dr, Dc, k, ctr, key, ro, co, A, lda, beta, B, mode, st);
+}
+inline int call_saso_all(int nd, const rb_comm_t* c, char l, char oS, char oA, int64_t d, int64_t n, int64_t m, double alpha,
+                         int64_t Dr, int64_t Dc, int64_t k, const uint32_t* ctr, const uint32_t* key, int64_t ro, int64_t co,
+                         const double* const* A, const int64_t* lda, double beta, double* const* B, int mode, void* const* st) {
+    return rb_lskges_mshard_all_f64(nd, c, l, oS, oA, d, n, m, alpha, Dr, Dc, k, ctr, key, ro, co, A, lda, beta, B, mode, st);
+}
 }  // namespace internal_mg
 
 // B = alpha * op(S[ro_s:, co_s:]) * op(A) + beta * B with the m rows of op(A) sharded over the GPUs of `comms`:
@@ -107,6 +128,34 @@ inline void sketch_general_mshard(const RankCommunicator& comm, blas::Layout lay
                                       alpha, S.dist.n_rows, S.dist.n_cols, (char) S.dist.family, (char) S.dist.major_axis,
                                       S.seed_state.counter.v, S.seed_state.key.v, ro_s, co_s, A_local, lda, beta, B_out, (int) mode,
                                       stream),
+                    __func__);
+}
+
+// The two calls above for an unsampled SASO operator (SparseDist with Axis::Short): sparse::lskges (RandBLAS/skge.hh:465-492) on
+// every GPU's row block, the d x n partials summed by the same collective.
+template <typename T, typename RNG, typename sint_t>
+inline void sketch_general_mshard(const Communicators& comms, blas::Layout layout, blas::Op opS, blas::Op opA, int64_t d, int64_t n,
+                                  int64_t m, T alpha, const SparseSkOp<T, RNG, sint_t>& S, int64_t ro_s, int64_t co_s,
+                                  const T* const* A_local, const int64_t* lda, T beta, T* const* B_out, Reduce mode = Reduce::Scatter,
+                                  void* const* streams = nullptr) {
+    randblas_require(S.nnz < 0);              // the operator is regenerated per GPU; a sampled S is a single-GPU object
+    randblas_require(S.dist.major_axis == Axis::Short);
+    internal::check(internal_mg::call_saso_all(comms.size(), comms.data(), internal::to_char(layout), internal::to_char(opS),
+                                               internal::to_char(opA), d, n, m, alpha, S.dist.n_rows, S.dist.n_cols, S.dist.vec_nnz,
+                                               S.seed_state.counter.v, S.seed_state.key.v, ro_s, co_s, A_local, lda, beta, B_out,
+                                               (int) mode, streams),
+                    __func__);
+}
+template <typename T, typename RNG, typename sint_t>
+inline void sketch_general_mshard(const RankCommunicator& comm, blas::Layout layout, blas::Op opS, blas::Op opA, int64_t d, int64_t n,
+                                  int64_t m, T alpha, const SparseSkOp<T, RNG, sint_t>& S, int64_t ro_s, int64_t co_s,
+                                  const T* A_local, int64_t lda, T beta, T* B_out, Reduce mode = Reduce::Scatter,
+                                  void* stream = nullptr) {
+    randblas_require(S.nnz < 0);
+    randblas_require(S.dist.major_axis == Axis::Short);
+    internal::check(internal_mg::call_saso(comm.get(), internal::to_char(layout), internal::to_char(opS), internal::to_char(opA), d, n,
+                                           m, alpha, S.dist.n_rows, S.dist.n_cols, S.dist.vec_nnz, S.seed_state.counter.v,
+                                           S.seed_state.key.v, ro_s, co_s, A_local, lda, beta, B_out, (int) mode, stream),
                     __func__);
 }
 

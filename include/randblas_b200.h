@@ -311,6 +311,29 @@ int rb_lskge3_mshard_all_f64(int ndev, const rb_comm_t* comms, char layout, char
                              const uint32_t ctr[4], const uint32_t key[2], int64_t ro_s, int64_t co_s,
                              const double* const* A_local, const int64_t* lda, double beta, double* const* B_out,
                              int mode, void* const* streams);
+/* The same for a SASO operator SparseDist(D_rows, D_cols, vec_nnz, Short) (sparse::lskges, RandBLAS/skge.hh:465-492, on
+ * row block M_g of op(A) with the operator window shifted by start(M_g) along the contraction index -- SURVEY.md 8(e),
+ * "SASO apply, m-sharded": the d x n partials (2 MB at BASELINE.json configs[3]) meet in the same reduce-scatter /
+ * all-reduce. Minor-axis vectors of the operator are independent (counter i * vec_nnz + j, sparse_skops.hh:72-102), so
+ * any block start would do; rb_mshard_block is used for both operator kinds. */
+int rb_lskges_mshard_f32(rb_comm_t comm, char layout, char opS, char opA, int64_t d, int64_t n, int64_t m_total,
+                         float alpha, int64_t D_rows, int64_t D_cols, int64_t vec_nnz, const uint32_t ctr[4],
+                         const uint32_t key[2], int64_t ro_s, int64_t co_s, const float* A_local, int64_t lda, float beta,
+                         float* B_out, int mode, void* stream);
+int rb_lskges_mshard_f64(rb_comm_t comm, char layout, char opS, char opA, int64_t d, int64_t n, int64_t m_total,
+                         double alpha, int64_t D_rows, int64_t D_cols, int64_t vec_nnz, const uint32_t ctr[4],
+                         const uint32_t key[2], int64_t ro_s, int64_t co_s, const double* A_local, int64_t lda,
+                         double beta, double* B_out, int mode, void* stream);
+int rb_lskges_mshard_all_f32(int ndev, const rb_comm_t* comms, char layout, char opS, char opA, int64_t d, int64_t n,
+                             int64_t m_total, float alpha, int64_t D_rows, int64_t D_cols, int64_t vec_nnz,
+                             const uint32_t ctr[4], const uint32_t key[2], int64_t ro_s, int64_t co_s,
+                             const float* const* A_local, const int64_t* lda, float beta, float* const* B_out, int mode,
+                             void* const* streams);
+int rb_lskges_mshard_all_f64(int ndev, const rb_comm_t* comms, char layout, char opS, char opA, int64_t d, int64_t n,
+                             int64_t m_total, double alpha, int64_t D_rows, int64_t D_cols, int64_t vec_nnz,
+                             const uint32_t ctr[4], const uint32_t key[2], int64_t ro_s, int64_t co_s,
+                             const double* const* A_local, const int64_t* lda, double beta, double* const* B_out,
+                             int mode, void* const* streams);
 
 /* ---- tuning / introspection (not part of the reference's surface) ----
  * rb_set_option("dense_path", v): 0 = auto (tensor-core kernels where the shape allows), 1 = force the

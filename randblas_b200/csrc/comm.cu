@@ -117,6 +117,11 @@ template <> struct Skge<float> {
                     int64_t lda, float beta, float* B, int64_t ldb, void* st) {
         return rb_lskge3_f32(layout, opS, opA, d, n, m, alpha, Dr, Dc, fam, ax, ctr, key, nullptr, ro, co, A, lda, beta, B, ldb, st);
     }
+    static int left_saso(char layout, char opS, char opA, int64_t d, int64_t n, int64_t m, float alpha, int64_t Dr, int64_t Dc,
+                         int64_t vec_nnz, const uint32_t* ctr, const uint32_t* key, int64_t ro, int64_t co, const float* A,
+                         int64_t lda, float beta, float* B, int64_t ldb, void* st) {
+        return rb_lskges_f32(layout, opS, opA, d, n, m, alpha, Dr, Dc, vec_nnz, ctr, key, ro, co, A, lda, beta, B, ldb, st);
+    }
 };
 template <> struct Skge<double> {
     static constexpr ncclDataType_t nt = ncclFloat64;
@@ -125,13 +130,26 @@ template <> struct Skge<double> {
                     int64_t lda, double beta, double* B, int64_t ldb, void* st) {
         return rb_lskge3_f64(layout, opS, opA, d, n, m, alpha, Dr, Dc, fam, ax, ctr, key, nullptr, ro, co, A, lda, beta, B, ldb, st);
     }
+    static int left_saso(char layout, char opS, char opA, int64_t d, int64_t n, int64_t m, double alpha, int64_t Dr, int64_t Dc,
+                         int64_t vec_nnz, const uint32_t* ctr, const uint32_t* key, int64_t ro, int64_t co, const double* A,
+                         int64_t lda, double beta, double* B, int64_t ldb, void* st) {
+        return rb_lskges_f64(layout, opS, opA, d, n, m, alpha, Dr, Dc, vec_nnz, ctr, key, ro, co, A, lda, beta, B, ldb, st);
+    }
+};
+
+// The operator of a sharded sketch: a DenseDist (family, axis) or, with vec_nnz > 0, a SASO SparseDist(D_rows, D_cols, vec_nnz).
+struct ShardOp {
+    int64_t D_rows, D_cols;
+    char family, axis;
+    int64_t vec_nnz;          // 0: dense operator
+    const uint32_t *ctr, *key;
 };
 
 // Phase 1 of the sharded sketch on ONE GPU: this rank's partial product into the communicator's buffer.
 template <typename T>
 static int mshard_local(rb_comm* c, char layout, char opS, char opA, int64_t d, int64_t n, int64_t m_total, T alpha,
-                        int64_t D_rows, int64_t D_cols, char family, char axis, const uint32_t* ctr, const uint32_t* key,
-                        int64_t ro_s, int64_t co_s, const T* A_local, int64_t lda, int mode, cudaStream_t st, T** partial_out) {
+                        const ShardOp& op, int64_t ro_s, int64_t co_s, const T* A_local, int64_t lda, int mode,
+                        cudaStream_t st, T** partial_out) {
     RB_REQUIRE(c != nullptr);
     RB_REQUIRE(mode == 0 || mode == 1);
     RB_REQUIRE(layout == 'R' || layout == 'C');
@@ -148,8 +166,11 @@ static int mshard_local(rb_comm* c, char layout, char opS, char opA, int64_t d, 
     // the contraction index of op(S) runs along the columns of S for opS = N, along its rows for opS = T
     const int64_t ro = ro_s + (opS == 'T' ? start : 0), co = co_s + (opS == 'N' ? start : 0);
     const int64_t ldw = (layout == 'C') ? d : n;
-    return Skge<T>::left(layout, opS, opA, d, n, count, alpha, D_rows, D_cols, family, axis, ctr, key, ro, co, A_local, lda,
-                         (T) 0, W, ldw, (void*) st);
+    if (op.vec_nnz > 0)
+        return Skge<T>::left_saso(layout, opS, opA, d, n, count, alpha, op.D_rows, op.D_cols, op.vec_nnz, op.ctr, op.key, ro, co,
+                                  A_local, lda, (T) 0, W, ldw, (void*) st);
+    return Skge<T>::left(layout, opS, opA, d, n, count, alpha, op.D_rows, op.D_cols, op.family, op.axis, op.ctr, op.key, ro, co,
+                         A_local, lda, (T) 0, W, ldw, (void*) st);
 }
 
 // Phase 2: the exchange step, then beta * B_out.
@@ -184,8 +205,8 @@ static int mshard_finish(rb_comm* c, int64_t d, int64_t n, T beta, T* W, T* B_ou
 
 template <typename T>
 static int lskge3_mshard(rb_comm* c, char layout, char opS, char opA, int64_t d, int64_t n, int64_t m_total, T alpha,
-                         int64_t D_rows, int64_t D_cols, char family, char axis, const uint32_t* ctr, const uint32_t* key,
-                         int64_t ro_s, int64_t co_s, const T* A_local, int64_t lda, T beta, T* B_out, int mode, void* stream) {
+                         const ShardOp& op, int64_t ro_s, int64_t co_s, const T* A_local, int64_t lda, T beta, T* B_out,
+                         int mode, void* stream) {
     cudaStream_t st = (cudaStream_t) stream;
     RB_REQUIRE(c != nullptr);
     NcclApi* nc = nullptr;
@@ -198,8 +219,7 @@ static int lskge3_mshard(rb_comm* c, char layout, char opS, char opA, int64_t d,
     RB_CUDA(cudaGetDevice(&dev));
     RB_REQUIRE(dev == c->device);                 // the caller selects the communicator's device (cudaSetDevice)
     T* W = nullptr;
-    int rc = mshard_local<T>(c, layout, opS, opA, d, n, m_total, alpha, D_rows, D_cols, family, axis, ctr, key, ro_s, co_s,
-                             A_local, lda, mode, st, &W);
+    int rc = mshard_local<T>(c, layout, opS, opA, d, n, m_total, alpha, op, ro_s, co_s, A_local, lda, mode, st, &W);
     if (rc) return rc;
     rc = mshard_exchange<T>(nc, c, d, n, beta, W, B_out, mode, st);
     if (rc) return rc;
@@ -209,8 +229,7 @@ static int lskge3_mshard(rb_comm* c, char layout, char opS, char opA, int64_t d,
 // One host thread driving all GPUs of a single-process communicator set (rb_comm_init).
 template <typename T>
 static int lskge3_mshard_all(int ndev, rb_comm* const* comms, char layout, char opS, char opA, int64_t d, int64_t n,
-                             int64_t m_total, T alpha, int64_t D_rows, int64_t D_cols, char family, char axis,
-                             const uint32_t* ctr, const uint32_t* key, int64_t ro_s, int64_t co_s, const T* const* A_local,
+                             int64_t m_total, T alpha, const ShardOp& op, int64_t ro_s, int64_t co_s, const T* const* A_local,
                              const int64_t* lda, T beta, T* const* B_out, int mode, void* const* streams) {
     RB_REQUIRE(ndev >= 1 && comms != nullptr && A_local != nullptr && lda != nullptr && B_out != nullptr);
     NcclApi* nc = nullptr;
@@ -225,8 +244,8 @@ static int lskge3_mshard_all(int ndev, rb_comm* const* comms, char layout, char 
     for (int g = 0; g < ndev && !rc; ++g) {                 // partial products: asynchronous, one stream per GPU
         RB_REQUIRE(comms[g] != nullptr && comms[g]->nranks == ndev && comms[g]->rank == g);
         cudaSetDevice(comms[g]->device);
-        rc = mshard_local<T>(comms[g], layout, opS, opA, d, n, m_total, alpha, D_rows, D_cols, family, axis, ctr, key, ro_s,
-                             co_s, A_local[g], lda[g], mode, streams ? (cudaStream_t) streams[g] : nullptr, &W[g]);
+        rc = mshard_local<T>(comms[g], layout, opS, opA, d, n, m_total, alpha, op, ro_s, co_s, A_local[g], lda[g], mode,
+                             streams ? (cudaStream_t) streams[g] : nullptr, &W[g]);
     }
     if (!rc && ndev > 1) {
         ncclResult_t r = nc->GroupStart();
@@ -341,16 +360,37 @@ int rb_mshard_block(int64_t m_total, int nranks, int rank, int64_t* start, int64
                                T alpha, int64_t D_rows, int64_t D_cols, char family, char major_axis,                    \
                                const uint32_t ctr[4], const uint32_t key[2], int64_t ro_s, int64_t co_s,                 \
                                const T* A_local, int64_t lda, T beta, T* B_out, int mode, void* stream) {                \
-        return lskge3_mshard<T>(comm, layout, opS, opA, d, n, m_total, alpha, D_rows, D_cols, family, major_axis, ctr,   \
-                                key, ro_s, co_s, A_local, lda, beta, B_out, mode, stream);                               \
+        const ShardOp op{D_rows, D_cols, family, major_axis, 0, ctr, key};                                               \
+        return lskge3_mshard<T>(comm, layout, opS, opA, d, n, m_total, alpha, op, ro_s, co_s, A_local, lda, beta, B_out, \
+                                mode, stream);                                                                           \
     }                                                                                                                    \
     int rb_lskge3_mshard_all_##sfx(int ndev, const rb_comm_t* comms, char layout, char opS, char opA, int64_t d,         \
                                    int64_t n, int64_t m_total, T alpha, int64_t D_rows, int64_t D_cols, char family,     \
                                    char major_axis, const uint32_t ctr[4], const uint32_t key[2], int64_t ro_s,          \
                                    int64_t co_s, const T* const* A_local, const int64_t* lda, T beta, T* const* B_out,   \
                                    int mode, void* const* streams) {                                                     \
-        return lskge3_mshard_all<T>(ndev, comms, layout, opS, opA, d, n, m_total, alpha, D_rows, D_cols, family,         \
-                                    major_axis, ctr, key, ro_s, co_s, A_local, lda, beta, B_out, mode, streams);         \
+        const ShardOp op{D_rows, D_cols, family, major_axis, 0, ctr, key};                                               \
+        return lskge3_mshard_all<T>(ndev, comms, layout, opS, opA, d, n, m_total, alpha, op, ro_s, co_s, A_local, lda,   \
+                                    beta, B_out, mode, streams);                                                         \
+    }                                                                                                                    \
+    int rb_lskges_mshard_##sfx(rb_comm_t comm, char layout, char opS, char opA, int64_t d, int64_t n, int64_t m_total,   \
+                               T alpha, int64_t D_rows, int64_t D_cols, int64_t vec_nnz, const uint32_t ctr[4],          \
+                               const uint32_t key[2], int64_t ro_s, int64_t co_s, const T* A_local, int64_t lda, T beta, \
+                               T* B_out, int mode, void* stream) {                                                       \
+        RB_REQUIRE(vec_nnz >= 1);                                                                                        \
+        const ShardOp op{D_rows, D_cols, 'U', 'S', vec_nnz, ctr, key};                                                   \
+        return lskge3_mshard<T>(comm, layout, opS, opA, d, n, m_total, alpha, op, ro_s, co_s, A_local, lda, beta, B_out, \
+                                mode, stream);                                                                           \
+    }                                                                                                                    \
+    int rb_lskges_mshard_all_##sfx(int ndev, const rb_comm_t* comms, char layout, char opS, char opA, int64_t d,         \
+                                   int64_t n, int64_t m_total, T alpha, int64_t D_rows, int64_t D_cols, int64_t vec_nnz, \
+                                   const uint32_t ctr[4], const uint32_t key[2], int64_t ro_s, int64_t co_s,             \
+                                   const T* const* A_local, const int64_t* lda, T beta, T* const* B_out, int mode,       \
+                                   void* const* streams) {                                                               \
+        RB_REQUIRE(vec_nnz >= 1);                                                                                        \
+        const ShardOp op{D_rows, D_cols, 'U', 'S', vec_nnz, ctr, key};                                                   \
+        return lskge3_mshard_all<T>(ndev, comms, layout, opS, opA, d, n, m_total, alpha, op, ro_s, co_s, A_local, lda,   \
+                                    beta, B_out, mode, streams);                                                         \
     }
 RB_DEF_MSHARD(float, f32)
 RB_DEF_MSHARD(double, f64)

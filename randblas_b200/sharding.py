@@ -79,6 +79,8 @@ def lskge3_mshard(comm, layout, opS, opA, d, n, m_total, alpha, S, ro_s, co_s, A
     op(A) sharded over the ranks of `comm` (this rank holds rows block(m_total, rank, nranks) as A_local).
     mode 0: reduce-scatter, B_out has d*n/nranks entries (this rank's slice of the packed result);
     mode 1: all-reduce, B_out has d*n entries. Device buffers only; asynchronous on the current stream."""
+    if isinstance(S, api.SparseSkOp):
+        return lskges_mshard(comm, layout, opS, opA, d, n, m_total, alpha, S, ro_s, co_s, A_local, lda, beta, B_out, mode)
     if not isinstance(S, api.DenseSkOp) or S.buff is not None:
         raise RandBLASError("lskge3_mshard takes an unfilled DenseSkOp (the operator columns are regenerated per rank)")
     dt = api._same_dtype(A_local, B_out)
@@ -86,6 +88,19 @@ def lskge3_mshard(comm, layout, opS, opA, d, n, m_total, alpha, S, ro_s, co_s, A
     seed, D = S.seed_state, S.dist
     call(f"rb_lskge3_mshard_{sfx}", "pcccqqq" + t + "qqccpp" + "qqpq" + t + "pip", comm._h.value, layout, opS, opA, int(d), int(n),
          int(m_total), alpha, D.n_rows, D.n_cols, D.family, D.major_axis, seed._c(), seed._k(), int(ro_s), int(co_s),
+         api._ptr(A_local), int(lda), beta, api._ptr(B_out), int(mode), api._stream(A_local, B_out))
+
+
+def lskges_mshard(comm, layout, opS, opA, d, n, m_total, alpha, S, ro_s, co_s, A_local, lda, beta, B_out, mode=0):
+    """rb_lskges_mshard_{f32,f64}: lskge3_mshard for an unsampled SASO SparseSkOp (Axis::Short): every rank regenerates the
+    minor-axis vectors of S that meet its rows of op(A); same modes, same buffers."""
+    if not isinstance(S, api.SparseSkOp) or S.nnz >= 0 or S.dist.major_axis != "S":
+        raise RandBLASError("lskges_mshard takes an unsampled SASO SparseSkOp (the operator is regenerated per rank)")
+    dt = api._same_dtype(A_local, B_out)
+    sfx, t = api._sfx(dt)
+    seed, D = S.seed_state, S.dist
+    call(f"rb_lskges_mshard_{sfx}", "pcccqqq" + t + "qqqpp" + "qqpq" + t + "pip", comm._h.value, layout, opS, opA, int(d), int(n),
+         int(m_total), alpha, D.n_rows, D.n_cols, D.vec_nnz, seed._c(), seed._k(), int(ro_s), int(co_s),
          api._ptr(A_local), int(lda), beta, api._ptr(B_out), int(mode), api._stream(A_local, B_out))
 
 

@@ -341,6 +341,25 @@ static void multi_gpu_checks() {
             CHECK(std::sqrt(num / den) < tol);
         }
     }
+    // the same data against an unsampled SASO operator (sparse::lskges per GPU, same collective)
+    {
+        SparseSkOp<T> Ssp(SparseDist(d, m, 4), seed);
+        std::vector<T> Bsp(d * n, T(0));
+        sketch_general(blas::Layout::RowMajor, blas::Op::NoTrans, blas::Op::NoTrans, d, n, m, T(1), Ssp, 0, 0, A.data(), n, T(0),
+                       Bsp.data(), n);
+        sketch_general_mshard(comms, blas::Layout::RowMajor, blas::Op::NoTrans, blas::Op::NoTrans, d, n, m, T(1), Ssp, 0, 0,
+                              cA.data(), lda.data(), T(0), dB.data(), Reduce::All);
+        for (int g = 0; g < nd; ++g) {
+            cudaSetDevice(comms.device(g));
+            cudaDeviceSynchronize();
+            std::vector<T> got((size_t) (d * n));
+            cudaMemcpy(got.data(), dB[g], sizeof(T) * (size_t) (d * n), cudaMemcpyDeviceToHost);
+            double num = 0, den = 0;
+            for (int64_t i = 0; i < d * n; ++i) { double e = (double) got[i] - (double) Bsp[i]; num += e * e; den += (double) Bsp[i] * Bsp[i]; }
+            CHECK(std::sqrt(num / den) < tol);
+        }
+        CHECK(Ssp.nnz < 0);                                     // the operator was not sampled by either call
+    }
     for (int g = 0; g < nd; ++g) { cudaSetDevice(comms.device(g)); cudaFree(dA[g]); cudaFree(dB[g]); }
     cudaSetDevice(0);
     // a filled operator is refused, as is a communicator array of the wrong size

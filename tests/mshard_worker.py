@@ -89,6 +89,45 @@ def main():
         worst[(np.dtype(dt).name, fam, d, n, m, layout)] = (float(errs.max().item()), e_ref)
         assert float(errs.max().item()) < tol, (dt, d, n, m, layout, errs.tolist())
         assert e_ref < tol, (dt, d, n, m, layout, e_ref)
+    # SASO operators through rb_lskges_mshard_* ("SASO apply, m-sharded"): a ragged small case and a block of
+    # BASELINE.json configs[3] (d=2048, n=256, vec_nnz 8) with 100000 rows per rank
+    for (dt, d, n, m, k, layout, tol) in [(np.float64, 64, 12 * world, 4099, 4, "C", 1e-12),
+                                            (np.float32, 2048, 256, 100000 * world, 8, "R", 1e-5)]:
+        tdt = torch.float32 if dt == np.float32 else torch.float64
+        Afull = torch.empty(m * n, dtype=tdt, device="cuda")
+        rb.fill_dense_unpacked("C", rb.DenseDist(m, n), m, n, 0, 0, Afull, rb.RNGState(99))     # ColMajor, lda = m
+        A2 = Afull.view(n, m).t()
+        start, count = block(m, rank, world, 4)
+        if layout == "C":
+            Aloc = A2[start:start + count, :].t().contiguous().view(-1)
+            lda_loc, lda_full, Ause, ldb = max(count, 1), m, Afull, d
+        else:
+            Aloc = A2[start:start + count, :].contiguous().view(-1)
+            lda_loc, lda_full, Ause, ldb = n, n, A2.contiguous().view(-1), n
+        S = rb.SparseSkOp(rb.SparseDist(d, m, k), rb.RNGState(1997), dtype=dt)
+        Bone = torch.zeros(d * n, dtype=tdt, device="cuda")
+        rb.sketch_general(layout, "N", "N", d, n, m, 1.0, S, 0, 0, Ause, lda_full, 0.0, Bone, ldb)
+        cnt = d * n // world
+        Bshard = torch.full((cnt,), float("nan"), dtype=tdt, device="cuda")
+        lskge3_mshard(comm, layout, "N", "N", d, n, m, 1.0, S, 0, 0, Aloc, lda_loc, 0.0, Bshard, mode=0)
+        B0 = torch.arange(d * n, dtype=tdt, device="cuda") / (d * n)
+        Ball = B0.clone()
+        lskge3_mshard(comm, layout, "N", "N", d, n, m, 2.0, S, 0, 0, Aloc, lda_loc, -0.5, Ball, mode=1)
+        torch.cuda.synchronize()
+        e0 = relerr(Bshard.cpu().numpy(), Bone[rank * cnt:(rank + 1) * cnt].cpu().numpy())
+        e1 = relerr(Ball.cpu().numpy(), (2.0 * Bone - 0.5 * B0).cpu().numpy())
+        errs = torch.tensor([e0, e1], dtype=torch.float64, device="cuda")
+        dist.all_reduce(errs, op=dist.ReduceOp.MAX)
+        e_ref = 0.0
+        if rank == 0:
+            want = B0.cpu().numpy().copy()
+            ref.lskges(layout, "N", "N", d, n, m, dt(2.0), (d, m, k, "S"), ctr, key, 0, 0, Ause.cpu().numpy(), lda_full,
+                       dt(-0.5), want, ldb)
+            e_ref = relerr(Ball.cpu().numpy(), want)
+        worst[("saso", np.dtype(dt).name, d, n, m, k, layout)] = (float(errs.max().item()), e_ref)
+        assert float(errs.max().item()) < tol, ("saso", dt, d, n, m, errs.tolist())
+        assert e_ref < tol, ("saso", dt, d, n, m, e_ref)
+        assert S.nnz < 0
     dist.barrier()
     if rank == 0:
         for k, v in worst.items():

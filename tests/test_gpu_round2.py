@@ -323,6 +323,26 @@ def test_mshard_entry_point_one_rank(gpu, ref, dt):
             lskge3_mshard(comm, layout, opS, opA, d, n, m, 1.5, S, ro, co, torch.from_numpy(A).cuda(), lda, beta, Bd, mode)
             torch.cuda.synchronize()
             assert relerr(Bd.cpu().numpy(), want) < tol, (layout, opS, opA, mode, beta)
+    # rb_lskges_mshard_*: the same entry point for an unsampled SASO operator
+    from randblas_b200.sharding import lskges_mshard
+    for layout, opS, k in (("C", "N", 4), ("R", "N", 8), ("C", "T", 3)):
+        d, n, m, ro, co = 48, 20, 1003, 0, 6
+        Dr, Dc = (d, m + 9) if opS == "N" else (m + 9, d)
+        lda = m if layout == "C" else n
+        ldb = d if layout == "C" else n
+        A = rng.standard_normal(m * n).astype(dt)
+        B0 = rng.standard_normal(d * n).astype(dt)
+        S = rb.SparseSkOp(rb.SparseDist(Dr, Dc, k), rb.RNGState(1997), dtype=dt)
+        for mode, beta in ((0, 0.0), (1, -0.5)):
+            want = B0.copy()
+            ref.lskges(layout, opS, "N", d, n, m, dt(1.5), (Dr, Dc, k, "S"), ctr, key, ro if opS == "N" else co,
+                       co if opS == "N" else ro, A, lda, dt(beta), want, ldb)
+            Bd = torch.from_numpy(B0.copy()).cuda()
+            lskges_mshard(comm, layout, opS, "N", d, n, m, 1.5, S, ro if opS == "N" else co, co if opS == "N" else ro,
+                          torch.from_numpy(A).cuda(), lda, beta, Bd, mode)
+            torch.cuda.synchronize()
+            assert relerr(Bd.cpu().numpy(), want) < tol, ("saso", layout, opS, k, mode, beta)
+        assert S.nnz < 0
     comm.destroy()
 
 
