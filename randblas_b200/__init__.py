@@ -11,4 +11,4 @@ from .api import (Axis, COOMatrix, CSCMatrix, CSRMatrix, DenseDist, DenseSkOp, L
                   sketch_symmetric, sample_indices_iid, sample_indices_iid_uniform, weights_to_cdf,
                   random_coo, random_csr, random_csc, sorted_idxs_to_compressed_ptr, csr_column_block,
                   csc_column_block)
-from ._lib import RandBLASError, counter, get_option, set_option  # noqa
+from ._lib import RandBLASError, counter, get_option, release_workspace, set_option  # noqa

@@ -70,3 +70,11 @@ def set_option(name, value):
     fn.restype = ctypes.c_int
     if fn(ctypes.c_char_p(name.encode()), ctypes.c_int64(int(value))) != 0:
         raise RandBLASError(lib().rb_last_error().decode(errors="replace"))
+
+
+def release_workspace():
+    """rb_release_workspace: frees every cached scratch buffer of the library (no call may be in flight)."""
+    fn = lib().rb_release_workspace
+    fn.restype = ctypes.c_int
+    if fn() != 0:
+        raise RandBLASError(lib().rb_last_error().decode(errors="replace"))

@@ -731,7 +731,7 @@ static int dense_tc_f32_via_panel(const DenseProblem<float>& p, bool x_t, cudaSt
     if (kp > p.K) kp = (p.K + 3) / 4 * 4;
     const int64_t ld = kp;
     float* panel = (float*) workspace(5, (size_t) p.P * (size_t) ld * sizeof(float), st);
-    if (!panel) return fail_cuda(cudaErrorMemoryAllocation, "operator panel workspace");
+    if (!panel) return -2;                          // no room for the scratch panel: the caller runs the fused kernel
     for (int64_t k0 = 0; k0 < p.K; k0 += kp) {
         const int64_t kc = (p.K - k0 < kp) ? p.K - k0 : kp;
         int rc;
@@ -781,8 +781,10 @@ int launch_dense_tc_f32(const DenseProblem<float>& p, cudaStream_t st) {
     if (tiles_p > 65535 || tiles_q > 0x7fffffff) return -1;
     {
         const int64_t mat_opt = get_option("tc_materialise");
-        if (!xmat && p.family == 'G' && (mat_opt == 2 || (mat_opt == 1 && tiles_q >= 2)) && p.K >= 64)
-            return dense_tc_f32_via_panel(p, x_t, st);
+        if (!xmat && p.family == 'G' && (mat_opt == 2 || (mat_opt == 1 && tiles_q >= 2)) && p.K >= 64) {
+            const int prc = dense_tc_f32_via_panel(p, x_t, st);
+            if (prc != -2) return prc;                  // -2: no memory for the panel, run fused
+        }
     }
     const int kshift = x_t ? 0 : (int) (p.u0 & 3);
     const int64_t steps = (p.K + BK - 1) / BK;

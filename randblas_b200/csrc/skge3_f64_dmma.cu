@@ -394,7 +394,7 @@ static int dense_dmma_f64_via_panel(const DenseProblem<double>& p, bool x_t, cud
     if (kp > p.K) kp = (p.K + 1) / 2 * 2;
     const int64_t ld = kp;
     double* panel = (double*) workspace(5, (size_t) p.P * (size_t) ld * sizeof(double), st);
-    if (!panel) return fail_cuda(cudaErrorMemoryAllocation, "operator panel workspace");
+    if (!panel) return -2;                          // no room for the scratch panel: the caller runs the fused kernel
     for (int64_t k0 = 0; k0 < p.K; k0 += kp) {
         const int64_t kc = (p.K - k0 < kp) ? p.K - k0 : kp;
         int rc;
@@ -434,8 +434,10 @@ int launch_dense_dmma_f64(const DenseProblem<double>& p, cudaStream_t st) {
     if (tiles_p > 65535 || tiles_q > 0x7fffffff) return -1;
     const int64_t steps = (p.K + DK - 1) / DK;
     if (steps > 0x7fffffff) return -1;
-    if (!xmat && p.family == 'G' && get_option("dmma_materialise") != 0 && p.K >= 4096)
-        return dense_dmma_f64_via_panel(p, x_t, st);
+    if (!xmat && p.family == 'G' && get_option("dmma_materialise") != 0 && p.K >= 4096) {
+        const int prc = dense_dmma_f64_via_panel(p, x_t, st);
+        if (prc != -2) return prc;                      // -2: no memory for the panel, run fused
+    }
     const int64_t tiles = tiles_p * tiles_q;
     const int sms = sm_count();
     // split K only to fill the SMs: pick the split count (<= 16) with the best wave efficiency

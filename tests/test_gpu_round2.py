@@ -545,6 +545,37 @@ def test_reference_componentwise_bound_dense_and_sparse_operators(gpu, port, dt)
         check(Br.reshape(d, n), S, A, alpha, beta, B0, m, ("saso", d, n, m, k))
 
 
+def test_panel_path_falls_back_to_fused_kernel_without_memory():
+    """The scratch panel of a Gaussian double operator (2 GB here) is an optimisation: when it cannot be allocated the
+    call runs the fused kernel instead of failing. Memory is taken away with a torch allocation; the result must equal
+    the fused kernel's (same kernel, bit for bit) and the launch counter must show ONE tensor-core launch, not panels."""
+    import torch
+    import randblas_b200 as rb
+    d, n, m = 4096, 64, 65536
+    A = torch.randn(m * n, dtype=torch.float64, device="cuda")
+    S = rb.DenseSkOp(rb.DenseDist(d, m), rb.RNGState(11), np.float64)
+    rb.set_option("dmma_materialise", 0)
+    Bf = torch.zeros(d * n, dtype=torch.float64, device="cuda")
+    rb.sketch_general("C", "N", "N", d, n, m, 1.0, S, 0, 0, A, m, 0.0, Bf, d)
+    torch.cuda.synchronize()
+    rb.set_option("dmma_materialise", 1)
+    rb.release_workspace()
+    torch.cuda.empty_cache()
+    free, _ = torch.cuda.mem_get_info()
+    hog = torch.empty(max(free - (1200 << 20), 0), dtype=torch.uint8, device="cuda")      # leaves ~1.2 GB: no 2 GB panel
+    try:
+        Bp = torch.zeros(d * n, dtype=torch.float64, device="cuda")
+        before = rb.counter("tensor_core_launches")
+        rb.sketch_general("C", "N", "N", d, n, m, 1.0, S, 0, 0, A, m, 0.0, Bp, d)
+        torch.cuda.synchronize()
+        assert rb.counter("tensor_core_launches") == before + 1
+        assert torch.equal(Bp, Bf)
+    finally:
+        del hog
+        torch.cuda.empty_cache()
+        rb.release_workspace()
+
+
 # ------------------------------------------------------------------------------ SASO apply, double
 def test_saso_binned_kernel_double_vs_oracle(gpu, port):
     """The register-tile SASO apply (saso_binned.cu) instantiated for double (16 columns of C per CTA = the same 128 bytes
