@@ -415,6 +415,16 @@ def test_example_sparse_low_rank_qb_recovers_planted_vectors():
     torch.cuda.synchronize()
 
 
+def test_example_spmm_performance_formats_agree():
+    """examples/spmm_performance.py (the reference's examples/simple-kernel-benchmarks/spmm_performance.cc): COO, CSR and CSC
+    forms of one random sparse matrix through left_spmm and right_spmm give the same product as densify + GEMM (the example
+    asserts 1e-12 between formats itself); every timing is positive."""
+    ex = _load_example("spmm_performance")
+    for (m, n, d, dens) in ((500, 500, 500, 0.01), (2000, 300, 64, 0.02), (300, 2000, 64, 0.02)):
+        out = ex.run_config(m, n, d, dens, trials=2, verbose=False)
+        assert out["nnz"] > 0 and all(v > 0 for k, v in out.items() if k != "nnz")
+
+
 # ------------------------------------------------------------------------------ Axis::Short operators on tensor cores
 @pytest.mark.parametrize("dt", [np.float32, np.float64])
 def test_short_axis_operators_on_tensor_cores_vs_oracle(gpu, port, dt):
