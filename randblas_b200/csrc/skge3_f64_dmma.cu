@@ -92,11 +92,11 @@ __device__ __forceinline__ void cp_async16(void* dst, const void* src, int src_b
 // YMN: Y is contiguous along Q (left sketch of RowMajor data, right sketch of ColMajor data); the tile is staged as
 // [k][q] and the B fragments are read across rows.
 // ---- the kernel: warp-specialised ------------------------------------------------------------------------------
-// 12 warps: warps 0-3 (one per scheduler) only GENERATE the S tile of every stage; warps 4-11 (two per scheduler) issue
-// the DMMAs and, between two steps, the cp.async copies of the Y tile two steps ahead (8 per thread). A DMMA warp never
-// leaves its DMMA stream, the producer warp of a scheduler fills the issue slots between DMMAs. Register split with
-// setmaxnreg: producers 72, DMMA warps 216. (A first design in which every warp generated and multiplied ran at 72.9-83.6 ms
-// on the C3 shard instead of 69.4)
+// 12 warps: warps 0-3 (one per scheduler) only PRODUCE the S tile of every stage (generated, or copied from a materialised
+// operator); warps 4-11 (two per scheduler) issue the DMMAs and, spread through the second half of each stage, the
+// cp.async copies of the Y tile two steps ahead (8 per thread). A DMMA warp never leaves its DMMA stream for long, the
+// producer warp of a scheduler fills the issue slots between DMMAs. Register split with setmaxnreg: producers 72, DMMA
+// warps 216. History of the design and what each step measured: DESIGN.md section 4 (K2b).
 #ifndef RB_DMMA_PROD_WARPS
 #define RB_DMMA_PROD_WARPS 4      // producer warps per CTA: one per scheduler (8 measured: no better)
 #endif
