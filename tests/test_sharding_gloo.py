@@ -34,7 +34,7 @@ def test_block_partition_properties():
     assert max(sizes) - min(sizes) <= 4
 
 
-def _worker(rank, world, port_no, d, n, m, tmpdir):
+def _worker(rank, world, port_no, d, n, m, tmpdir, kind="dense"):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port_no)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -48,11 +48,13 @@ def _worker(rank, world, port_no, d, n, m, tmpdir):
         start, count = block(m, rank, world, 4)
 
         class Op:                                             # what the injected sketch needs to know about S
-            dist_t = (d, m, "G", "L")
+            dist_t = (d, m, "G", "L") if kind == "dense" else (d, m, 3, "S")      # DenseDist / SASO SparseDist, vec_nnz 3
+
+        sketch = port.lskge3 if kind == "dense" else port.lskges
 
         def local_sketch(layout, opS, opA, d_, n_, m_, alpha, S, ro_s, co_s, A_loc, lda, beta, B, ldb):
-            port.lskge3(layout, opS, opA, d_, n_, m_, float(alpha), S.dist_t, ctr, key, ro_s, co_s, A_loc.numpy(), lda,
-                        float(beta), B.numpy(), ldb)
+            sketch(layout, opS, opA, d_, n_, m_, float(alpha), S.dist_t, ctr, key, ro_s, co_s, A_loc.numpy(), lda,
+                   float(beta), B.numpy(), ldb)
 
         # ColMajor local block: rows [start, start+count) of A, leading dimension = count
         A_loc = torch.from_numpy(np.ascontiguousarray(A[start:start + count, :].T).ravel().copy())
@@ -65,8 +67,7 @@ def _worker(rank, world, port_no, d, n, m, tmpdir):
         if rank == 0:
             got = torch.cat(gathered).numpy()
             want = np.zeros(d * n)
-            port.lskge3("C", "N", "N", d, n, m, 1.0, (d, m, "G", "L"), ctr, key, 0, 0,
-                        np.ascontiguousarray(A.T).ravel(), m, 0.0, want, d)
+            sketch("C", "N", "N", d, n, m, 1.0, Op.dist_t, ctr, key, 0, 0, np.ascontiguousarray(A.T).ravel(), m, 0.0, want, d)
             err = np.linalg.norm(got - want) / np.linalg.norm(want)
             with open(os.path.join(tmpdir, "result.txt"), "w") as f:
                 f.write(repr(float(err)))
@@ -74,10 +75,10 @@ def _worker(rank, world, port_no, d, n, m, tmpdir):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world", [2, 3])
-def test_m_sharded_left_sketch_reduce_scatter(world, tmp_path):
+@pytest.mark.parametrize("world,kind", [(2, "dense"), (3, "dense"), (2, "saso")])
+def test_m_sharded_left_sketch_reduce_scatter(world, kind, tmp_path):
     d, n, m = 12, 6 * world, 203                 # d*n divisible by world; m not a multiple of 4 * world
-    port_no = 29500 + (os.getpid() % 2000) + world
-    mp.spawn(_worker, args=(world, port_no, d, n, m, str(tmp_path)), nprocs=world, join=True)
+    port_no = 29500 + (os.getpid() % 2000) + world + (7 if kind == "saso" else 0)
+    mp.spawn(_worker, args=(world, port_no, d, n, m, str(tmp_path), kind), nprocs=world, join=True)
     err = float(open(tmp_path / "result.txt").read())
     assert err < 1e-12, err
