@@ -69,7 +69,9 @@ struct TcArgs {
     int kshift;        // u0 & 3: when non-zero every 4-wide chunk of X straddles two Philox blocks
     int64_t P, Q;
     int steps_total;   // ceil(K / 32)
-    int y_mn;          // 1: Y is Q-contiguous; raw tiles are transposed by the generator warps
+    int y_mn;          // Y is Q-contiguous: 2 = its tiles go to the tensor core as they are (MN-major B operand, TMA boxes of
+                       // 32 q x 32 k with the 32-byte-atom 128B swizzle); 1 = raw tiles transposed by the generator warps (round 2's
+                       // first form, "tc_ymn" = 1); 0 = Y is K-contiguous
     int x_t;           // 1: the operator's Philox blocks run along the ROWS of X (Axis::Short operators, transposed use of a
                        //    Long one): a block is 4 consecutive rows of one column k; v0 then counts along k, ublk0 along i
     int splits;
@@ -169,14 +171,23 @@ __device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int c0, 
 __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t addr) {
     return (uint64_t) ((addr >> 4) & 0x3fffu) | (1ull << 16) | ((uint64_t) (1024u >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
-// kind::tf32, fp32 accumulate, both operands K-major, M = 128, N = 256
+// MN-major (contiguous along N) B operand, tf32: the only shared-memory layout the tensor core takes is the 128B swizzle with
+// 32-byte atoms (cute: SWIZZLE_128B_BASE32B, Swizzle<2,5,2>; TMA: CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B): rows of 128 bytes = 32
+// consecutive columns of one k, the 32-byte chunk index XORed with (k & 3), atoms of 4 k rows. Leading byte offset = distance
+// between two 32-column blocks (one TMA box of 32 k rows: 4096), stride byte offset = distance between the two 4-row atoms of a
+// K = 8 instruction (512). Probed in isolation first: tools/micro/mn_major_probe.cu (the plain 128B swizzle returns garbage).
+__device__ __forceinline__ uint64_t smem_desc_mn32(uint32_t addr) {
+    return (uint64_t) ((addr >> 4) & 0x3fffu) | ((uint64_t) (4096u >> 4) << 16) | ((uint64_t) (512u >> 4) << 32) | (1ull << 46) | (1ull << 61);
+}
+// kind::tf32, fp32 accumulate, both operands K-major, M = 128, N = 256; IDESC_B_MN: the B operand is MN-major
 constexpr uint32_t IDESC_TF32 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t) (BN >> 3) << 17) | ((uint32_t) (BM >> 4) << 24);
+constexpr uint32_t IDESC_B_MN = 1u << 16;
 
-__device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t da, uint64_t db, uint32_t accumulate) {
+__device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t da, uint64_t db, uint32_t accumulate, uint32_t idesc = IDESC_TF32) {
     asm volatile(
         "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(d_tmem), "l"(da), "l"(db), "r"(IDESC_TF32), "r"(accumulate)
+        ::"r"(d_tmem), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
         : "memory");
 }
 __device__ __forceinline__ void mma_commit(uint32_t bar) {
@@ -187,11 +198,12 @@ __device__ __forceinline__ void mma_commit(uint32_t bar) {
 // accumulator and HALF of the Y tile (128 of the 256 columns), so per SM and K step the tensor core reads half the Y
 // bytes, TMA writes half and the generators split half (shared-memory port: 176 KB per step instead of 272).
 constexpr uint32_t IDESC_TF32_PAIR = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t) (BN >> 3) << 17) | ((uint32_t) ((2 * BM) >> 4) << 24);
-__device__ __forceinline__ void mma_tf32_pair(uint32_t d_tmem, uint64_t da, uint64_t db, uint32_t accumulate) {
+__device__ __forceinline__ void mma_tf32_pair(uint32_t d_tmem, uint64_t da, uint64_t db, uint32_t accumulate,
+                                              uint32_t idesc = IDESC_TF32_PAIR) {
     asm volatile(
         "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(d_tmem), "l"(da), "l"(db), "r"(IDESC_TF32_PAIR), "r"(accumulate)
+        ::"r"(d_tmem), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
         : "memory");
 }
 // commit of the pair's MMAs, arriving on the barrier at this offset in BOTH CTAs
@@ -331,27 +343,29 @@ __global__ void __launch_bounds__(TC_THREADS, 1) skge3_tc_kernel(const __grid_co
     if (warp == 0) {
         if (lane == 0) {
             constexpr int PF = 6;
-            if (!a.y_mn) {
+            if (a.y_mn != 1) {
                 const int jy = (int) j0 + (PAIR ? (int) crank * (BN / 2) : 0);      // first column this CTA loads
-                for (int it = 0; it < min(PF, nsteps); ++it) tma_prefetch_2d(&tmY, (s_begin + it) * BK, jy);
+                constexpr int NBOX = (PAIR ? BN / 2 : BN) / 32;                     // y_mn == 2: boxes of 32 columns x 32 k
+                // K-contiguous Y: one box of 32 k x (this CTA's columns); Q-contiguous Y (2): NBOX boxes, 4096 bytes apart
+                auto prefetch_y = [&](int step) {
+                    if (a.y_mn == 0) { tma_prefetch_2d(&tmY, step * BK, jy); return; }
+                    for (int b = 0; b < NBOX; ++b) tma_prefetch_2d(&tmY, jy + 32 * b, step * BK);
+                };
+                auto load_y = [&](uint32_t dst, uint32_t bar, int step) {
+                    if (a.y_mn == 0) { tma_load_2d(dst, &tmY, bar, step * BK, jy); return; }
+                    for (int b = 0; b < NBOX; ++b) tma_load_2d(dst + 4096u * (uint32_t) b, &tmY, bar, jy + 32 * b, step * BK);
+                };
+                for (int it = 0; it < min(PF, nsteps); ++it) prefetch_y(s_begin + it);
                 for (int it = 0; it < nsteps; ++it) {
                     const int st = it % NST;
                     const uint32_t ph = (it / NST) & 1;
-                    if (it + PF < nsteps) tma_prefetch_2d(&tmY, (s_begin + it + PF) * BK, jy);
+                    if (it + PF < nsteps) prefetch_y(s_begin + it + PF);
                     mbar_wait(bar_empty(st), ph ^ 1);
-                    if constexpr (PAIR) {
-                        // this CTA's 128 columns of the tile (the tensor map's box is 32 k x 128 columns in this mode)
-                        mbar_arrive_expect_tx(bar_full(st), XMAT ? YB + X_BYTES : YB);
-                        tma_load_2d(base + st * SB + 2 * X_BYTES, &tmY, bar_full(st), (s_begin + it) * BK, jy);
-                        if constexpr (XMAT)         // this CTA's own 128 rows of the materialised operator
-                            tma_load_2d(base + st * SB, &tmX, bar_full(st), (int) a.xk0 + (s_begin + it) * BK, (int) (a.xr0 + i0));
-                        continue;
-                    }
-                    mbar_arrive_expect_tx(bar_full(st), XMAT ? Y_BYTES + X_BYTES : Y_BYTES);
-                    tma_load_2d(base + st * SB + 2 * X_BYTES, &tmY, bar_full(st), (s_begin + it) * BK, (int) j0);
+                    // PAIR: this CTA's 128 columns of the tile and its own 128 rows of a materialised operator
+                    mbar_arrive_expect_tx(bar_full(st), XMAT ? YB + X_BYTES : YB);
+                    load_y(base + st * SB + 2 * X_BYTES, bar_full(st), s_begin + it);
                     if constexpr (XMAT)
-                        tma_load_2d(base + st * SB, &tmX, bar_full(st), (int) a.xk0 + (s_begin + it) * BK,
-                                    (int) (a.xr0 + i0));
+                        tma_load_2d(base + st * SB, &tmX, bar_full(st), (int) a.xk0 + (s_begin + it) * BK, (int) (a.xr0 + i0));
                 }
             } else {
                 // tensor map (Q, K), box 256 q (128 for a CTA of a pair) x RAW_K k, no swizzle: one raw tile in flight
@@ -384,18 +398,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) skge3_tc_kernel(const __grid_co
                     // both CTAs' generator warps arrive here after their X tile, their half of Y (TMA, observed through
                     // their own full barrier) and its low part are in place
                     mbar_wait_cluster(bar_ready(st), ph);
-                    if (XMAT || !a.y_mn) mbar_wait(bar_full(st), ph);
+                    if (XMAT || a.y_mn != 1) mbar_wait(bar_full(st), ph);
                     fence_proxy_async();
                     tc_fence_after();
                     const uint32_t xh = base + st * SB, xl = xh + X_BYTES, yh = xl + X_BYTES, yl = yh + YB;
+                    const bool ymn = a.y_mn == 2;                 // Y tiles MN-major: 8 k rows = 1024 bytes per instruction
+                    const uint32_t idesc = IDESC_TF32_PAIR | (ymn ? IDESC_B_MN : 0u);
 #pragma unroll
                     for (int kk = 0; kk < BK / 8; ++kk) {
                         const uint64_t dxh = smem_desc_sw128(xh + kk * 32), dxl = smem_desc_sw128(xl + kk * 32);
-                        const uint64_t dyh = smem_desc_sw128(yh + kk * 32), dyl = smem_desc_sw128(yl + kk * 32);
+                        const uint64_t dyh = ymn ? smem_desc_mn32(yh + kk * 1024) : smem_desc_sw128(yh + kk * 32);
+                        const uint64_t dyl = ymn ? smem_desc_mn32(yl + kk * 1024) : smem_desc_sw128(yl + kk * 32);
                         const uint32_t acc = (it > 0 || kk > 0) ? 1u : 0u;
-                        mma_tf32_pair(tmem_base + BN, dxl, dyh, acc);
-                        mma_tf32_pair(tmem_base + BN, dxh, dyl, 1u);
-                        mma_tf32_pair(tmem_base, dxh, dyh, acc);
+                        mma_tf32_pair(tmem_base + BN, dxl, dyh, acc, idesc);
+                        mma_tf32_pair(tmem_base + BN, dxh, dyl, 1u, idesc);
+                        mma_tf32_pair(tmem_base, dxh, dyh, acc, idesc);
                     }
                     mma_commit_group2(bar_empty(st));
                 }
@@ -416,18 +433,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) skge3_tc_kernel(const __grid_co
                 const uint32_t ph = (it / NST) & 1;
                 if constexpr (CL > 1) mbar_wait_cluster(bar_ready(st), ph);
                 else mbar_wait(bar_ready(st), ph);
-                if (XMAT || !a.y_mn) mbar_wait(bar_full(st), ph);
+                if (XMAT || a.y_mn != 1) mbar_wait(bar_full(st), ph);
                 if constexpr (CL > 1) fence_proxy_async();     // the peer's generic-proxy stores into this CTA's tiles
                 tc_fence_after();
                 const uint32_t xh = base + st * SB, xl = xh + X_BYTES, yh = xl + X_BYTES, yl = yh + YB;
+                const bool ymn = a.y_mn == 2;
+                const uint32_t idesc = IDESC_TF32 | (ymn ? IDESC_B_MN : 0u);
 #pragma unroll
                 for (int kk = 0; kk < BK / 8; ++kk) {
                     const uint64_t dxh = smem_desc_sw128(xh + kk * 32), dxl = smem_desc_sw128(xl + kk * 32);
-                    const uint64_t dyh = smem_desc_sw128(yh + kk * 32), dyl = smem_desc_sw128(yl + kk * 32);
+                    const uint64_t dyh = ymn ? smem_desc_mn32(yh + kk * 1024) : smem_desc_sw128(yh + kk * 32);
+                    const uint64_t dyl = ymn ? smem_desc_mn32(yl + kk * 1024) : smem_desc_sw128(yl + kk * 32);
                     const uint32_t acc = (it > 0 || kk > 0) ? 1u : 0u;
-                    mma_tf32(tmem_base + BN, dxl, dyh, acc);
-                    mma_tf32(tmem_base + BN, dxh, dyl, 1u);
-                    mma_tf32(tmem_base, dxh, dyh, acc);
+                    mma_tf32(tmem_base + BN, dxl, dyh, acc, idesc);
+                    mma_tf32(tmem_base + BN, dxh, dyl, 1u, idesc);
+                    mma_tf32(tmem_base, dxh, dyh, acc, idesc);
                 }
                 if constexpr (CL > 1) mma_commit_pair(bar_empty(st));
                 else mma_commit(bar_empty(st));
@@ -508,7 +528,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) skge3_tc_kernel(const __grid_co
             const uint32_t ph = (it / NST) & 1;
             uint8_t* stage = smem + st * SB;
             mbar_wait(bar_empty(st), ph ^ 1);
-            if (a.y_mn) {
+            if (a.y_mn == 1) {
                 // transpose the raw Q-contiguous tile into the K-major swizzled Y (the tensor core truncates it to TF32
                 // itself) and Y_lo tiles of this stage, then hand the raw buffer back to the TMA producer
                 const uint8_t* rawt = smem + RAW_OFFSET;
@@ -517,8 +537,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) skge3_tc_kernel(const __grid_co
 #pragma unroll
                 for (int half = 0; half < BK / RAW_K; ++half) {
                     mbar_wait(bar_raw_full, (uint32_t) half);          // raw tile 2 it + half: parity = half
-#pragma unroll
                     constexpr int BNL = PAIR ? BN / 2 : BN;               // columns of the tile held by this CTA
+#pragma unroll
                     for (int q4 = 0; q4 < (BNL * RAW_K / 4) / (32 * GEN_WARPS); ++q4) {
                         const int ch = gt + 32 * GEN_WARPS * q4;
                         const int qq = ch & (BNL - 1), kl = ch / BNL;      // column of the tile, 4-deep k chunk of this half
@@ -606,7 +626,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) skge3_tc_kernel(const __grid_co
             }
             }   // !x_t
             }
-            if (!a.y_mn) {
+            if (a.y_mn != 1) {          // the low part of Y element by element: the same code for K-major and MN-major tiles
             mbar_wait(bar_full(st), ph);
             const uint8_t* ysrc = stage + 2 * X_BYTES;
             uint8_t* ydst = stage + 2 * X_BYTES + YB;
@@ -825,10 +845,15 @@ int launch_dense_tc_f32(const DenseProblem<float>& p, cudaStream_t st) {
     CUtensorMap tm;
     const cuuint64_t gdim[2] = {(cuuint64_t) (y_mn ? p.Q : p.K), (cuuint64_t) (y_mn ? p.K : p.Q)};
     const cuuint64_t gstr[1] = {(cuuint64_t) (y_mn ? p.yrs : p.ycs) * 4ull};
-    const cuuint32_t box[2] = {(cuuint32_t) (y_mn ? (pair ? BN / 2 : BN) : BK), (cuuint32_t) (y_mn ? RAW_K : (pair ? BN / 2 : BN))};
+    // Q-contiguous data: "tc_ymn" 0 (default) = tiles go to the tensor core as they are, as an MN-major operand (boxes of 32 q x
+    // 32 k, 128B swizzle with 32-byte atoms); 1 = the transposing path of the first half of round 2 (raw boxes of 256 q x 16 k)
+    const int ymode = !y_mn ? 0 : (get_option("tc_ymn") == 1 ? 1 : 2);
+    const cuuint32_t box[2] = {(cuuint32_t) (ymode == 2 ? 32 : ymode == 1 ? (pair ? BN / 2 : BN) : BK),
+                               (cuuint32_t) (ymode == 2 ? BK : ymode == 1 ? RAW_K : (pair ? BN / 2 : BN))};
     const cuuint32_t estr[2] = {1, 1};
     CUresult cr = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(p.Y), gdim, gstr, box, estr,
-                      CU_TENSOR_MAP_INTERLEAVE_NONE, y_mn ? CU_TENSOR_MAP_SWIZZLE_NONE : CU_TENSOR_MAP_SWIZZLE_128B,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE,
+                      ymode == 2 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : ymode == 1 ? CU_TENSOR_MAP_SWIZZLE_NONE : CU_TENSOR_MAP_SWIZZLE_128B,
                       CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (cr != CUDA_SUCCESS) return -1;
 
@@ -852,7 +877,7 @@ int launch_dense_tc_f32(const DenseProblem<float>& p, cudaStream_t st) {
     a.ublk0 = p.u0 >> 2;
     a.P = p.P; a.Q = p.Q;
     a.steps_total = (int) steps;
-    a.y_mn = y_mn ? 1 : 0;
+    a.y_mn = ymode;
     a.x_t = x_t ? 1 : 0;
     a.splits = splits;
     a.alpha = p.alpha; a.beta = p.beta;
