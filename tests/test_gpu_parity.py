@@ -821,18 +821,30 @@ def test_tensor_core_float_sketch_vs_oracle(gpu, port):
         assert np.array_equal(B1.reshape(n, d + 1)[:, d], B0.reshape(n, d + 1)[:, d])
 
 
-def test_tensor_core_float_sketch_mn_major_data_vs_oracle(gpu, port):
-    """The tcgen05 kernel with the data matrix as an MN-major operand (contiguous along the non-contracted
-    dimension): left sketch of RowMajor A and right sketch of ColMajor A (A * S, the range-finder call), ragged in all
-    dimensions, windows, both families, alpha/beta. The launch counter proves the tensor-core kernel is what ran."""
+@pytest.mark.parametrize("ymn", [0, 1])
+def test_tensor_core_float_sketch_mn_major_data_vs_oracle(gpu, port, ymn):
+    """The tcgen05 kernel with data contiguous along the non-contracted dimension: left sketch of RowMajor A and right sketch
+    of ColMajor A (A * S, the range-finder call), ragged in all dimensions (tiles that end inside a 32-column TMA box, K
+    tails), windows, both families, alpha/beta, shapes that take CTA pairs and shapes that do not. ymn = 0: tiles fed to the
+    tensor core as an MN-major operand (default); ymn = 1: tiles transposed by the generator warps. The launch counter proves
+    the tensor-core kernel is what ran."""
     import randblas_b200 as rb
+    rb.set_option("tc_ymn", ymn)
+    try:
+        _mn_major_cases(gpu, port, rb)
+    finally:
+        rb.set_option("tc_ymn", 0)
+
+
+def _mn_major_cases(gpu, port, rb):
     rng = np.random.default_rng(6)
     ctr, key = ol.state_from_u64(1997)
     dt = np.float32
     # left, RowMajor: B(d x n) = S(d x m) A(m x n), A row-major with lda = n (multiple of 4)
     for (d, n, m, Dr, Dc, ro, co, fam, alpha, beta) in [(128, 256, 4096, 128, 4096, 0, 0, "U", 1.0, 0.0),
                                                          (200, 300, 5003, 210, 6000, 3, 6, "G", 0.5, -1.5),
-                                                         (64, 600, 777, 64, 800, 0, 8, "U", 1.0, 0.25)]:
+                                                         (64, 600, 777, 64, 800, 0, 8, "U", 1.0, 0.25),
+                                                         (256, 140, 3000, 256, 3000, 0, 0, "U", 2.0, 0.0)]:      # two row tiles: CTA pair
         lda = n + (4 - n % 4) % 4
         A = rng.standard_normal(m * lda).astype(dt)
         B0 = rng.standard_normal(d * (n + 1)).astype(dt)
