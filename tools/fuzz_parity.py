@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Randomised differential test (GPU library against the C oracle): random shapes, layouts, transposes, operator windows,
-leading dimensions, families, axes, alpha / beta and data types for the dense sketch (left and right), the SASO sketch and
-fill_dense windows. Sizes are drawn so that every kernel family is reached (tensor-core float / DMMA double with single
+leading dimensions, families, axes, alpha / beta and data types for the dense sketch (left and right), the SASO sketch,
+sketch_sparse (CSR / CSC / COO, int32 / int64 indices) and fill_dense windows. Sizes are drawn so that every kernel family is reached (tensor-core float / DMMA double with single
 CTAs, CTA pairs, panels; the generic kernels; binned and atomic SASO kernels).
 
     python tools/fuzz_parity.py [seconds] [seed]          prints one line per failure, a summary at the end; exit code 1 on failure
@@ -131,6 +131,54 @@ def fill_case(rng, gpu, port, ctr, key):
     return what, e, ok and list(n1) == list(n2)
 
 
+def sksp_case(rng, gpu, port, ctr, key):
+    import scipy.sparse as sp
+    dt = pick(rng, [np.float32, np.float64])
+    tol = 1e-5 if dt == np.float32 else 1e-12
+    big = rng.random() < 0.4
+    d = int(rng.integers(64, 520)) if big else int(rng.integers(1, 50))
+    n = int(rng.integers(30, 400)) if big else int(rng.integers(1, 60))
+    m = int(rng.integers(500, 5000)) if big else int(rng.integers(1, 200))
+    layout, opS, opA = pick(rng, "CR"), pick(rng, "NT"), pick(rng, "NT")
+    fam, ax, fmt = pick(rng, "GU"), pick(rng, "LS"), int(rng.integers(0, 3))
+    idt = pick(rng, [np.int32, np.int64])
+    left = rng.random() < 0.6
+    ro, co = int(rng.integers(0, 6)), int(rng.integers(0, 6))
+    alpha, beta = pick(rng, [1.0, -0.5]), pick(rng, [0.0, 1.0, -1.5])
+    dens = float(pick(rng, [0.002, 0.02, 0.15]))
+    if left:       # B(d x n) = op(S)(d x m) op(A)(m x n)
+        Dr, Dc = ((d, m) if opS == "N" else (m, d))
+        ra, ca = ((m, n) if opA == "N" else (n, m))
+        rB, cB = d, n
+    else:          # B(m x d) = op(A)(m x n) op(S)(n x d)
+        Dr, Dc = ((n, d) if opS == "N" else (d, n))
+        ra, ca = ((m, n) if opA == "N" else (n, m))
+        rB, cB = m, d
+    Dr, Dc = Dr + ro + int(rng.integers(0, 4)), Dc + co + int(rng.integers(0, 4))
+    M = sp.random(ra, ca, density=dens, random_state=int(rng.integers(1 << 30)), dtype=np.float64)
+    if fmt == 0:
+        Mc = M.tocsr(); Mc.sort_indices()
+        spA = (ra, ca, Mc.nnz, Mc.data.astype(dt), Mc.indptr.astype(np.int64), Mc.indices.astype(np.int64))
+    elif fmt == 1:
+        Mc = M.tocsc(); Mc.sort_indices()
+        spA = (ra, ca, Mc.nnz, Mc.data.astype(dt), Mc.indices.astype(np.int64), Mc.indptr.astype(np.int64))
+    else:
+        Mc = M.tocoo()
+        spA = (ra, ca, Mc.nnz, Mc.data.astype(dt), Mc.row.astype(np.int64), Mc.col.astype(np.int64))
+    ldb = (rB if layout == "C" else cB) + int(rng.integers(0, 3))
+    B0 = rng.standard_normal((cB if layout == "C" else rB) * ldb).astype(dt)
+    B1, B2 = B0.copy(), B0.copy()
+    what = ("sksp", "left" if left else "right", np.dtype(dt).name, fmt, layout, opS, opA, d, n, m, Dr, Dc, fam, ax, ro, co, ldb, alpha, beta, dens)
+    if left:
+        gpu.lsksp3(fmt, layout, opS, opA, d, n, m, dt(alpha), (Dr, Dc, fam, ax), ctr, key, ro, co, spA, dt(beta), B1, ldb, idx_dtype=idt)
+        port.lsksp3(fmt, layout, opS, opA, d, n, m, dt(alpha), (Dr, Dc, fam, ax), ctr, key, ro, co, spA, dt(beta), B2, ldb)
+    else:
+        gpu.rsksp3(fmt, layout, opA, opS, m, d, n, dt(alpha), spA, (Dr, Dc, fam, ax), ctr, key, ro, co, dt(beta), B1, ldb, idx_dtype=idt)
+        port.rsksp3(fmt, layout, opA, opS, m, d, n, dt(alpha), spA, (Dr, Dc, fam, ax), ctr, key, ro, co, dt(beta), B2, ldb)
+    e = relerr(B1, B2)
+    return what, e, e < tol
+
+
 def main():
     budget = float(sys.argv[1]) if len(sys.argv) > 1 else 60.0
     seed = int(sys.argv[2]) if len(sys.argv) > 2 else 0
@@ -142,7 +190,7 @@ def main():
     before = rb.counter("tensor_core_launches")
     while time.time() - t0 < budget:
         ctr, key = ol.state_from_u64(int(rng.integers(0, 2**31)))
-        case = pick(rng, [dense_case, dense_case, saso_case, fill_case])
+        case = pick(rng, [dense_case, dense_case, saso_case, fill_case, sksp_case])
         try:
             what, e, ok = case(rng, gpu, port, ctr, key)
         except Exception as ex:                       # an error one side raises and the other does not is a finding too
