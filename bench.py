@@ -157,6 +157,8 @@ def bind_to_gpu_numa_node(local):
     return None, old
 
 
+COOLDOWN_S = 2.0          # idle time between two configurations of one bench run
+
 # ---------------------------------------------------------------------------------------------- workloads
 class Workload:
     key = ""
@@ -928,6 +930,11 @@ def main():
     records = {}
     t_all = time.perf_counter()
     for i, key in enumerate(keys):
+        if i > 0:
+            # the configurations are independent measurements: let the power / clock state of the previous one settle (measured:
+            # C1 right after the power-capped C2 runs at 1.05 ms with SM clocks still at 1710-1856 MHz, alone at 1.01 ms)
+            torch.cuda.synchronize()
+            time.sleep(COOLDOWN_S)
         wl = WORKLOADS[key]()
         steps = args.steps if i == 0 else wl.default_steps
         rec = run_workload(wl, rb, torch, dist, rank, world, local, comm, steps, args.warmup, args, old_affinity)
