@@ -344,7 +344,8 @@ int rb_lskges_mshard_all_f64(int ndev, const rb_comm_t* comms, char layout, char
  * pipeline; the first two blocks are a quarter and a half of it), "tc_pair" (CTA pairs, cta_group::2: 0 never / 1 where it pays / 2 whenever possible), "tc_materialise"
  * (Gaussian float operators generated once per K panel: 0 never / 1 with >= 2 column tiles / 2 always),
  * "tc_ymn" (float kernel, Q-contiguous data: 0 = tiles fed to the tensor core as an MN-major operand, the default; 1 = tiles
- * transposed by the generator warps),
+ * transposed by the generator warps), "tc_xmn" (materialised operators contiguous along the rows of op(S), i.e. filled
+ * Axis::Short operators: 1 = tensor-core / DMMA kernels, the default; 0 = generic kernel),
  * "dmma_materialise" (the same for double: 1 = Gaussian operators with K >= 4096, the default; 0 = fused kernel),
  * "dmma_panel_mb" (size of that panel, default 2048).
  * rb_get_counter("kernel_launches" | "tensor_core_launches" | "saso_owner_launches") counts kernels this library

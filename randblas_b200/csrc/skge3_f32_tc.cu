@@ -34,6 +34,9 @@
 // operand -- instruction-descriptor bit 16, LBO 4096 / SBO 1024 -- faulted with "illegal memory access" on this
 // toolchain and was dropped.)
 //
+// Materialised operators contiguous along the ROWS of X (a filled Axis::Short operator): the tile is an MN-major A operand
+// (instruction-descriptor bit 15), delivered by four TMA boxes of 32 rows x 32 k with the same 32-byte-atom swizzle.
+//
 // Roofline: tensor. 2*P*Q*K algorithmic flops, 3 MMAs issued per product => peak = TF32 dense peak / 3.
 #include <cuda.h>
 #include "common.cuh"
@@ -80,6 +83,8 @@ struct TcArgs {
     int64_t crs, ccs;
     int64_t xr0;       // XMAT: first row of X in the materialised operator (tensor-map coordinates)
     int64_t xk0;       // XMAT: first column of X
+    int x_mn;          // XMAT: the materialised operator is contiguous along the ROWS of X (a filled Axis::Short operator): its
+                       // tiles go to the tensor core as an MN-major A operand, 4 TMA boxes of 32 rows x 32 k (32-byte-atom swizzle)
     float* W;          // split-K workspace: W[split][j][i], i fastest, ld = P_pad; null when splits == 1
     int64_t P_pad, Q_pad;
 };
@@ -182,6 +187,7 @@ __device__ __forceinline__ uint64_t smem_desc_mn32(uint32_t addr) {
 // kind::tf32, fp32 accumulate, both operands K-major, M = 128, N = 256; IDESC_B_MN: the B operand is MN-major
 constexpr uint32_t IDESC_TF32 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t) (BN >> 3) << 17) | ((uint32_t) (BM >> 4) << 24);
 constexpr uint32_t IDESC_B_MN = 1u << 16;
+constexpr uint32_t IDESC_A_MN = 1u << 15;   // the A operand is MN-major (same 32-byte-atom layout, blocks of 32 rows)
 
 __device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t da, uint64_t db, uint32_t accumulate, uint32_t idesc = IDESC_TF32) {
     asm volatile(
@@ -364,8 +370,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) skge3_tc_kernel(const __grid_co
                     // PAIR: this CTA's 128 columns of the tile and its own 128 rows of a materialised operator
                     mbar_arrive_expect_tx(bar_full(st), XMAT ? YB + X_BYTES : YB);
                     load_y(base + st * SB + 2 * X_BYTES, bar_full(st), s_begin + it);
-                    if constexpr (XMAT)
-                        tma_load_2d(base + st * SB, &tmX, bar_full(st), (int) a.xk0 + (s_begin + it) * BK, (int) (a.xr0 + i0));
+                    if constexpr (XMAT) {
+                        if (!a.x_mn)
+                            tma_load_2d(base + st * SB, &tmX, bar_full(st), (int) a.xk0 + (s_begin + it) * BK, (int) (a.xr0 + i0));
+                        else
+                            for (int b = 0; b < BM / 32; ++b)      // row-contiguous operator: boxes of 32 rows x 32 k, 4096 bytes apart
+                                tma_load_2d(base + st * SB + 4096u * (uint32_t) b, &tmX, bar_full(st), (int) (a.xr0 + i0) + 32 * b,
+                                            (int) a.xk0 + (s_begin + it) * BK);
+                    }
                 }
             } else {
                 // tensor map (Q, K), box 256 q (128 for a CTA of a pair) x RAW_K k, no swizzle: one raw tile in flight
@@ -403,10 +415,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) skge3_tc_kernel(const __grid_co
                     tc_fence_after();
                     const uint32_t xh = base + st * SB, xl = xh + X_BYTES, yh = xl + X_BYTES, yl = yh + YB;
                     const bool ymn = a.y_mn == 2;                 // Y tiles MN-major: 8 k rows = 1024 bytes per instruction
-                    const uint32_t idesc = IDESC_TF32_PAIR | (ymn ? IDESC_B_MN : 0u);
+                    const bool xmn = XMAT && a.x_mn;              // row-contiguous materialised operator: X tiles MN-major
+                    const uint32_t idesc = IDESC_TF32_PAIR | (ymn ? IDESC_B_MN : 0u) | (xmn ? IDESC_A_MN : 0u);
 #pragma unroll
                     for (int kk = 0; kk < BK / 8; ++kk) {
-                        const uint64_t dxh = smem_desc_sw128(xh + kk * 32), dxl = smem_desc_sw128(xl + kk * 32);
+                        const uint64_t dxh = xmn ? smem_desc_mn32(xh + kk * 1024) : smem_desc_sw128(xh + kk * 32);
+                        const uint64_t dxl = xmn ? smem_desc_mn32(xl + kk * 1024) : smem_desc_sw128(xl + kk * 32);
                         const uint64_t dyh = ymn ? smem_desc_mn32(yh + kk * 1024) : smem_desc_sw128(yh + kk * 32);
                         const uint64_t dyl = ymn ? smem_desc_mn32(yl + kk * 1024) : smem_desc_sw128(yl + kk * 32);
                         const uint32_t acc = (it > 0 || kk > 0) ? 1u : 0u;
@@ -438,10 +452,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) skge3_tc_kernel(const __grid_co
                 tc_fence_after();
                 const uint32_t xh = base + st * SB, xl = xh + X_BYTES, yh = xl + X_BYTES, yl = yh + YB;
                 const bool ymn = a.y_mn == 2;
-                const uint32_t idesc = IDESC_TF32 | (ymn ? IDESC_B_MN : 0u);
+                const bool xmn = XMAT && a.x_mn;
+                const uint32_t idesc = IDESC_TF32 | (ymn ? IDESC_B_MN : 0u) | (xmn ? IDESC_A_MN : 0u);
 #pragma unroll
                 for (int kk = 0; kk < BK / 8; ++kk) {
-                    const uint64_t dxh = smem_desc_sw128(xh + kk * 32), dxl = smem_desc_sw128(xl + kk * 32);
+                    const uint64_t dxh = xmn ? smem_desc_mn32(xh + kk * 1024) : smem_desc_sw128(xh + kk * 32);
+                    const uint64_t dxl = xmn ? smem_desc_mn32(xl + kk * 1024) : smem_desc_sw128(xl + kk * 32);
                     const uint64_t dyh = ymn ? smem_desc_mn32(yh + kk * 1024) : smem_desc_sw128(yh + kk * 32);
                     const uint64_t dyl = ymn ? smem_desc_mn32(yl + kk * 1024) : smem_desc_sw128(yl + kk * 32);
                     const uint32_t acc = (it > 0 || kk > 0) ? 1u : 0u;
@@ -777,8 +793,10 @@ int launch_dense_tc_f32(const DenseProblem<float>& p, cudaStream_t st) {
     if (!xmat && p.family == 'G' && !p.gen.logtab) return -1;
     // Philox blocks along K (the default Axis::Long operators used as they are), or along the rows of X (Axis::Short
     // operators and transposed uses: reference case table dense_skops.hh:187-199) when the window starts on a block
+    // A materialised operator whose vectors run along the rows of X (a filled Axis::Short operator) is read as an MN-major A operand.
     const bool x_t = (p.ui == 1 && p.vk == 1);
-    if (!(p.uk == 1 && p.vi == 1) && !(x_t && !xmat && (p.u0 & 3) == 0)) return -1;
+    if (!(p.uk == 1 && p.vi == 1) && !(x_t && (p.u0 & 3) == 0)) return -1;
+    if (x_t && xmat && get_option("tc_xmn") == 0) return -1;  // experiment switch: row-contiguous materialised operators to the generic kernel
     // Y K-contiguous, or Q-contiguous (left sketch of RowMajor data, right sketch of ColMajor data)
     const bool y_mn = (p.yrs != 1);
     if (y_mn && p.ycs != 1) return -1;
@@ -791,8 +809,9 @@ int launch_dense_tc_f32(const DenseProblem<float>& p, cudaStream_t st) {
         // vector v of the operator is the contiguous run S_buff[v * S_ld ...]: X(i, k) = S_buff[(v0 + i) * S_ld + u0 + k]
         // TMA: base, row pitch and the box's first element must all sit on 16-byte boundaries (a window whose first
         // column is not a multiple of 4 trapped the pipeline on the device), so such windows go to the generic kernel
+        // (row-contiguous operators, x_t: X(i, k) = S_buff[(v0 + k) * S_ld + u0 + i], the same rules with the roles of i and k swapped)
         if ((reinterpret_cast<uintptr_t>(p.S_buff) & 15) != 0 || (p.S_ld & 3) != 0 || (p.u0 & 3) != 0) return -1;
-        if (p.v0 + p.P > 0x7fffff00LL || p.u0 + p.K > 0x7fffff00LL) return -1;
+        if (p.v0 + (x_t ? p.K : p.P) > 0x7fffff00LL || p.u0 + (x_t ? p.P : p.K) > 0x7fffff00LL) return -1;
     }
     EncodeTiledFn enc = encode_tiled();
     if (!enc) return -1;
@@ -847,7 +866,7 @@ int launch_dense_tc_f32(const DenseProblem<float>& p, cudaStream_t st) {
     const cuuint64_t gstr[1] = {(cuuint64_t) (y_mn ? p.yrs : p.ycs) * 4ull};
     // Q-contiguous data: "tc_ymn" 0 (default) = tiles go to the tensor core as they are, as an MN-major operand (boxes of 32 q x
     // 32 k, 128B swizzle with 32-byte atoms); 1 = the transposing path of the first half of round 2 (raw boxes of 256 q x 16 k)
-    const int ymode = !y_mn ? 0 : (get_option("tc_ymn") == 1 ? 1 : 2);
+    const int ymode = !y_mn ? 0 : ((get_option("tc_ymn") == 1 && !(xmat && x_t)) ? 1 : 2);
     const cuuint32_t box[2] = {(cuuint32_t) (ymode == 2 ? 32 : ymode == 1 ? (pair ? BN / 2 : BN) : BK),
                                (cuuint32_t) (ymode == 2 ? BK : ymode == 1 ? RAW_K : (pair ? BN / 2 : BN))};
     const cuuint32_t estr[2] = {1, 1};
@@ -860,17 +879,19 @@ int launch_dense_tc_f32(const DenseProblem<float>& p, cudaStream_t st) {
     CUtensorMap tmx = tm;
     if (xmat) {
         // extents end at the window's last column / row so that the K tail and the rows past P read as zeros
-        const cuuint64_t xdim[2] = {(cuuint64_t) (p.u0 + p.K), (cuuint64_t) (p.v0 + p.P)};
+        const cuuint64_t xdim[2] = {(cuuint64_t) (p.u0 + (x_t ? p.P : p.K)), (cuuint64_t) (p.v0 + (x_t ? p.K : p.P))};
         const cuuint64_t xstr[1] = {(cuuint64_t) p.S_ld * 4ull};
-        const cuuint32_t xbox[2] = {(cuuint32_t) BK, (cuuint32_t) BM};
+        // K-contiguous operator: one box of 32 k x 128 rows, 128B swizzle; row-contiguous: boxes of 32 rows x 32 k, 32-byte atoms
+        const cuuint32_t xbox[2] = {(cuuint32_t) (x_t ? 32 : BK), (cuuint32_t) (x_t ? BK : BM)};
         cr = enc(&tmx, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(p.S_buff), xdim, xstr, xbox, estr,
-                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                 CU_TENSOR_MAP_INTERLEAVE_NONE, x_t ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                 CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (cr != CUDA_SUCCESS) return -1;
     }
 
     TcArgs a;
-    a.xr0 = p.v0; a.xk0 = p.u0;
+    a.xr0 = (xmat && x_t) ? p.u0 : p.v0; a.xk0 = (xmat && x_t) ? p.v0 : p.u0;
+    a.x_mn = (xmat && x_t) ? 1 : 0;
     a.ctr = p.gen.ctr; a.key = p.gen.key; a.R = p.gen.R; a.logtab = p.gen.logtab;
     a.v0 = p.v0;
     a.kshift = kshift;

@@ -216,13 +216,34 @@ __global__ void __launch_bounds__(WS_THREADS, 1) skge3_dmma_ws_kernel(const Dmma
             const int buf = step % D_STAGES;
             if (step >= D_STAGES) tma::mbar_wait(bar_empty + 8u * (uint32_t) buf, (uint32_t) ((step / D_STAGES - 1) & 1));
             // S tile
-            if (!XMAT && a.x_t) {
+            if (a.x_t) {
                 // blocks along the rows of X: thread -> (column k of the step, 4-row block); element (i, k) is lane
                 // (u0 + i0 + i) & 3 of block (v0 + k) * R + (u0 + i0 + i) / 4, u0 % 4 == 0 (checked by the launcher)
                 const int kl = tid & (DK - 1), rb0 = tid / DK;
 #pragma unroll 2
                 for (int rr = 0; rr < P_GR; ++rr) {
                     const int rb = rb0 + (WS_PROD / DK) * rr;
+                    if constexpr (XMAT) {
+                        // materialised operator contiguous along the rows of X (a filled Axis::Short operator):
+                        // X(i, k) = X[(xk0 + k) * xld + xr0 + i]; the same thread mapping, four consecutive rows per load pair
+                        const int64_t i = i0 + 4 * rb, k = (int64_t) (s_begin + step) * DK + kl;
+                        double2 x01 = make_double2(0.0, 0.0), x23 = make_double2(0.0, 0.0);
+                        if (k < a.K && i < a.P) {
+                            const double* src = a.X + (a.xk0 + k) * a.xld + a.xr0 + i;
+                            if (a.x_al && i + 3 < a.P) {
+                                x01 = __ldg(reinterpret_cast<const double2*>(src));
+                                x23 = __ldg(reinterpret_cast<const double2*>(src) + 1);
+                            } else {
+                                x01.x = __ldg(src);
+                                if (i + 1 < a.P) x01.y = __ldg(src + 1);
+                                if (i + 2 < a.P) x23.x = __ldg(src + 2);
+                                if (i + 3 < a.P) x23.y = __ldg(src + 3);
+                            }
+                        }
+                        double* dst = Xs + ((size_t) buf * DM + 4 * rb) * DLD + kl;
+                        dst[0] = x01.x; dst[DLD] = x01.y; dst[2 * DLD] = x23.x; dst[3 * DLD] = x23.y;
+                        continue;
+                    }
                     const uint64_t o = (uint64_t) ((a.v0 + (int64_t) (s_begin + step) * DK + kl) * a.R + a.ublk0 + (i0 >> 2) + rb);
                     const uint64_t lo = seed_lo + o;
                     const uint64_t hi = seed_hi + (lo < seed_lo ? 1ull : 0ull);
@@ -420,7 +441,9 @@ int launch_dense_dmma_f64(const DenseProblem<double>& p, cudaStream_t st) {
     // Philox blocks (rows of a materialised operator) along K, or -- generated operators only -- along the rows of X
     // (Axis::Short operators and transposed uses, dense_skops.hh:187-199) when the window starts on a block boundary
     const bool x_t = (p.ui == 1 && p.vk == 1);
-    if (!(p.uk == 1 && p.vi == 1) && !(x_t && !xmat && (p.u0 & 3) == 0)) return -1;
+    // (a materialised operator with that orientation, i.e. a filled Axis::Short one, is copied tile by tile with the same mapping)
+    if (!(p.uk == 1 && p.vi == 1) && !(x_t && (xmat || (p.u0 & 3) == 0))) return -1;
+    if (x_t && xmat && get_option("tc_xmn") == 0) return -1;  // experiment switch: such operators to the generic kernel
     // Y K-contiguous, or Q-contiguous (left sketch of RowMajor data, right sketch of ColMajor data)
     const bool y_mn = (p.yrs != 1);
     if (y_mn && p.ycs != 1) return -1;
@@ -468,7 +491,8 @@ int launch_dense_dmma_f64(const DenseProblem<double>& p, cudaStream_t st) {
     a.Y = p.Y; a.ycs = y_mn ? p.yrs : p.ycs;
     a.C = p.C; a.crs = p.crs; a.ccs = p.ccs;
     a.P_pad = tiles_p * DM; a.Q_pad = tiles_q * DN;
-    a.X = p.S_buff; a.xld = p.S_ld; a.xr0 = p.v0; a.xk0 = p.u0;
+    // K-contiguous operator: X(i, k) = X[(xr0 + i) * xld + xk0 + k]; row-contiguous (x_t): X(i, k) = X[(xk0 + k) * xld + xr0 + i]
+    a.X = p.S_buff; a.xld = p.S_ld; a.xr0 = (xmat && x_t) ? p.u0 : p.v0; a.xk0 = (xmat && x_t) ? p.v0 : p.u0;
     a.x_al = (xmat && (reinterpret_cast<uintptr_t>(p.S_buff) & 15) == 0 && (p.S_ld & 1) == 0 && (p.u0 & 1) == 0) ? 1 : 0;
     a.W = nullptr;
     if (splits > 1) {

@@ -474,6 +474,67 @@ def test_short_axis_operators_on_tensor_cores_vs_oracle(gpu, port, dt):
         assert relerr(B1, B2) < tol, (("right", lay), relerr(B1, B2))
 
 
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+def test_filled_short_axis_operators_on_tensor_cores_vs_oracle(gpu, port, dt):
+    """MATERIALISED operators whose vectors run along the rows of op(S) -- a filled (S.buff) Axis::Short operator, or a
+    filled tall Axis::Long one used transposed -- were the last dense case on the SIMT kernel. The float kernel now reads their
+    tiles as an MN-major A operand of tcgen05.mma (TMA boxes of 32 rows x 32 k, 32-byte-atom swizzle), the DMMA kernel
+    copies them with the thread mapping of its row-block generator. Ragged tiles, both data layouts, CTA-pair shapes
+    (an even number of row tiles), windows with an aligned and an unaligned first row; vs the oracle (whose operator entries are the same numbers the fill wrote), with the launch counter proving which kernel ran and the tc_xmn = 0 switch (generic kernel) giving
+    the same result within the contract."""
+    import randblas_b200 as rb
+    rng = np.random.default_rng(23)
+    ctr, key = ol.state_from_u64(2024)
+    tol = 1e-5 if dt == np.float32 else 1e-12
+    f32 = dt == np.float32
+    # (layout, opS, d, n, m, D_rows, D_cols, axis, ro, co, family, alpha, beta, tensor cores for float?)
+    cases = [("C", "N", 200, 300, 5003, 212, 6000, "S", 4, 6, "G", 0.5, -1.5, True),
+             ("C", "N", 256, 520, 2500, 256, 9000, "S", 0, 4001, "U", -2.0, 1.0, True),     # two row tiles: CTA pair
+             ("R", "N", 256, 130, 1031, 256, 1031, "S", 0, 0, "U", 1.0, 0.0, True),         # Q-contiguous data as well
+             ("C", "T", 200, 90, 3000, 3100, 204, "S", 7, 0, "G", 1.0, 0.25, True),        # tall + Short, transposed use
+             ("C", "T", 130, 300, 2100, 2200, 132, "L", 3, 0, "U", 1.0, 0.0, False),         # tall + Long, transposed: K-contiguous
+             ("C", "N", 200, 300, 5003, 212, 6000, "S", 3, 6, "G", 0.5, -1.5, False)]       # first row not 16-byte aligned
+    for (lay, opS, d, n, m, Dr, Dc, ax, ro, co, fam, alpha, beta, tc32) in cases:
+        pad = 4 if f32 else 2
+        inner = m if lay == "C" else n
+        lda = inner + (pad - inner % pad) % pad
+        A = rng.standard_normal((n if lay == "C" else m) * lda).astype(dt)
+        ldb = (d if lay == "C" else n) + 1
+        B0 = rng.standard_normal((n if lay == "C" else d) * ldb).astype(dt)
+        B1, B2, B3 = B0.copy(), B0.copy(), B0.copy()
+        before = rb.counter("tensor_core_launches")
+        gpu.lskge3(lay, opS, "N", d, n, m, dt(alpha), (Dr, Dc, fam, ax), ctr, key, ro, co, A, lda, dt(beta), B1, ldb, prefill=1)
+        ran_tc = rb.counter("tensor_core_launches") == before + 1
+        if ax == "S":
+            assert ran_tc == (tc32 if f32 else True), (lay, opS, d, n, m, ax, ro, co, ran_tc)
+        port.lskge3(lay, opS, "N", d, n, m, dt(alpha), (Dr, Dc, fam, ax), ctr, key, ro, co, A, lda, dt(beta), B2, ldb)
+        assert relerr(B1, B2) < tol, ((lay, opS, d, n, m, ax, ro, co, fam), relerr(B1, B2))
+        if ax == "S":
+            rb.set_option("tc_xmn", 0)
+            try:
+                before = rb.counter("tensor_core_launches")
+                gpu.lskge3(lay, opS, "N", d, n, m, dt(alpha), (Dr, Dc, fam, ax), ctr, key, ro, co, A, lda, dt(beta), B3, ldb, prefill=1)
+                assert rb.counter("tensor_core_launches") == before, "tc_xmn = 0 sends these operators to the generic kernel"
+            finally:
+                rb.set_option("tc_xmn", 1)
+            assert relerr(B3, B2) < tol and relerr(B1, B3) < 2 * tol
+    # right sketch: B(m x d) = A(m x n) S(n x d) with a FILLED tall Axis::Short operator (RowMajor natural layout)
+    mm, dd, nn = 1500, 100, 977
+    for lay in "CR":
+        inner = mm if lay == "C" else nn
+        pad = 4 if f32 else 2
+        lda = inner + (pad - inner % pad) % pad
+        A = rng.standard_normal((nn if lay == "C" else mm) * lda).astype(dt)
+        ldb = (mm if lay == "C" else dd) + 3
+        B0 = rng.standard_normal((dd if lay == "C" else mm) * ldb).astype(dt)
+        B1, B2 = B0.copy(), B0.copy()
+        before = rb.counter("tensor_core_launches")
+        gpu.rskge3(lay, "N", "T", mm, dd, nn, dt(-0.5), A, lda, (120, 1000, "G", "S"), ctr, key, 4, 8, dt(2.0), B1, ldb, prefill=1)
+        assert rb.counter("tensor_core_launches") == before + 1, ("right", lay)
+        port.rskge3(lay, "N", "T", mm, dd, nn, dt(-0.5), A, lda, (120, 1000, "G", "S"), ctr, key, 4, 8, dt(2.0), B2, ldb)
+        assert relerr(B1, B2) < tol, (("right", lay), relerr(B1, B2))
+
+
 def test_double_gaussian_operator_through_panels_vs_fused_and_oracle(gpu, port):
     """Double Gaussian operators with K >= 4096 are generated per K panel into scratch memory and multiplied by the
     materialised-operator DMMA kernel (dmma_materialise = 1, the default). With a 16 MB panel the cases below take four to

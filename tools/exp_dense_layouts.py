@@ -48,6 +48,27 @@ def main():
         Sg = rb.DenseSkOp(rb.DenseDist(d, m, rb.ScalarDist.Gaussian, rb.Axis.Short), rb.RNGState(1997), dt)
         t = timeit(lambda: rb.sketch_general("C", "N", "N", d, n, m, 1.0, Sg, 0, 0, A, m, 0.0, B, d))
         print(f"{np.dtype(dt).name} left ColMajor, Axis::Short Gaussian operator: {t:.3f} ms, {flops / t / 1e9:.1f} TFLOP/s", flush=True)
+        # the same operators FILLED (S.buff): K-contiguous tiles (Axis::Long) and row-contiguous tiles (Axis::Short: MN-major A
+        # operand of the float kernel, row-block copies of the DMMA kernel; tc_xmn = 0 is the generic kernel they used before)
+        Sf = rb.DenseSkOp(rb.DenseDist(d, m, rb.ScalarDist.Uniform), rb.RNGState(1997), dt)
+        rb.fill_dense(Sf)
+        t = timeit(lambda: rb.sketch_general("C", "N", "N", d, n, m, 1.0, Sf, 0, 0, A, m, 0.0, B, d))
+        print(f"{np.dtype(dt).name} left ColMajor, FILLED Axis::Long operator: {t:.3f} ms, {flops / t / 1e9:.1f} TFLOP/s", flush=True)
+        del Sf
+        Sfs = rb.DenseSkOp(rb.DenseDist(d, m, rb.ScalarDist.Uniform, rb.Axis.Short), rb.RNGState(1997), dt)
+        rb.fill_dense(Sfs)
+        before = rb.counter("tensor_core_launches")
+        t = timeit(lambda: rb.sketch_general("C", "N", "N", d, n, m, 1.0, Sfs, 0, 0, A, m, 0.0, B, d))
+        print(f"{np.dtype(dt).name} left ColMajor, FILLED Axis::Short operator: {t:.3f} ms, {flops / t / 1e9:.1f} TFLOP/s "
+              f"(tensor-core launches {rb.counter('tensor_core_launches') - before})", flush=True)
+        t = timeit(lambda: rb.sketch_general("R", "N", "N", d, n, m, 1.0, Sfs, 0, 0, A, n, 0.0, B, n))
+        print(f"{np.dtype(dt).name} left RowMajor, FILLED Axis::Short operator: {t:.3f} ms, {flops / t / 1e9:.1f} TFLOP/s", flush=True)
+        rb.set_option("tc_xmn", 0)
+        t = timeit(lambda: rb.sketch_general("C", "N", "N", d, n, m, 1.0, Sfs, 0, 0, A, m, 0.0, B, d), reps=2)
+        print(f"{np.dtype(dt).name} left ColMajor, FILLED Axis::Short operator, generic SIMT kernel (tc_xmn = 0): {t:.3f} ms, "
+              f"{flops / t / 1e9:.1f} TFLOP/s", flush=True)
+        rb.set_option("tc_xmn", 1)
+        del Sfs
         rb.set_option("dense_path", 1)
         t = timeit(lambda: rb.sketch_general("C", "N", "N", d, n, m, 1.0, Ss, 0, 0, A, m, 0.0, B, d), reps=2)
         print(f"{np.dtype(dt).name} left ColMajor, Axis::Short operator, generic SIMT kernel: {t:.3f} ms, {flops / t / 1e9:.1f} TFLOP/s", flush=True)
