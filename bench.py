@@ -563,7 +563,7 @@ class C4SasoApply(Workload):
         del Sf
         return {"fill_sparse": {"ms": ms, "nnz": nnz, "Mnnz_per_s": nnz / ms / 1e3, "bytes_written": nnz * 20,
                                 "achieved_GBs": gbs, "frac_hbm": gbs / pk["hbm_gbs"],
-                                "kernel": "saso_fill_group_kernel<int64, float, 8>"}}
+                                "kernel": "saso_fill_vec_kernel<int64, float, 8>"}}
 
     def e2e_setup(self):
         torch = self.torch

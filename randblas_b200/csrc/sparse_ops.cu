@@ -15,6 +15,8 @@
 //  * coo_apply_kernel   -- the same contraction for an already-sampled operator handed over as COO arrays.
 //
 // Roofline: HBM. fill: bytes written = full_nnz * (2*idx_bytes + val_bytes). apply: bytes of A read once.
+#include <type_traits>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -126,6 +128,118 @@ __global__ void __launch_bounds__(256) saso_fill_group_kernel(Ctr128 ctr, Philox
     }
 }
 
+// ---- thread per vector (K = 2, 4, 8, 16 entries, dim_major < 2^31) -------------------------------------------------
+// The lane-per-entry kernel above spends most of its time on the 16-lane integer pipe: per nonzero a masked backward
+// trace through 7 shuffles (3 integer instructions per step), a 128-bit counter addition and 64-bit index arithmetic
+// (~150 instructions per warp-level nonzero, ALU pipe 73% busy). With one THREAD per vector the K pivots live in
+// registers: the trace of entry j is j compares-and-selects with compile-time bounds (K (K - 1) / 2 per vector, no
+// shuffles, no masks), the counter of entry j is the vector's counter plus j (one 128-bit addition per vector), the K
+// divisors' reciprocals are kernel parameters (constant-bank operands), and a thread's K consecutive entries of each COO
+// array leave as 32-byte (STG.256) or 16-byte stores: every store instruction writes whole sectors.
+struct SasoVecMagic {
+    uint32_t m[16];      // fastmod_magic(dim_major - j)
+};
+
+__device__ __forceinline__ void st256(void* p, unsigned long long a, unsigned long long b, unsigned long long c,
+                                      unsigned long long d) {
+    asm volatile("st.global.v4.b64 [%0], {%1,%2,%3,%4};" ::"l"(p), "l"(a), "l"(b), "l"(c), "l"(d) : "memory");
+}
+__device__ __forceinline__ void st256(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t e, uint32_t f,
+                                      uint32_t g, uint32_t h) {
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d), "r"(e), "r"(f),
+                 "r"(g), "r"(h)
+                 : "memory");
+}
+// the bits of an index or value as the unsigned integer of its size
+template <typename T>
+__device__ __forceinline__ auto bits_of(T x) {
+    if constexpr (sizeof(T) == 8) {
+        if constexpr (std::is_floating_point<T>::value) return (unsigned long long) __double_as_longlong((double) x);
+        else return (unsigned long long) x;
+    } else {
+        if constexpr (std::is_floating_point<T>::value) return (uint32_t) __float_as_uint((float) x);
+        else return (uint32_t) x;
+    }
+}
+
+// N consecutive elements of T from registers to dst (dst is 32-byte aligned whenever N * sizeof(T) is a multiple of 32,
+// 16-byte aligned when it is a multiple of 16: the launcher checks the base pointers)
+template <typename T, int N>
+__device__ __forceinline__ void store_run(T* dst, const T (&x)[N]) {
+    constexpr int BYTES = N * (int) sizeof(T);
+    if constexpr (BYTES % 32 == 0 && sizeof(T) == 8) {
+#pragma unroll
+        for (int c = 0; c < N / 4; ++c)
+            st256(dst + 4 * c, bits_of(x[4 * c]), bits_of(x[4 * c + 1]), bits_of(x[4 * c + 2]), bits_of(x[4 * c + 3]));
+    } else if constexpr (BYTES % 32 == 0) {
+#pragma unroll
+        for (int c = 0; c < N / 8; ++c)
+            st256(dst + 8 * c, bits_of(x[8 * c]), bits_of(x[8 * c + 1]), bits_of(x[8 * c + 2]), bits_of(x[8 * c + 3]),
+                  bits_of(x[8 * c + 4]), bits_of(x[8 * c + 5]), bits_of(x[8 * c + 6]), bits_of(x[8 * c + 7]));
+    } else if constexpr (BYTES % 16 == 0 && sizeof(T) == 8) {
+#pragma unroll
+        for (int c = 0; c < N / 2; ++c)
+            *reinterpret_cast<ulonglong2*>(dst + 2 * c) = make_ulonglong2(bits_of(x[2 * c]), bits_of(x[2 * c + 1]));
+    } else if constexpr (BYTES % 16 == 0) {
+#pragma unroll
+        for (int c = 0; c < N / 4; ++c)
+            *reinterpret_cast<uint4*>(dst + 4 * c) = make_uint4(bits_of(x[4 * c]), bits_of(x[4 * c + 1]), bits_of(x[4 * c + 2]),
+                                                                bits_of(x[4 * c + 3]));
+    } else {
+#pragma unroll
+        for (int c = 0; c < N; ++c) dst[c] = x[c];
+    }
+}
+
+template <typename IDX, typename VAL, int K>
+__global__ void __launch_bounds__(256) saso_fill_vec_kernel(Ctr128 ctr, PhiloxKey key, uint32_t dim_major, int64_t dim_minor,
+                                                            const __grid_constant__ SasoVecMagic mg, IDX* __restrict__ maj,
+                                                            IDX* __restrict__ mnr, VAL* __restrict__ vals) {
+    const int64_t nthreads = (int64_t) gridDim.x * blockDim.x;
+    for (int64_t v = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; v < dim_minor; v += nthreads) {
+        const Ctr128 c0 = ctr_add(ctr, (uint64_t) v * (uint64_t) K);
+        const bool nocarry = c0.c0 <= 0xffffffffu - (uint32_t) K;      // entry j's counter differs in the low word only
+        uint32_t piv[K], neg[K];
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+            Ctr128 cj = c0;
+            if (nocarry) cj.c0 = c0.c0 + (uint32_t) j;
+            else cj = ctr_add(c0, (uint64_t) j);
+            const uint4 w = philox4x32_10(cj, key);
+            piv[j] = (uint32_t) j + fastmod(w.x, dim_major - (uint32_t) j, mg.m[j]);          // sparse_skops.hh:78
+            neg[j] = w.y & 1u;
+        }
+        // value at position piv[j] after swaps 0..j-1 of an identity permutation (see saso_vector_warp)
+        IDX om[K], on[K];
+        VAL ov[K];
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+            uint32_t pos = piv[j];
+#pragma unroll
+            for (int t = j - 1; t >= 0; --t)
+                if (pos == piv[t]) pos = (uint32_t) t;
+            om[j] = (IDX) pos;
+            on[j] = (IDX) v;
+            ov[j] = neg[j] ? (VAL) -1 : (VAL) 1;
+        }
+        store_run<IDX, K>(maj + v * K, om);
+        if (mnr) store_run<IDX, K>(mnr + v * K, on);
+        if (vals) store_run<VAL, K>(vals + v * K, ov);
+    }
+}
+
+template <typename IDX, typename VAL, int K>
+static void launch_saso_vec(Ctr128 ctr, PhiloxKey key, int64_t dim_major, int64_t dim_minor, void* maj, void* mnr, void* vals,
+                            cudaStream_t st) {
+    SasoVecMagic mg;
+    for (int j = 0; j < 16; ++j) mg.m[j] = (j < K && dim_major - j > 0) ? 0xffffffffu / (uint32_t) (dim_major - j) : 0u;
+    int64_t grid = (dim_minor + 255) / 256;
+    const int64_t cap = (int64_t) sm_count() * 32;
+    if (grid > cap) grid = cap;
+    saso_fill_vec_kernel<IDX, VAL, K><<<(unsigned) grid, 256, 0, st>>>(ctr, key, (uint32_t) dim_major, dim_minor, mg, (IDX*) maj,
+                                                                       (IDX*) mnr, (VAL*) vals);
+}
+
 // any k: thread per vector, pivots in global scratch (k entries per thread of the grid)
 template <typename IDX, typename VAL>
 __global__ void saso_fill_thread_kernel(Ctr128 ctr, PhiloxKey key, int64_t k, int64_t dim_major, int64_t dim_minor,
@@ -146,7 +260,18 @@ __global__ void saso_fill_thread_kernel(Ctr128 ctr, PhiloxKey key, int64_t k, in
 template <typename IDX, typename VAL>
 int launch_saso_t(Ctr128 ctr, PhiloxKey key, int64_t k, int64_t dim_major, int64_t dim_minor, void* maj, void* mnr,
                   void* vals, cudaStream_t st) {
-    if (k <= 32 && dim_major < 0x7fffffffLL && get_option("saso_fill_path") == 0) {
+    // saso_fill_path: 0 auto (thread per vector for k = 2, 4, 8, 16; lane per entry otherwise), 1 warp per vector,
+    // 2 lane per entry always
+    const bool aligned32 = ((reinterpret_cast<uintptr_t>(maj) | reinterpret_cast<uintptr_t>(mnr) | reinterpret_cast<uintptr_t>(vals)) & 31) == 0;
+    if ((k == 2 || k == 4 || k == 8 || k == 16) && dim_major < 0x7fffffffLL && dim_major >= k && aligned32 &&
+        get_option("saso_fill_path") == 0) {
+        switch (k) {
+            case 2: launch_saso_vec<IDX, VAL, 2>(ctr, key, dim_major, dim_minor, maj, mnr, vals, st); break;
+            case 4: launch_saso_vec<IDX, VAL, 4>(ctr, key, dim_major, dim_minor, maj, mnr, vals, st); break;
+            case 8: launch_saso_vec<IDX, VAL, 8>(ctr, key, dim_major, dim_minor, maj, mnr, vals, st); break;
+            default: launch_saso_vec<IDX, VAL, 16>(ctr, key, dim_major, dim_minor, maj, mnr, vals, st); break;
+        }
+    } else if (k <= 32 && dim_major < 0x7fffffffLL && (get_option("saso_fill_path") & ~2) == 0) {
         const int G = k <= 1 ? 1 : k <= 2 ? 2 : k <= 4 ? 4 : k <= 8 ? 8 : k <= 16 ? 16 : 32;
         const int64_t vpb = 8 * (32 / G);                      // vectors per 256-thread CTA and iteration
         int64_t grid = (dim_minor + vpb - 1) / vpb;

@@ -242,16 +242,19 @@ def test_saso_sweep_vs_oracle(gpu, port):
     rng = np.random.default_rng(2)
     import randblas_b200 as rb
     shapes = [(7, 20, 3), (20, 7, 7), (1, 9, 1), (64, 64, 64), (40, 1000, 33), (2048, 20000, 8), (300, 5, 5),
-              (100, 100000, 32), (33, 50, 1), (50, 400, 16), (9, 300, 2), (20, 3000, 11)]
+              (100, 100000, 32), (33, 50, 1), (50, 400, 16), (9, 300, 2), (20, 3000, 11), (30, 1000, 4), (16, 100, 16),
+              (5000, 8, 8), (2, 70, 2)]
     try:
-        for path in (0, 1):     # 0: sub-warp groups (saso_fill_group_kernel), 1: warp per vector
+        # 0: thread per vector for k = 2, 4, 8, 16 (saso_fill_vec_kernel), sub-warp groups otherwise; 1: warp per vector;
+        # 2: sub-warp groups (saso_fill_group_kernel) for every k <= 32
+        for path in (0, 1, 2):
             rb.set_option("saso_fill_path", path)
             for (r, c, k) in shapes:
                 ctr, key = ol.state_from_u64(int(rng.integers(0, 1 << 62)))
-                ctr = ol.ctr_add(ctr, (1 << 32) - 7)
-                for idt in (np.int32, np.int64):
-                    a = gpu.fill_sparse(r, c, k, "S", ctr, key, np.float32, idt)
-                    b = port.fill_sparse(r, c, k, "S", ctr, key, np.float32, idt)
+                ctr = ol.ctr_add(ctr, (1 << 32) - 7)      # the low counter word wraps inside the run
+                for idt, vdt in ((np.int32, np.float32), (np.int64, np.float32), (np.int64, np.float64)):
+                    a = gpu.fill_sparse(r, c, k, "S", ctr, key, vdt, idt)
+                    b = port.fill_sparse(r, c, k, "S", ctr, key, vdt, idt)
                     for x, y in zip(a, b):
                         assert np.array_equal(x, y), (path, r, c, k)
     finally:
