@@ -94,19 +94,25 @@ struct BinArgs {
     int Ppad;              // Prows + 8: per-chunk stride of offs16
     uint32_t* sorted;      // [nchunks][BN_ENT_CAP]
     uint16_t* offs16;      // [nchunks][Ppad]
+    uint32_t magic[16];    // VEC kernels: fastmod_magic(dim_major - j), constant-bank operands
 };
 
 // G lanes per column of X (power of two >= k). All index arithmetic in 32 bits: dim_major < 2^31 on this path.
-template <int G>
-__global__ void __launch_bounds__(BIN_THREADS) saso_bin_kernel(const BinArgs a) {
-    extern __shared__ uint32_t bsm[];
+// VEC (k == G = 2, 4, 8, 16): one THREAD regenerates a whole column -- the pivots stay in its registers, the backward trace
+// has compile-time bounds (no shuffles, no masks) and a column needs one 128-bit counter addition (the generation scheme of
+// saso_fill_vec_kernel, sparse_ops.cu; the lane-per-entry form spent ~280 instructions per entry, most of them on the
+// 16-lane integer pipe).
+template <int G, bool VEC = false, int NT = BIN_THREADS, int MINB = 1>
+__global__ void __launch_bounds__(NT, MINB) saso_bin_kernel(const __grid_constant__ BinArgs a) {
+    extern __shared__ __align__(16) uint32_t bsm[];
     uint32_t* cnt = bsm;                               // [Prows + 1] counters, then running offsets
     uint32_t* raw = cnt + a.Prows + 32;                // [BN_ENT] (row << 1 | negative), ~0 = outside the window
     uint32_t* srt = raw + BN_ENT;                      // [BN_ENT] sorted words
+    constexpr int BIN_THREADS = NT;                    // (shadows the default thread count in this kernel)
     __shared__ uint32_t wsum[BIN_THREADS / 32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, sub = lane & (G - 1);
     constexpr int VPP = BIN_THREADS / G;               // columns per pass
-    const int per_thr = a.Prows / BIN_THREADS;         // counters scanned per thread (Prows is a multiple of 1024)
+    const int per_thr = (a.Prows + BIN_THREADS - 1) / BIN_THREADS;     // counters scanned per thread
     const uint32_t dv = sub < a.k ? a.dim_major - (uint32_t) sub : 1u, dm = fastmod_magic(dv);
 
     for (int64_t c = blockIdx.x; c < a.nchunks; c += gridDim.x) {
@@ -115,6 +121,41 @@ __global__ void __launch_bounds__(BIN_THREADS) saso_bin_kernel(const BinArgs a) 
         for (int i = tid; i < a.Prows; i += BIN_THREADS) cnt[i] = 0;
         __syncthreads();
         // ---- generate the chunk's nonzeros, count them per target row ----
+        if constexpr (VEC) {
+            for (int vl = tid; vl < nv; vl += BIN_THREADS) {
+                const Ctr128 c0 = ctr_add(a.ctr, (uint64_t) (a.vec_lo + v0 + vl) * (uint64_t) G);
+                const bool nocarry = c0.c0 <= 0xffffffffu - (uint32_t) G;
+                uint32_t piv[G], neg[G];
+#pragma unroll
+                for (int j = 0; j < G; ++j) {
+                    Ctr128 cj = c0;
+                    if (nocarry) cj.c0 = c0.c0 + (uint32_t) j;
+                    else cj = ctr_add(c0, (uint64_t) j);
+                    const uint4 w = philox4x32_10(cj, a.key);
+                    piv[j] = (uint32_t) j + fastmod(w.x, a.dim_major - (uint32_t) j, a.magic[j]);   // sparse_skops.hh:78
+                    neg[j] = w.y & 1u;
+                }
+                uint32_t out[G];
+#pragma unroll
+                for (int j = 0; j < G; ++j) {
+                    uint32_t pos = piv[j];
+#pragma unroll
+                    for (int t = j - 1; t >= 0; --t)
+                        if (pos == piv[t]) pos = (uint32_t) t;
+                    const int64_t r = (int64_t) pos - a.m0;
+                    const bool in = r >= 0 && r < a.P;
+                    out[j] = in ? (((uint32_t) r << 1) | neg[j]) : 0xffffffffu;                       // :84-88
+                    if (in) atomicAdd(&cnt[r], 1u);
+                }
+                if constexpr (G % 4 == 0) {
+#pragma unroll
+                    for (int q = 0; q < G / 4; ++q)
+                        *reinterpret_cast<uint4*>(raw + vl * G + 4 * q) = make_uint4(out[4 * q], out[4 * q + 1], out[4 * q + 2], out[4 * q + 3]);
+                } else {
+                    *reinterpret_cast<uint2*>(raw + vl * G) = make_uint2(out[0], out[1]);
+                }
+            }
+        } else
         for (int vb = 0; vb < nv; vb += VPP) {
             const int vl = vb + tid / G;
             const bool live = vl < nv && sub < a.k;
@@ -142,7 +183,8 @@ __global__ void __launch_bounds__(BIN_THREADS) saso_bin_kernel(const BinArgs a) 
         // ---- exclusive scan of the counters (per_thr consecutive counters per thread) ----
         {
             uint32_t loc = 0;
-            for (int i = 0; i < per_thr; ++i) loc += cnt[tid * per_thr + i];
+            for (int i = 0; i < per_thr; ++i)
+                if (tid * per_thr + i < a.Prows) loc += cnt[tid * per_thr + i];
             uint32_t incl = loc;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
@@ -164,6 +206,7 @@ __global__ void __launch_bounds__(BIN_THREADS) saso_bin_kernel(const BinArgs a) 
             __syncthreads();
             uint32_t run = incl - loc + wsum[warp];
             for (int i = 0; i < per_thr; ++i) {
+                if (tid * per_thr + i >= a.Prows) break;
                 const uint32_t v = cnt[tid * per_thr + i];
                 cnt[tid * per_thr + i] = run;
                 run += v;
@@ -176,7 +219,7 @@ __global__ void __launch_bounds__(BIN_THREADS) saso_bin_kernel(const BinArgs a) 
             const uint32_t w = raw[e];
             if (w != 0xffffffffu) {
                 const uint32_t dst = atomicAdd(&cnt[w >> 1], 1u);
-                const uint32_t vl = (uint32_t) e / (uint32_t) a.k;
+                const uint32_t vl = VEC ? (uint32_t) e / (uint32_t) G : (uint32_t) e / (uint32_t) a.k;   // VEC: k == G, a shift
                 srt[dst] = (vl * (uint32_t) (BN_W * 2)) | ((w & 1u) << 31);
             }
         }
@@ -371,11 +414,11 @@ __global__ void __launch_bounds__(BN_THREADS, 1) saso_binned_kernel(const __grid
     }
 }
 
-template <int G>
+template <int G, bool VEC = false, int NT = BIN_THREADS, int MINB = 1>
 int launch_bin(const BinArgs& a, size_t smem, cudaStream_t st) {
     static DevOnce attr_done;
     if (attr_done.need()) {
-        if (cudaFuncSetAttribute(saso_bin_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024) != cudaSuccess) {
+        if (cudaFuncSetAttribute(saso_bin_kernel<G, VEC, NT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024) != cudaSuccess) {
             cudaGetLastError();
             return -1;
         }
@@ -384,7 +427,7 @@ int launch_bin(const BinArgs& a, size_t smem, cudaStream_t st) {
     int64_t grid = a.nchunks;
     const int64_t cap = (int64_t) sm_count() * 4;
     if (grid > cap) grid = cap;
-    saso_bin_kernel<G><<<(unsigned) grid, BIN_THREADS, smem, st>>>(a);
+    saso_bin_kernel<G, VEC, NT, MINB><<<(unsigned) grid, NT, smem, st>>>(a);
     return 0;
 }
 
@@ -443,8 +486,17 @@ int launch_saso_binned(const SasoProblem<T>& p, cudaStream_t st) {
         b.ctr = p.ctr; b.key = p.key; b.k = k; b.dim_major = (uint32_t) p.dim_major;
         b.vec_lo = w0 + v0; b.nvec = nv; b.m0 = m0; b.P = p.P; b.Kc = Kc; b.nchunks = nchunks;
         b.Prows = Prows; b.Ppad = Ppad; b.sorted = sorted; b.offs16 = offs16;
+        for (int j = 0; j < 16; ++j) b.magic[j] = (j < k && p.dim_major - j > 0) ? 0xffffffffu / (uint32_t) (p.dim_major - j) : 0u;
+        // saso_bin_path: 0 auto (thread per column for vec_nnz = 2, 4, 8, 16), 1 lane per entry always
+        const bool vec = get_option("saso_bin_path") == 0 && p.dim_major >= k;
         int rc;
-        if (k <= 1) rc = launch_bin<1>(b, bin_smem, st);
+        // (352 threads x 3 CTAs per SM -- two FULL passes over a 704-column chunk -- measured slower than 512 x 2 with a
+        // ragged second pass: 71.0 against 64.5 us per 1e6 columns; the template parameters stay for such experiments)
+        if (vec && k == 2) rc = launch_bin<2, true, BIN_THREADS, 2>(b, bin_smem, st);
+        else if (vec && k == 4) rc = launch_bin<4, true, BIN_THREADS, 2>(b, bin_smem, st);
+        else if (vec && k == 8) rc = launch_bin<8, true, BIN_THREADS, 2>(b, bin_smem, st);
+        else if (vec && k == 16) rc = launch_bin<16, true, BIN_THREADS, 1>(b, bin_smem, st);
+        else if (k <= 1) rc = launch_bin<1>(b, bin_smem, st);
         else if (k <= 2) rc = launch_bin<2>(b, bin_smem, st);
         else if (k <= 4) rc = launch_bin<4>(b, bin_smem, st);
         else if (k <= 8) rc = launch_bin<8>(b, bin_smem, st);

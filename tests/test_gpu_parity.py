@@ -604,9 +604,13 @@ def test_saso_owner_kernel_vs_oracle_and_vs_atomic_kernel(gpu, port):
         # saso_path 2 = force the binned kernel (saso_binned.cu, the default for large problems)
         for path, (d, n, m, vn, ro, co) in [(pp, sh) for pp in (2,) for sh in (
                 (45, 29, 2111, 3, 2, 5), (1500, 64, 3000, 8, 0, 0), (1100, 100, 1537, 17, 7, 3),
-                (300, 36, 900, 32, 0, 1), (64, 32, 5000, 1, 1, 0), (2048, 40, 777, 5, 0, 0), (3000, 33, 1409, 2, 1, 1))]:
+                (300, 36, 900, 32, 0, 1), (64, 32, 5000, 1, 1, 0), (2048, 40, 777, 5, 0, 0), (3000, 33, 1409, 2, 1, 1),
+                (1500, 64, 3000, 8, 3, 2), (700, 40, 2000, 16, 2, 1), (90, 36, 1800, 4, 1, 1))]:
             rb.set_option("saso_path", path)
-            for opS in "NT":
+            # vec_nnz = 2, 4, 8, 16: the binning pass regenerates a column per THREAD (saso_bin_path 0, default) or
+            # per lane group (1, the only form for other vec_nnz); both are run
+            for binp, opS in [(bp, o) for bp in ((0, 1) if vn in (2, 4, 8, 16) else (0,)) for o in "NT"]:
+                rb.set_option("saso_bin_path", binp)
                 Dr, Dc = (d + ro + 3, m + co + 6) if opS == "N" else (m + ro + 6, d + co + 3)
                 A, lda = _mk(rng, m, n, "R", 4 - n % 4 if n % 4 else 0, dt)      # lda % 4 == 0: TMA-addressable
                 B0, ldb = _mk(rng, d, n, "R", 1, dt)
@@ -642,6 +646,7 @@ def test_saso_owner_kernel_vs_oracle_and_vs_atomic_kernel(gpu, port):
         assert float(torch.linalg.norm(Ba.double() - want) / torch.linalg.norm(want)) < 1e-5
     finally:
         rb.set_option("saso_path", 0)
+        rb.set_option("saso_bin_path", 0)
 
 
 def test_saso_apply_full_size_exact_on_all_ones(gpu):
