@@ -60,12 +60,15 @@ def dense_case(rng, gpu, port, ctr, key):
     ldb = (rB if layout == "C" else cB) + int(rng.integers(0, 3))
     B0 = rng.standard_normal((cB if layout == "C" else rB) * ldb).astype(dt)
     B1, B2 = B0.copy(), B0.copy()
-    what = ("dense", "left" if left else "right", np.dtype(dt).name, layout, opS, opA, d, n, m, Dr, Dc, fam, ax, ro, co, lda, ldb, alpha, beta)
+    # a third of the operators are FILLED first (S.buff: the materialised-operator kernels, K- and row-contiguous tiles)
+    prefill = 1 if rng.random() < 0.35 else 0
+    what = ("dense", "left" if left else "right", np.dtype(dt).name, layout, opS, opA, d, n, m, Dr, Dc, fam, ax, ro, co, lda, ldb, alpha, beta,
+            "filled" if prefill else "unfilled")
     if left:
-        gpu.lskge3(layout, opS, opA, d, n, m, dt(alpha), (Dr, Dc, fam, ax), ctr, key, ro, co, A, lda, dt(beta), B1, ldb)
+        gpu.lskge3(layout, opS, opA, d, n, m, dt(alpha), (Dr, Dc, fam, ax), ctr, key, ro, co, A, lda, dt(beta), B1, ldb, prefill=prefill)
         port.lskge3(layout, opS, opA, d, n, m, dt(alpha), (Dr, Dc, fam, ax), ctr, key, ro, co, A, lda, dt(beta), B2, ldb)
     else:
-        gpu.rskge3(layout, opA, opS, m, d, n, dt(alpha), A, lda, (Dr, Dc, fam, ax), ctr, key, ro, co, dt(beta), B1, ldb)
+        gpu.rskge3(layout, opA, opS, m, d, n, dt(alpha), A, lda, (Dr, Dc, fam, ax), ctr, key, ro, co, dt(beta), B1, ldb, prefill=prefill)
         port.rskge3(layout, opA, opS, m, d, n, dt(alpha), A, lda, (Dr, Dc, fam, ax), ctr, key, ro, co, dt(beta), B2, ldb)
     e = relerr(B1, B2)
     return what, e, e < tol
@@ -107,6 +110,23 @@ def saso_case(rng, gpu, port, ctr, key):
         port.rskges(layout, opA, "T", n, d, m, dt(alpha), A, lda, (Dr, Dc, k, "S"), ctr, key, 0, co, dt(beta), B2, ldb)
     e = relerr(B1, B2)
     return what, e, e < tol
+
+
+def fill_sparse_case(rng, gpu, port, ctr, key):
+    # SASO index / sign arrays, bit for bit: thread-per-vector kernel (vec_nnz 2, 4, 8, 16) and lane-per-entry kernel
+    short = int(rng.integers(1, 3000))
+    long_ = int(rng.integers(short, 20000))
+    k = int(pick(rng, [1, 2, 3, 4, 5, 8, 8, 16, 16, 7, 32])) if rng.random() < 0.8 else int(rng.integers(1, 40))
+    k = max(1, min(k, short))
+    r, c = (short, long_) if rng.random() < 0.5 else (long_, short)
+    idt = pick(rng, [np.int32, np.int64])
+    vdt = pick(rng, [np.float32, np.float64])
+    if rng.random() < 0.3:
+        ctr = ol.ctr_add(ctr, (1 << 32) - int(rng.integers(1, 50000)))      # the low counter word wraps inside the run
+    a = gpu.fill_sparse(r, c, k, "S", ctr, key, vdt, idt)
+    b = port.fill_sparse(r, c, k, "S", ctr, key, vdt, idt)
+    ok = all(np.array_equal(x, y) for x, y in zip(a, b))
+    return ("fill_sparse", r, c, k, np.dtype(idt).name, np.dtype(vdt).name), 0.0 if ok else 1.0, ok
 
 
 def fill_case(rng, gpu, port, ctr, key):
@@ -190,7 +210,7 @@ def main():
     before = rb.counter("tensor_core_launches")
     while time.time() - t0 < budget:
         ctr, key = ol.state_from_u64(int(rng.integers(0, 2**31)))
-        case = pick(rng, [dense_case, dense_case, saso_case, fill_case, sksp_case])
+        case = pick(rng, [dense_case, dense_case, dense_case, saso_case, saso_case, fill_case, fill_sparse_case, sksp_case])
         try:
             what, e, ok = case(rng, gpu, port, ctr, key)
         except Exception as ex:                       # an error one side raises and the other does not is a finding too
