@@ -271,7 +271,13 @@ __device__ __forceinline__ double word_sign_f64(uint32_t p) {
     return __hiloint2double((int) ((p & 0x80000000u) | 0x3ff00000u), 0);
 }
 
-template <typename T>
+// RL ("row per lane"): thread t of the CTA owns ROW t of the 1024 x 32 tile -- all 128 bytes of it, as eight 16-byte
+// chunks -- instead of 16 bytes of eight rows. A warp then walks 32 lists in lockstep, one entry per lane and step:
+// per step 8 address XORs, 8 LDS.128 and 32 FMAs serve up to 32 entries (the group form: 12 instructions for up to 4
+// entries of 16 bytes... per lane), and the number of steps is the longest of the 32 lists. Lane l reads chunk j ^ (l & 7) in
+// sub-step j, so the eight lanes of a quarter-warp hit eight different 16-byte bank groups whatever rows of Y they point at
+// (conflict-free); accumulator set j of a lane therefore holds chunk j ^ (l & 7) of its row.
+template <typename T, bool RL = false>
 __global__ void __launch_bounds__(BN_THREADS, 1) saso_binned_kernel(const __grid_constant__ CUtensorMap tmY,
                                                                     const BinnedArgs<T> a) {
     constexpr int CW = BN_W * 4 / (int) sizeof(T);     // columns of C per CTA
@@ -336,6 +342,42 @@ __global__ void __launch_bounds__(BN_THREADS, 1) saso_binned_kernel(const __grid
         const uint32_t stage = sbase + (uint32_t) b * BN_STAGE;
         tma::mbar_wait(bar_full + 8u * (uint32_t) b, par);
 
+        if constexpr (RL) {
+            uint32_t o0, o1, lo;
+            asm volatile("ld.shared.u16 %0, [%1];" : "=r"(o0) : "r"(stage + BN_OFF_OFFS + 2u * (uint32_t) tid));
+            asm volatile("ld.shared.u16 %0, [%1];" : "=r"(o1) : "r"(stage + BN_OFF_OFFS + 2u * (uint32_t) tid + 2u));
+            asm volatile("ld.shared.u16 %0, [%1];" : "=r"(lo) : "r"(stage + BN_OFF_OFFS));
+            const uint32_t len = o1 - o0;
+            const uint32_t pa = stage + BN_OFF_LIST - 4u * (lo & ~3u) + 4u * o0;
+            const uint32_t steps = __reduce_max_sync(0xffffffffu, len);
+            const uint32_t yb = stage + (uint32_t) l8 * 16;
+#pragma unroll 1
+            for (uint32_t t = 0; t < steps; ++t) {
+                if (t < len) {
+                    const uint32_t w = lds32(pa + 4u * t);
+                    const uint32_t e = yb + (w << 1);                 // row of Y (128-byte aligned) + this lane's rotation
+                    if constexpr (sizeof(T) == 4) {
+                        const float sg = word_sign(w);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            Vec16<T> y;
+                            y.load(e ^ (uint32_t) (j << 4));
+#pragma unroll
+                            for (int x = 0; x < VN; ++x) acc[j][x] = fmaf(y.v[x], sg, acc[j][x]);
+                        }
+                    } else {
+                        const double sg = word_sign_f64(w);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            Vec16<T> y;
+                            y.load(e ^ (uint32_t) (j << 4));
+#pragma unroll
+                            for (int x = 0; x < VN; ++x) acc[j][x] = fma(y.v[x], sg, acc[j][x]);
+                        }
+                    }
+                }
+            }
+        } else {
         // offsets of this group's 8 rows (relative to the chunk's list), 16-byte aligned in shared memory
         const uint32_t oaddr = stage + BN_OFF_OFFS + (uint32_t) gi * (BN_RPG * 2);
         uint32_t o01, o23, o45, o67;
@@ -377,6 +419,7 @@ __global__ void __launch_bounds__(BN_THREADS, 1) saso_binned_kernel(const __grid
                 p = pn;
             }
         }
+        }   // !RL
         // release the stage; the last warp to leave re-arms it with chunk c + 2G
         __syncwarp();
         if (lane == 0) {
@@ -390,10 +433,11 @@ __global__ void __launch_bounds__(BN_THREADS, 1) saso_binned_kernel(const __grid
     }
 
     // ---- add the tile into C (beta was applied beforehand; G CTAs share the tile) ----
-    const int64_t col = (int64_t) col0 + l8 * VN;
 #pragma unroll
     for (int q = 0; q < BN_RPG; ++q) {
-        const int64_t row = row0 + (int64_t) gi * BN_RPG + q;
+        // group form: lane = 16 bytes of rows 8 gi .. 8 gi + 7; row-per-lane form: accumulator set q = chunk q ^ l8 of row tid
+        const int64_t col = (int64_t) col0 + (RL ? (q ^ l8) : l8) * VN;
+        const int64_t row = RL ? row0 + tid : row0 + (int64_t) gi * BN_RPG + q;
         if (row >= a.P || col >= a.Q) continue;
         T* cp = a.C + row * a.crs + col;
         if constexpr (sizeof(T) == 4) {
@@ -455,7 +499,8 @@ int launch_saso_binned(const SasoProblem<T>& p, cudaStream_t st) {
     {
         static DevOnce attr_done;
         if (attr_done.need()) {
-            if (cudaFuncSetAttribute(saso_binned_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, BN_SMEM) != cudaSuccess) {
+            if (cudaFuncSetAttribute(saso_binned_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BN_SMEM) != cudaSuccess ||
+                cudaFuncSetAttribute(saso_binned_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BN_SMEM) != cudaSuccess) {
                 cudaGetLastError();
                 return -1;
             }
@@ -529,7 +574,9 @@ int launch_saso_binned(const SasoProblem<T>& p, cudaStream_t st) {
         a.C = p.C; a.crs = p.crs;
         a.c_vec4 = ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0 && ((p.crs * (int64_t) sizeof(T)) & 15) == 0) ? 1 : 0;
         dim3 grid((unsigned) ns, (unsigned) np, (unsigned) G);
-        saso_binned_kernel<T><<<grid, BN_THREADS, BN_SMEM, st>>>(tm, a);
+        // saso_rows: 1 = a lane owns a whole row of the tile (RL), 0 = an 8-lane group owns 8 rows
+        if (get_option("saso_rows") != 0) saso_binned_kernel<T, true><<<grid, BN_THREADS, BN_SMEM, st>>>(tm, a);
+        else saso_binned_kernel<T, false><<<grid, BN_THREADS, BN_SMEM, st>>>(tm, a);
         count_launch();
         count_owner_launch();
         RB_CUDA(cudaGetLastError());

@@ -609,8 +609,10 @@ def test_saso_owner_kernel_vs_oracle_and_vs_atomic_kernel(gpu, port):
             rb.set_option("saso_path", path)
             # vec_nnz = 2, 4, 8, 16: the binning pass regenerates a column per THREAD (saso_bin_path 0, default) or
             # per lane group (1, the only form for other vec_nnz); both are run
-            for binp, opS in [(bp, o) for bp in ((0, 1) if vn in (2, 4, 8, 16) else (0,)) for o in "NT"]:
+            # saso_rows: 1 (default) a lane of the apply kernel owns a whole row of the tile, 0 an 8-lane group owns 8 rows
+            for binp, rows_mode, opS in [(bp, rm, o) for bp in ((0, 1) if vn in (2, 4, 8, 16) else (0,)) for rm in (1, 0) for o in "NT"]:
                 rb.set_option("saso_bin_path", binp)
+                rb.set_option("saso_rows", rows_mode)
                 Dr, Dc = (d + ro + 3, m + co + 6) if opS == "N" else (m + ro + 6, d + co + 3)
                 A, lda = _mk(rng, m, n, "R", 4 - n % 4 if n % 4 else 0, dt)      # lda % 4 == 0: TMA-addressable
                 B0, ldb = _mk(rng, d, n, "R", 1, dt)
@@ -647,6 +649,7 @@ def test_saso_owner_kernel_vs_oracle_and_vs_atomic_kernel(gpu, port):
     finally:
         rb.set_option("saso_path", 0)
         rb.set_option("saso_bin_path", 0)
+        rb.set_option("saso_rows", 1)
 
 
 def test_saso_apply_full_size_exact_on_all_ones(gpu):

@@ -663,7 +663,8 @@ def test_saso_binned_kernel_double_vs_oracle(gpu, port):
         before = rb.counter("saso_owner_launches")
         for (d, n, m, vn, ro, co) in ((45, 29, 2111, 3, 2, 5), (1500, 34, 3000, 8, 0, 0), (1100, 50, 1537, 17, 7, 3),
                                       (300, 36, 900, 32, 0, 1), (64, 16, 5000, 1, 1, 0), (2048, 20, 777, 5, 0, 0)):
-            for opS in "NT":
+            for rows_mode, opS in [(rm, o) for rm in (1, 0) for o in "NT"]:      # lane per row (default) / 8-lane groups
+                rb.set_option("saso_rows", rows_mode)
                 Dr, Dc = (d + ro + 3, m + co + 6) if opS == "N" else (m + ro + 6, d + co + 3)
                 lda = n + (n % 2)                                # 16-byte aligned rows for TMA
                 A = rng.standard_normal(m * lda)
@@ -689,3 +690,4 @@ def test_saso_binned_kernel_double_vs_oracle(gpu, port):
         assert float(torch.linalg.norm(Bo - want) / torch.linalg.norm(want)) < 1e-12
     finally:
         rb.set_option("saso_path", 0)
+        rb.set_option("saso_rows", 1)
