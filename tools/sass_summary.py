@@ -38,8 +38,9 @@ def main():
     lines = [__doc__.strip(), "", f"library: randblas_b200/librandblas_b200.so ({os.path.getsize(LIB)} bytes), {len(kernels)} kernels", ""]
     tot = collections.Counter()
     for (mangled, c), name in zip(kernels.items(), names):
-        short = re.sub(r"\(.*", "", name)
-        short = short.replace("void rb::", "").replace("(anonymous namespace)::", "")
+        short = name.replace("(anonymous namespace)::", "")          # before the argument list is cut at the first "("
+        short = re.sub(r"\(.*", "", short)
+        short = short.replace("void rb::", "")
         hits = "  ".join(f"{k}={c[k]}" for k in KEYS if c[k])
         lines.append(f"{short[:110]:110s} total={c['_total']:6d}  {hits}")
         tot.update(c)
