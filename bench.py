@@ -91,8 +91,79 @@ class ClockSampler:
         self.dev = dev_index
         self.proc = None
         self.lines = []
+        self.nvml = None
+
+    # NVML in-process (a polling thread, first sample taken before start() returns): nvidia-smi needs 0.2-1 s to deliver its
+    # first line, longer than the timed region of the short configurations ("no samples" on an 8-GPU box)
+    def _start_nvml(self):
+        import pynvml
+        pynvml.nvmlInit()
+        h = None
+        try:                                   # the CUDA device's own UUID: immune to device-order differences
+            import torch
+            uuid = "GPU-" + str(torch.cuda.get_device_properties(self.dev).uuid)
+            h = pynvml.nvmlDeviceGetHandleByUUID(uuid)
+        except Exception:
+            h = None
+        if h is None:
+            h = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index())
+        self.nvml = (pynvml, h)
+        self.samples = []
+        self._stop = threading.Event()
+        self._sample()
+        self.t = threading.Thread(target=self._poll, daemon=True)
+        self.t.start()
+
+    def _physical_index(self):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            ids = [x.strip() for x in vis.split(",") if x.strip()]
+            if self.dev < len(ids) and ids[self.dev].isdigit():
+                return int(ids[self.dev])
+        return self.dev
+
+    def _sample(self):
+        nv, h = self.nvml
+        try:
+            sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+            mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            pw = nv.nvmlDeviceGetPowerUsage(h) / 1000.0
+            rs = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+            self.samples.append((sm, mx, pw, rs))
+        except Exception:
+            pass
+
+    def _poll(self):
+        while not self._stop.wait(0.02):
+            self._sample()
+
+    def _stop_nvml(self):
+        nv, h = self.nvml
+        self._stop.set()
+        self.t.join(timeout=1)
+        self._sample()
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        names = (("hw_slowdown", "nvmlClocksEventReasonHwSlowdown", "nvmlClocksThrottleReasonHwSlowdown"),
+                 ("hw_thermal_slowdown", "nvmlClocksEventReasonHwThermalSlowdown", "nvmlClocksThrottleReasonHwThermalSlowdown"),
+                 ("sw_thermal_slowdown", "nvmlClocksEventReasonSwThermalSlowdown", "nvmlClocksThrottleReasonSwThermalSlowdown"),
+                 ("sw_power_cap", "nvmlClocksEventReasonSwPowerCap", "nvmlClocksThrottleReasonSwPowerCap"))
+        reasons = set()
+        for _, _, _, rs in self.samples:
+            for name, a, b in names:
+                bit = getattr(nv, a, None) or getattr(nv, b, 0)
+                if bit and (rs & bit):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median([x[0] for x in self.samples])), "sm_max_mhz": float(max(x[1] for x in self.samples)),
+                "reasons": sorted(reasons), "power_w_max": float(max(x[2] for x in self.samples)), "samples": len(self.samples),
+                "source": "nvml"}
 
     def start(self):
+        try:
+            self._start_nvml()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-lms", "100", "-i", str(self.dev)], stdout=subprocess.PIPE,
@@ -107,6 +178,8 @@ class ClockSampler:
             self.lines.append(line.strip())
 
     def stop(self):
+        if self.nvml is not None:
+            return self._stop_nvml()
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
