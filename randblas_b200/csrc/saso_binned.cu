@@ -12,13 +12,16 @@
 //      This is the only form of S that ever exists (4 B + ~6/vec_nnz B per nonzero instead of the 20 B of the
 //      reference's COO triplets), and it is built once (a first design re-sorted every chunk in each of the
 //      ns x np CTAs that needed it: 9.9 ms at the C4 shape instead of 5.5).
-//   2. saso_binned_kernel: a CTA owns a 1024 x 32 tile of C in REGISTERS for the whole kernel (every 8-lane group
-//      owns 8 rows x 32 columns, 4 columns per lane) and walks over its share of the chunks. A two-stage
+//   2. saso_binned_kernel: a CTA owns a 1024 x 32 tile of C in REGISTERS for the whole kernel and walks over its share of
+//      the chunks. Default (RL, "saso_rows" = 1): thread t owns row t of the tile, all 32 columns, and walks that row's
+//      list -- a warp walks 32 lists in lockstep, 8 conflict-free LDS.128 and 32 FMAs per lane and step. First form
+//      ("saso_rows" = 0): every 8-lane group owns 8 rows x 32 columns, 4 columns per lane, one data-dependent loop per row. A two-stage
 //      TMA pipeline brings in, per chunk, the 32 columns it needs of the Kc rows of Y (2D tensor map, 128-byte
 //      rows), the part of the sorted list that targets its rows and the matching offsets (bulk copies). Warps
 //      run decoupled: full[] mbarriers signal arrival, the last warp to finish a stage (elected through a
 //      shared-memory counter, ordered by an empty[] mbarrier) re-arms it with the next chunk. No __syncthreads
-//      in the loop, no atomics on C, one conflict-free 128-byte shared-memory read per (entry, group).
+//      in the loop, no atomics on C, conflict-free 16-byte shared-memory reads (RL: lane l reads chunk j ^ (l & 7) of
+//      its entry's row in sub-step j; groups: one 128-byte row per (entry, group)).
 //
 // Roofline: HBM, bytes of Y (the data matrix A) read once. The inner loop itself is bound by shared-memory read
 // bandwidth and issue slots: every element of A is added into vec_nnz accumulators, i.e. vec_nnz * 4 B of
