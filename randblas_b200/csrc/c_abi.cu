@@ -25,6 +25,7 @@ static std::atomic<int64_t> g_tc_halves{1};      // generator warps split into t
 static std::atomic<int64_t> g_tc_materialise{1};  // Gaussian float operators with >= 3 column tiles: generate each K panel once, then the XMAT kernel
 static std::atomic<int64_t> g_saso_bin_path{0};    // binning pass of the SASO apply: 0 thread per column where possible, 1 lane per entry
 static std::atomic<int64_t> g_saso_rows{1};        // SASO apply: 1 (default) a lane owns a whole row of the tile, 0 an 8-lane group owns 8 rows
+static std::atomic<int64_t> g_fill_unroll{1};      // Uniform float fill of long vectors: 1 = 16 Philox blocks per thread and tile, 0 = 4
 static std::atomic<int64_t> g_tc_xmn{1};             // row-contiguous MATERIALISED operators (filled Axis::Short): 1 tensor cores / DMMA, 0 generic kernel
 static std::atomic<int64_t> g_tc_ymn{0};             // float tensor-core kernel, Q-contiguous data: 0 MN-major operand, 1 transposing path
 static std::atomic<int64_t> g_dmma_materialise{1};  // double Gaussian operators: panel-materialise + XMAT DMMA kernel
@@ -92,6 +93,7 @@ int64_t get_option(const char* name) {
     if (!std::strcmp(name, "tc_pair")) return g_tc_pair.load();
     if (!std::strcmp(name, "tc_ymn")) return g_tc_ymn.load();
     if (!std::strcmp(name, "tc_xmn")) return g_tc_xmn.load();
+    if (!std::strcmp(name, "fill_unroll")) return g_fill_unroll.load();
     if (!std::strcmp(name, "saso_rows")) return g_saso_rows.load();
     if (!std::strcmp(name, "saso_bin_path")) return g_saso_bin_path.load();
     if (!std::strcmp(name, "dmma_materialise")) return g_dmma_materialise.load();
@@ -1130,6 +1132,7 @@ int rb_set_option(const char* name, int64_t value) {
     if (!std::strcmp(name, "tc_pair")) { g_tc_pair = value; return 0; }
     if (!std::strcmp(name, "tc_ymn")) { g_tc_ymn = value; return 0; }
     if (!std::strcmp(name, "tc_xmn")) { g_tc_xmn = value; return 0; }
+    if (!std::strcmp(name, "fill_unroll")) { g_fill_unroll = value; return 0; }
     if (!std::strcmp(name, "saso_rows")) { g_saso_rows = value; return 0; }
     if (!std::strcmp(name, "saso_bin_path")) { g_saso_bin_path = value; return 0; }
     if (!std::strcmp(name, "dmma_materialise")) { g_dmma_materialise = value; return 0; }

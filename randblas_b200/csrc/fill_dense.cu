@@ -225,7 +225,13 @@ int launch_fill_dense(const DenseGen& g, char family, int64_t v0, int64_t nv, in
     // Tiled fast path. Gaussian: 8 blocks per thread and tile, 5 CTAs (10 warps per scheduler, 48 registers) -- the
     // Box-Muller chains want both the instruction-level and the thread-level parallelism (measured on C2: 561 vs 518
     // Gsamples/s for 4 blocks / 4 CTAs; tools/exp_fill_variants.py). Uniform: 4 blocks, 4 CTAs (already at the HBM roofline).
-    const int unroll = gauss_ ? 8 : FILL_UNROLL;
+    // Uniform float, long vectors: 16 blocks per thread and tile, 3 CTAs per SM. With 16 bytes written per Philox block this
+    // instantiation is bound by instructions, not by HBM, and the per-tile set-up (128-bit counter base, tile index
+    // arithmetic, interior test: ~87 instructions) is a quarter of the work at 4 blocks of 61 instructions. Measured
+    // (2048 x 1e6 window, tools/exp_fill_unroll.py): 4 blocks / 4 CTAs 1157 Gsamples/s, 8 / 4 1289, 8 / 5 1282, 16 / 4 1346,
+    // 16 / 3 1367 = 5.47 TB/s = 0.84 of measured HBM; bit-identical. "fill_unroll" = 0 restores 4 blocks.
+    const bool u16 = !gauss_ && sizeof(T) == 4 && a.nblk >= 2 * 256 * 16 && get_option("fill_unroll") != 0;
+    const int unroll = gauss_ ? 8 : (u16 ? 16 : FILL_UNROLL);
     if (!walk_v && su == 1 && a.nblk >= 2 * 256 * unroll) {
         FillTileArgs t;
         t.ctr = g.ctr; t.key = g.key; t.R = g.R; t.logtab = g.logtab; t.v0 = v0; t.nv = nv; t.u0 = u0; t.nu = nu;
@@ -238,6 +244,7 @@ int launch_fill_dense(const DenseGen& g, char family, int64_t v0, int64_t nv, in
         t.q_step = tgrid / t.tiles_per_vec;
         t.r_step = tgrid % t.tiles_per_vec;
         if (gauss_) fill_dense_tiled_kernel<T, true, 8, 5><<<(unsigned) tgrid, 256, 0, st>>>(t, dst);
+        else if (u16) fill_dense_tiled_kernel<T, false, 16, 3><<<(unsigned) tgrid, 256, 0, st>>>(t, dst);
         else fill_dense_tiled_kernel<T, false, FILL_UNROLL, 4><<<(unsigned) tgrid, 256, 0, st>>>(t, dst);
         count_launch();
         RB_CUDA(cudaGetLastError());
