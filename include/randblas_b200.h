@@ -341,6 +341,7 @@ int rb_lskges_mshard_all_f64(int ndev, const rb_comm_t* comms, char layout, char
  * "tc_cluster" (0 / 1 / 2: 2-CTA cluster mode of the float tensor-core kernel: never / where it pays / whenever
  * possible), "tc_splits", "tc_halves", "saso_path" (0 auto / 1 atomic kernel / 2 binned kernel), "saso_fill_path" (0 auto: thread per vector for
  * vec_nnz = 2, 4, 8, 16 / 1 warp per vector / 2 lane per entry), "saso_bin_path" (binning pass of the apply: 0 auto / 1 lane per entry),
+ * "fill_rep" (Gaussian fill_dense of long vectors: 1 = tiles of four passes of 8 Philox blocks per thread, the default / 0 = one pass),
  * "fill_unroll" (Uniform float fill_dense of long vectors: 1 = 16 Philox blocks per thread and tile, the default / 0 = 4),
  * "saso_rows" (apply kernel: 1 = a lane owns a whole row of the register tile, the default / 0 = an 8-lane group owns 8 rows),
  * "spdata_path" (1 = the deterministic column-owner kernel), "h2d_chunk_mb" (block size of the host-pointer sketch

@@ -26,6 +26,7 @@ static std::atomic<int64_t> g_tc_materialise{1};  // Gaussian float operators wi
 static std::atomic<int64_t> g_saso_bin_path{0};    // binning pass of the SASO apply: 0 thread per column where possible, 1 lane per entry
 static std::atomic<int64_t> g_saso_rows{1};        // SASO apply: 1 (default) a lane owns a whole row of the tile, 0 an 8-lane group owns 8 rows
 static std::atomic<int64_t> g_fill_unroll{1};      // Uniform float fill of long vectors: 1 = 16 Philox blocks per thread and tile, 0 = 4
+static std::atomic<int64_t> g_fill_rep{1};         // Gaussian fill of long vectors: 1 = tiles of 4 passes of 8 blocks per thread, 0 = one pass
 static std::atomic<int64_t> g_tc_xmn{1};             // row-contiguous MATERIALISED operators (filled Axis::Short): 1 tensor cores / DMMA, 0 generic kernel
 static std::atomic<int64_t> g_tc_ymn{0};             // float tensor-core kernel, Q-contiguous data: 0 MN-major operand, 1 transposing path
 static std::atomic<int64_t> g_dmma_materialise{1};  // double Gaussian operators: panel-materialise + XMAT DMMA kernel
@@ -93,6 +94,7 @@ int64_t get_option(const char* name) {
     if (!std::strcmp(name, "tc_pair")) return g_tc_pair.load();
     if (!std::strcmp(name, "tc_ymn")) return g_tc_ymn.load();
     if (!std::strcmp(name, "tc_xmn")) return g_tc_xmn.load();
+    if (!std::strcmp(name, "fill_rep")) return g_fill_rep.load();
     if (!std::strcmp(name, "fill_unroll")) return g_fill_unroll.load();
     if (!std::strcmp(name, "saso_rows")) return g_saso_rows.load();
     if (!std::strcmp(name, "saso_bin_path")) return g_saso_bin_path.load();
@@ -1132,6 +1134,7 @@ int rb_set_option(const char* name, int64_t value) {
     if (!std::strcmp(name, "tc_pair")) { g_tc_pair = value; return 0; }
     if (!std::strcmp(name, "tc_ymn")) { g_tc_ymn = value; return 0; }
     if (!std::strcmp(name, "tc_xmn")) { g_tc_xmn = value; return 0; }
+    if (!std::strcmp(name, "fill_rep")) { g_fill_rep = value; return 0; }
     if (!std::strcmp(name, "fill_unroll")) { g_fill_unroll = value; return 0; }
     if (!std::strcmp(name, "saso_rows")) { g_saso_rows = value; return 0; }
     if (!std::strcmp(name, "saso_bin_path")) { g_saso_bin_path = value; return 0; }

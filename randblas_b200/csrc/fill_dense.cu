@@ -105,7 +105,10 @@ struct FillTileArgs {
     const double2* logtab;
 };
 
-template <typename T, bool GAUSS, int FILL_UNROLL = 4, int MINB = 4>
+// REP: a tile is REP passes of FILL_UNROLL x 256 blocks. The per-tile set-up (128-bit counter base, 64-bit tile / pointer
+// arithmetic, interior test: ~87 instructions, every thread) is then shared by REP x FILL_UNROLL blocks without the register
+// pressure of a longer unrolled body.
+template <typename T, bool GAUSS, int FILL_UNROLL = 4, int MINB = 4, int REP = 1>
 __global__ void __launch_bounds__(256, MINB) fill_dense_tiled_kernel(const FillTileArgs a, T* __restrict__ dst) {
     __shared__ __align__(16) double2 logtab[GAUSS ? LOGF_TABLE_ENTRIES : 1];
     if constexpr (GAUSS) {
@@ -116,7 +119,7 @@ __global__ void __launch_bounds__(256, MINB) fill_dense_tiled_kernel(const FillT
     if (t >= a.total_tiles) return;
     int64_t vl = t / a.tiles_per_vec;
     int64_t ch = t - vl * a.tiles_per_vec;
-    constexpr int64_t TILE = 256 * FILL_UNROLL;
+    constexpr int64_t TILE = 256 * FILL_UNROLL * REP;
     for (; t < a.total_tiles; t += gridDim.x) {
         const int64_t b0 = ch * TILE;                                  // first block of the tile (window-relative)
         const Ctr128 base = ctr_add(a.ctr, (uint64_t) ((a.v0 + vl) * a.R + a.blk_first + b0));
@@ -128,17 +131,20 @@ __global__ void __launch_bounds__(256, MINB) fill_dense_tiled_kernel(const FillT
                               ((reinterpret_cast<uintptr_t>(p0) & (4 * sizeof(T) - 1)) == 0);
         // predicate-free path: whole interior tile whose block counters do not carry out of the low 64 bits
         if (interior && nb == TILE && base_lo + (uint64_t) TILE >= base_lo) {
+#pragma unroll 1
+            for (int rep = 0; rep < REP; ++rep) {
 #pragma unroll
-            for (int j = 0; j < FILL_UNROLL; ++j) {
-                const uint32_t off = j * 256 + threadIdx.x;
-                const uint64_t lo = base_lo + off;
-                const Ctr128 c{(uint32_t) lo, (uint32_t) (lo >> 32), base.c2, base.c3};
-                const float4 f = transform4<GAUSS>(philox4x32_10(c, a.key), logtab);
-                store4_vec<T>(p0 + 4 * off, finish_sample<T, GAUSS>(f.x), finish_sample<T, GAUSS>(f.y),
-                              finish_sample<T, GAUSS>(f.z), finish_sample<T, GAUSS>(f.w));
+                for (int j = 0; j < FILL_UNROLL; ++j) {
+                    const uint32_t off = (uint32_t) (rep * FILL_UNROLL + j) * 256u + threadIdx.x;
+                    const uint64_t lo = base_lo + off;
+                    const Ctr128 c{(uint32_t) lo, (uint32_t) (lo >> 32), base.c2, base.c3};
+                    const float4 f = transform4<GAUSS>(philox4x32_10(c, a.key), logtab);
+                    store4_vec<T>(p0 + 4 * off, finish_sample<T, GAUSS>(f.x), finish_sample<T, GAUSS>(f.y),
+                                  finish_sample<T, GAUSS>(f.z), finish_sample<T, GAUSS>(f.w));
+                }
             }
         } else {
-            for (int j = 0; j < FILL_UNROLL; ++j) {
+            for (int j = 0; j < FILL_UNROLL * REP; ++j) {
                 const int64_t off = j * 256 + threadIdx.x;
                 if (off >= nb) break;
                 const Ctr128 c = ctr_add(base, (uint64_t) off);
@@ -231,7 +237,13 @@ int launch_fill_dense(const DenseGen& g, char family, int64_t v0, int64_t nv, in
     // (2048 x 1e6 window, tools/exp_fill_unroll.py): 4 blocks / 4 CTAs 1157 Gsamples/s, 8 / 4 1289, 8 / 5 1282, 16 / 4 1346,
     // 16 / 3 1367 = 5.47 TB/s = 0.84 of measured HBM; bit-identical. "fill_unroll" = 0 restores 4 blocks.
     const bool u16 = !gauss_ && sizeof(T) == 4 && a.nblk >= 2 * 256 * 16 && get_option("fill_unroll") != 0;
-    const int unroll = gauss_ ? 8 : (u16 ? 16 : FILL_UNROLL);
+    // Gaussian, long vectors: tiles of REP = 4 passes of 8 blocks ("fill_rep" = 0: one pass, 2: two passes). Measured
+    // (tools/exp_fill_rep.py, 1024 x 1e6 window): 558 -> 570 Gsamples/s (two passes: 551, the tile count no longer divides
+    // the grid well); the full C2 fill 553 -> 563; bit-identical.
+    const int64_t ropt = get_option("fill_rep");
+    const bool rep4 = gauss_ && a.nblk >= 2 * 256 * 8 * 4 && ropt == 1;
+    const bool rep2 = gauss_ && a.nblk >= 2 * 256 * 8 * 2 && ropt == 2;
+    const int unroll = gauss_ ? (rep4 ? 32 : rep2 ? 16 : 8) : (u16 ? 16 : FILL_UNROLL);       // blocks per thread and tile
     if (!walk_v && su == 1 && a.nblk >= 2 * 256 * unroll) {
         FillTileArgs t;
         t.ctr = g.ctr; t.key = g.key; t.R = g.R; t.logtab = g.logtab; t.v0 = v0; t.nv = nv; t.u0 = u0; t.nu = nu;
@@ -243,7 +255,9 @@ int launch_fill_dense(const DenseGen& g, char family, int64_t v0, int64_t nv, in
         if (tgrid > tcap) tgrid = tcap;
         t.q_step = tgrid / t.tiles_per_vec;
         t.r_step = tgrid % t.tiles_per_vec;
-        if (gauss_) fill_dense_tiled_kernel<T, true, 8, 5><<<(unsigned) tgrid, 256, 0, st>>>(t, dst);
+        if (rep4) fill_dense_tiled_kernel<T, true, 8, 5, 4><<<(unsigned) tgrid, 256, 0, st>>>(t, dst);
+        else if (rep2) fill_dense_tiled_kernel<T, true, 8, 5, 2><<<(unsigned) tgrid, 256, 0, st>>>(t, dst);
+        else if (gauss_) fill_dense_tiled_kernel<T, true, 8, 5><<<(unsigned) tgrid, 256, 0, st>>>(t, dst);
         else if (u16) fill_dense_tiled_kernel<T, false, 16, 3><<<(unsigned) tgrid, 256, 0, st>>>(t, dst);
         else fill_dense_tiled_kernel<T, false, FILL_UNROLL, 4><<<(unsigned) tgrid, 256, 0, st>>>(t, dst);
         count_launch();
