@@ -276,8 +276,10 @@ __device__ __forceinline__ double word_sign_f64(uint32_t p) {
 
 // RL ("row per lane"): thread t of the CTA owns ROW t of the 1024 x 32 tile -- all 128 bytes of it, as eight 16-byte
 // chunks -- instead of 16 bytes of eight rows. A warp then walks 32 lists in lockstep, one entry per lane and step:
-// per step 8 address XORs, 8 LDS.128 and 32 FMAs serve up to 32 entries (the group form: 12 instructions for up to 4
-// entries of 16 bytes... per lane), and the number of steps is the longest of the 32 lists. Lane l reads chunk j ^ (l & 7) in
+// per step 8 address XORs, 8 LDS.128 and 32 FMAs serve up to 32 entries of 128 bytes (the group form spends 12 instructions
+// per step on up to 4 entries, 16 bytes per lane), and the number of steps is the longest of the 32 lists (redux.sync.max).
+// What bounds it is the shared-memory port: a quarter-warp costs a wavefront per LDS.128 as soon as one of its eight lanes has
+// an entry at that step (lists are Poisson(2.75): 1.9 wavefronts issued per useful one). Lane l reads chunk j ^ (l & 7) in
 // sub-step j, so the eight lanes of a quarter-warp hit eight different 16-byte bank groups whatever rows of Y they point at
 // (conflict-free); accumulator set j of a lane therefore holds chunk j ^ (l & 7) of its row.
 template <typename T, bool RL = false>
