@@ -87,3 +87,19 @@ def test_sampling_utilities_argument_checks_and_state_arithmetic_without_gpu():
     rb.set_option("tc_cluster", rb.get_option("tc_cluster"))
     with pytest.raises(rb.RandBLASError):
         rb.set_option("no_such_option", 1)
+
+
+def test_kernel_selection_options_round_trip_without_gpu():
+    """The switches that choose among kernels computing the same result (include/randblas_b200.h, "tuning") exist in the
+    library with the documented defaults, can be set and read back, and an unknown name is rejected by the setter."""
+    import randblas_b200 as rb
+    defaults = {"dense_path": 0, "saso_path": 0, "saso_fill_path": 0, "saso_bin_path": 0, "saso_rows": 1, "tc_xmn": 1,
+                "tc_ymn": 0, "tc_pair": 1, "fill_rep": 1, "fill_unroll": 1, "spdata_path": 0}
+    for name, want in defaults.items():
+        assert rb.get_option(name) == want, (name, rb.get_option(name))
+        rb.set_option(name, 1 - want if want in (0, 1) else 0)
+        assert rb.get_option(name) == (1 - want if want in (0, 1) else 0), name
+        rb.set_option(name, want)
+        assert rb.get_option(name) == want
+    with pytest.raises(rb.RandBLASError):
+        rb.set_option("no_such_option", 1)
